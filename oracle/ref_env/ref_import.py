@@ -1,0 +1,98 @@
+"""Import the UNMODIFIED reference (Qiskit Terra 0.18, /root/reference) in this container.
+
+TEST INFRASTRUCTURE ONLY.  Used by tests/golden/make_golden.py (to generate the committed
+golden fixtures) and by the CPU-side adapter tests that are skipped when /root/reference is
+absent (it is absent on the GPU box).  Nothing in the product package imports this file.
+
+The reference needs a few third-party modules that are not installed here and cannot be
+installed (no network): retworkx, ply, fastjsonschema, python-constraint, plus three Cython
+extensions that are not built in the read-only tree.  None of them is on the BasicAer
+arithmetic path (qiskit/providers/basicaer/qasm_simulator.py:145-161 is numpy only), so
+they are replaced by inert stand-ins registered in ``sys.modules`` *before* ``import qiskit``.
+The reference sources are read where they lie; nothing is copied or written.
+"""
+import importlib
+import os
+import sys
+import types
+
+REFERENCE_ROOT = os.environ.get("QISKIT_REFERENCE_ROOT", "/root/reference")
+
+
+def reference_available():
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "qiskit", "providers", "basicaer"))
+
+
+class _Missing:
+    """Attribute bag whose members raise only when they are *used*."""
+
+    def __init__(self, name):
+        self._name = name
+
+    def __call__(self, *a, **k):
+        raise ImportError("stub for %s: not available in this environment" % self._name)
+
+    def __getattr__(self, item):
+        if item.startswith("__"):
+            raise AttributeError(item)
+        return _Missing(self._name + "." + item)
+
+
+def _stub_module(name, **attrs):
+    mod = types.ModuleType(name)
+    mod.__dict__.update(attrs)
+
+    def _getattr(item, _name=name):
+        if item.startswith("__"):
+            raise AttributeError(item)
+        # classes are used as base classes / in isinstance checks at import time
+        return type(item, (), {"__init__": lambda self, *a, **k: (_ for _ in ()).throw(
+            ImportError("stub for %s.%s" % (_name, item)))})
+
+    mod.__getattr__ = _getattr
+    sys.modules[name] = mod
+    return mod
+
+
+def _install_stubs():
+    import numpy as np
+
+    if not hasattr(np, "product"):  # removed in numpy 2; used by quantum_info (operators/random.py:53)
+        np.product = np.prod
+    if "retworkx" not in sys.modules:
+        rx = _stub_module("retworkx")
+        _stub_module("retworkx.visualization")
+        rx.visualization = sys.modules["retworkx.visualization"]
+    if "ply" not in sys.modules:
+        ply = _stub_module("ply")
+        ply.lex = _stub_module("ply.lex")
+        ply.yacc = _stub_module("ply.yacc")
+    if "fastjsonschema" not in sys.modules:
+        fj = _stub_module("fastjsonschema", compile=lambda schema, *a, **k: (lambda data: data))
+        exc = _stub_module("fastjsonschema.exceptions", JsonSchemaException=type(
+            "JsonSchemaException", (Exception,), {}))
+        fj.exceptions = exc
+        fj.JsonSchemaException = exc.JsonSchemaException
+    if "constraint" not in sys.modules:
+        _stub_module("constraint")
+    # Cython extensions (not built in the read-only tree, none on the BasicAer path)
+    for name in (
+        "qiskit.quantum_info.states.cython.exp_value",
+        "qiskit.transpiler.passes.routing.cython.stochastic_swap.utils",
+        "qiskit.transpiler.passes.routing.cython.stochastic_swap.swap_trial",
+    ):
+        if name not in sys.modules:
+            _stub_module(name)
+
+
+def import_reference():
+    """Return the reference ``qiskit`` package, imported from REFERENCE_ROOT."""
+    if not reference_available():
+        raise ImportError("reference tree not found at %s" % REFERENCE_ROOT)
+    sys.dont_write_bytecode = True
+    _install_stubs()
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    # namespace-ish parent for the un-__init__'d cython dir
+    qiskit = importlib.import_module("qiskit")
+    return qiskit
