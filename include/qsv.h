@@ -1,0 +1,158 @@
+/*
+ * qsv.h -- C-ABI of libqsv, the B200 (sm_100a) statevector engine.
+ *
+ * This is the drop-in boundary for the one data-parallel hot path of Qiskit Terra 0.18's BasicAer
+ * simulators.  The reference has NO native interface on this path: every entry point below replaces
+ * a numpy call made from Python in
+ *     qiskit/providers/basicaer/qasm_simulator.py      (QasmSimulatorPy / StatevectorSimulatorPy)
+ *     qiskit/providers/basicaer/unitary_simulator.py   (UnitarySimulatorPy)
+ * and is what a ctypes binding inside those files would call.  Each prototype
+ * cites the reference lines it stands in for.
+ *
+ * Conventions
+ *   - A state is 2^n complex128 amplitudes in device memory, interleaved (re, im) float64, i.e.
+ *     numpy complex128 layout.  Qubit q is bit q of the flat amplitude index (the C-order flattening
+ *     of the reference's rank-n tensor whose axis n-1-q is qubit q; basicaertools.py:132-180).
+ *   - Matrices are row-major, interleaved (re, im) float64; for a k-qubit gate on qubits[0..k-1],
+ *     qubits[0] is the LEAST significant bit of the row/column index (qasm_simulator.py:145-161).
+ *   - Plain pointers and sizes only.  `sv` / `probs` / `ws` are DEVICE pointers owned by the caller;
+ *     `host_*` are HOST pointers owned by the caller.  `stream` is a cudaStream_t passed as void*
+ *     (NULL = default stream).  The library keeps no per-state handle and allocates no device memory.
+ *   - Every function returns 0 on success, a negative QSV_E* code for argument errors, or a positive
+ *     cudaError_t.  qsv_last_error() returns a thread-local message for the last failure.
+ *   - One host thread per state at a time (the reference backends are not re-entrant either;
+ *     qasm_simulator.py:118-131 keeps per-run state on the instance).
+ */
+#ifndef QSV_H
+#define QSV_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QSV_VERSION 100
+
+#define QSV_EINVAL (-1)   /* bad argument */
+#define QSV_ERANGE (-2)   /* size outside what the kernels support */
+#define QSV_ENORM (-3)    /* probabilities do not sum to 1 (numpy choice() ValueError) */
+
+#define QSV_MAX_TILE_QUBITS 13 /* 2^13 amplitudes * 16 B = 128 KiB of shared memory */
+#define QSV_MAX_PASS_GATES 48
+#define QSV_MAX_DENSE_K 12
+
+/* Gate kinds inside a fused pass. */
+enum {
+  QSV_GATE_DENSE1 = 1, /* 2x2 dense on q0: m = 4 complex, row-major                    */
+  QSV_GATE_DENSE2 = 2, /* 4x4 dense on (q0,q1), q0 = LSB of the index: m = 16 complex  */
+  QSV_GATE_DIAG1 = 3,  /* diag(m[0], m[1]) on q0 (u1, rz, measure collapse)            */
+  QSV_GATE_DIAG2 = 4,  /* diag(m[0..3]) on (q0,q1)                                     */
+  QSV_GATE_CX = 5      /* q0 = control, q1 = target (basicaertools.py:70-72)           */
+};
+
+typedef struct qsv_gate {
+  int32_t kind;
+  int32_t q0;
+  int32_t q1;
+  int32_t reserved;
+  double m[32]; /* interleaved re,im */
+} qsv_gate_t;
+
+int qsv_version(void);
+const char* qsv_last_error(void);
+
+/* psi = e^{i phase} |0...0>.  Replaces _initialize_statevector (qasm_simulator.py:319-328) fused with
+ * the global-phase multiply (qasm_simulator.py:522).  Writes 16*2^n bytes. */
+int qsv_init_basis0(double* sv, int n_qubits, double phase_re, double phase_im, void* stream);
+
+/* U = e^{i phase} * identity as a 2n-"qubit" vector, flat index row*2^n + col.  Replaces
+ * _initialize_unitary (unitary_simulator.py:190-199). */
+int qsv_init_identity(double* sv, int n_qubits, double phase_re, double phase_im, void* stream);
+
+/* psi <- host amplitudes (initial_statevector option, qasm_simulator.py:299-311,326) times
+ * (phase_re + i phase_im).  n_amps must be 2^n. */
+int qsv_upload(double* sv, int n_qubits, const double* host_amps, size_t n_amps, double phase_re,
+               double phase_im, void* stream);
+
+/* psi *= (re + i im), elementwise. */
+int qsv_scale(double* sv, int n_qubits, double re, double im, void* stream);
+
+/* One cache-blocked pass: every CTA stages the 2^n_tile amplitudes spanned by `tile_qubits` in shared
+ * memory (one HBM read), applies `gates` in order there, and writes the tile back (one HBM write).
+ * All gate qubits must be in tile_qubits; n_tile <= min(n_qubits, QSV_MAX_TILE_QUBITS).  For full
+ * memory coalescing tile_qubits should contain qubits 0,1,2 (128-byte runs).  Replaces a RUN of
+ * consecutive _add_unitary calls (qasm_simulator.py:145-161, loop :526-559), each of which is one
+ * np.einsum pass over the whole vector in the reference. */
+int qsv_apply_pass(double* sv, int n_qubits, const int32_t* tile_qubits, int n_tile,
+                   const qsv_gate_t* gates, int n_gates, void* stream);
+
+/* psi <- (G on qubits) psi for a dense k-qubit matrix, k >= 1.  Replaces one _add_unitary call
+ * (qasm_simulator.py:145-161; `unitary` instruction :543-546).  k <= 2 goes through qsv_apply_pass;
+ * 3 <= k <= QSV_MAX_DENSE_K uses the staged dense kernel, which needs `dev_mat_scratch`, a device
+ * buffer of at least 2*4^k doubles (the matrix is copied there). */
+int qsv_apply_matrix(double* sv, int n_qubits, const int32_t* qubits, int k, const double* host_matrix,
+                     double* dev_mat_scratch, void* stream);
+
+/* (p0, p1) of one qubit: p_b = sum over amplitudes with bit `qubit` == b of |psi|^2.  Replaces the
+ * np.sum(np.abs(psi)**2, axis=...) in _get_measure_outcome (qasm_simulator.py:173-176).  `ws` needs
+ * qsv_reduce_workspace_bytes() bytes.  Synchronises the stream; result in host_out[2]. */
+size_t qsv_reduce_workspace_bytes(void);
+int qsv_prob_qubit(const double* sv, int n_qubits, int qubit, void* ws, double* host_out, void* stream);
+
+/* Projective collapse + renormalisation: the diag / reset update matrices that _add_qasm_measure
+ * (qasm_simulator.py:247-253) and _add_qasm_reset (:265-273) pass to _add_unitary.
+ * is_reset = 0: amplitudes with bit != outcome are zeroed, the rest scaled by 1/sqrt(prob).
+ * is_reset = 1: as above, and for outcome 1 the |1> half is moved to |0>. */
+int qsv_collapse(double* sv, int n_qubits, int qubit, int outcome, double prob, int is_reset,
+                 void* stream);
+
+/* Marginal probabilities of m measured qubits: probs[s] = sum |psi_i|^2 over all i whose bit
+ * measured_sorted[pos] equals bit pos of s.  Replaces np.sum(np.abs(psi)**2, axis=...) in
+ * _add_sample_measure (qasm_simulator.py:202-209).  dev_probs holds 2^m doubles. */
+size_t qsv_marginal_workspace_bytes(int n_qubits, int m);
+int qsv_marginal(const double* sv, int n_qubits, const int32_t* measured_sorted, int m,
+                 double* dev_probs, void* ws, void* stream);
+
+/* Draw `shots` samples: the RandomState.choice(range(2^m), shots, p) of _add_sample_measure
+ * (qasm_simulator.py:213), i.e. cdf = cumsum(p); cdf /= cdf[-1]; idx = searchsorted(cdf, u, 'right')
+ * for the caller-supplied uniforms u (RandomState.random_sample(shots)).
+ *   src            : from_amplitudes != 0 -> 2^log2_bins complex amplitudes, p_i = |psi_i|^2
+ *                    (all qubits measured); else 2^log2_bins doubles (a marginal from qsv_marginal).
+ *   exact_order    : != 0 -> the CDF is accumulated strictly left to right in float64, like
+ *                    numpy's cumsum, so samples equal the reference's bit for bit (serial, meant for
+ *                    log2_bins <= ~26); 0 -> blocked parallel scan (any size).
+ *   host_total     : receives cdf[-1] before normalisation (must be ~1).
+ * Returns QSV_ENORM if |total - 1| > sqrt(eps) as numpy's choice() does.  Synchronises the stream. */
+size_t qsv_sample_workspace_bytes(int log2_bins, int shots);
+int qsv_sample(const double* src, int from_amplitudes, int log2_bins, const double* host_uniforms,
+               int shots, int64_t* host_out_idx, int exact_order, void* ws, double* host_total,
+               void* stream);
+
+/* psi[abs(psi) < threshold] = 0 (qasm_simulator.py:330-334, unitary_simulator.py:201-207). */
+int qsv_chop(double* sv, int n_qubits, double threshold, void* stream);
+
+/* Device -> host copy of 2^n amplitudes (the ndarray returned in data["statevector"]). */
+int qsv_download(const double* sv, int n_qubits, double* host_amps, void* stream);
+
+/* ---- multi-GPU support (sv sharded by the high-order "global" qubits) -------------- */
+
+/* Pack / unpack the half of the local shard whose local bit `local_qubit` equals `bit_value` into a
+ * contiguous buffer of 2^(n_local-1) amplitudes, chunk [chunk_begin, chunk_begin+chunk_amps).  Used
+ * around the NCCL exchange that swaps a global qubit with a local one. */
+int qsv_pack_half(const double* sv, int n_local, int local_qubit, int bit_value, double* dev_buf,
+                  size_t chunk_begin, size_t chunk_amps, void* stream);
+int qsv_unpack_half(double* sv, int n_local, int local_qubit, int bit_value, const double* dev_buf,
+                    size_t chunk_begin, size_t chunk_amps, void* stream);
+
+/* Sum of |psi|^2 over the local shard (for distributed normalisation / sampling). */
+int qsv_norm2(const double* sv, int n_qubits, void* ws, double* host_out, void* stream);
+
+/* Number of kernels launched by this library in the calling process (bench.py's gpu_launches). */
+uint64_t qsv_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QSV_H */

@@ -1,0 +1,68 @@
+// Shared helpers for libqsv (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "qsv.h"
+
+namespace qsv {
+
+extern thread_local char g_err[512];
+extern unsigned long long g_launches;
+
+inline int fail(int code, const char* msg) {
+  snprintf(g_err, sizeof(g_err), "%s", msg);
+  return code;
+}
+
+#define QSV_CUDA(expr)                                                                       \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      snprintf(qsv::g_err, sizeof(qsv::g_err), "%s failed: %s (%s:%d)", #expr,               \
+               cudaGetErrorString(_e), __FILE__, __LINE__);                                  \
+      return (int)_e;                                                                        \
+    }                                                                                        \
+  } while (0)
+
+#define QSV_LAUNCHED()                                                                       \
+  do {                                                                                       \
+    __sync_fetch_and_add(&qsv::g_launches, 1ULL);                                            \
+    QSV_CUDA(cudaGetLastError());                                                            \
+  } while (0)
+
+constexpr int kThreads = 256;
+constexpr int kNumSMs = 148;  // B200
+
+typedef unsigned long long u64;
+
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+  return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+// acc += a * b (complex), 4 DFMA
+__device__ __forceinline__ void cfma(double2& acc, double2 a, double2 b) {
+  acc.x = fma(a.x, b.x, acc.x);
+  acc.x = fma(-a.y, b.y, acc.x);
+  acc.y = fma(a.x, b.y, acc.y);
+  acc.y = fma(a.y, b.x, acc.y);
+}
+
+// XOR swizzle of a tile-local amplitude index (16-byte slots).  Bank group = slot & 7; bit j of the
+// index contributes to bank bit (j mod 3), so any three index bits with distinct residues mod 3 are
+// conflict-free across the 8 lanes of a quarter warp (LDS.128 is served per quarter warp).
+__device__ __forceinline__ uint32_t swz(uint32_t li) {
+  uint32_t x = li >> 3;
+  x ^= x >> 3;
+  x ^= x >> 6;
+  return li ^ (x & 7u);
+}
+
+inline __host__ uint32_t swz_host(uint32_t li) {
+  uint32_t x = li >> 3;
+  x ^= x >> 3;
+  x ^= x >> 6;
+  return li ^ (x & 7u);
+}
+
+}  // namespace qsv

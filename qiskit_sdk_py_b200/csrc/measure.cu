@@ -1,0 +1,399 @@
+// Probabilities, marginals and shot sampling (K7, K9, K10, K13 of SURVEY 2.5) for sm_100a.
+//
+// Replaces, in /root/reference/qiskit/providers/basicaer/qasm_simulator.py:
+//   _get_measure_outcome  :163-182   np.sum(np.abs(psi)**2, axis=all but one)
+//   _add_sample_measure   :184-225   marginal + RandomState.choice == cumsum / normalise / searchsorted
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace qsv {
+
+constexpr int kReduceBlocks = kNumSMs * 8;   // fixed grid -> deterministic two-stage reduction
+constexpr int kChunkLog2 = 10;               // sampler chunk: 1024 bins
+constexpr int kChunk = 1 << kChunkLog2;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide sum of two values, result valid in thread 0; fixed order -> deterministic
+__device__ __forceinline__ void block_sum2(double& a, double& b) {
+  __shared__ double sa[kThreads / 32], sb[kThreads / 32];
+  a = warp_sum(a);
+  b = warp_sum(b);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) {
+    sa[wid] = a;
+    sb[wid] = b;
+  }
+  __syncthreads();
+  if (wid == 0) {
+    a = lane < kThreads / 32 ? sa[lane] : 0.0;
+    b = lane < kThreads / 32 ? sb[lane] : 0.0;
+    a = warp_sum(a);
+    b = warp_sum(b);
+  }
+  __syncthreads();
+}
+
+// stage 1: partial[2*blk + bit] = sum over this block's grid-stride slice of |psi|^2 with bit q == bit
+__global__ void __launch_bounds__(kThreads)
+prob_qubit_kernel(const double2* __restrict__ sv, u64 n_amps, int q, double* __restrict__ partial) {
+  double p0 = 0.0, p1 = 0.0;
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_amps; i += stride) {
+    const double2 a = sv[i];
+    const double p = fma(a.x, a.x, a.y * a.y);
+    if ((i >> q) & 1ull) p1 += p; else p0 += p;
+  }
+  block_sum2(p0, p1);
+  if (threadIdx.x == 0) {
+    partial[2 * blockIdx.x] = p0;
+    partial[2 * blockIdx.x + 1] = p1;
+  }
+}
+
+// stage 2: one block adds the partials in a fixed order
+__global__ void __launch_bounds__(kThreads)
+reduce_pairs_kernel(const double* __restrict__ partial, int nblocks, double* __restrict__ out) {
+  double p0 = 0.0, p1 = 0.0;
+  for (int i = threadIdx.x; i < nblocks; i += kThreads) {
+    p0 += partial[2 * i];
+    p1 += partial[2 * i + 1];
+  }
+  block_sum2(p0, p1);
+  if (threadIdx.x == 0) {
+    out[0] = p0;
+    out[1] = p1;
+  }
+}
+
+// ---- marginal over m measured qubits: grid = (parts, bins) ----
+struct MargDesc {
+  int32_t n, m, log2_parts, pad;
+  uint8_t mq[40];   // measured qubits ascending
+  uint8_t uq[40];   // unmeasured qubits ascending
+};
+
+__global__ void __launch_bounds__(kThreads)
+marginal_kernel(const double2* __restrict__ sv, const __grid_constant__ MargDesc d,
+                double* __restrict__ partial) {
+  const u64 bin = blockIdx.y + (u64)blockIdx.z * gridDim.y;
+  const u64 part = blockIdx.x;
+  const int nu = d.n - d.m;
+  u64 base = 0;
+  for (int j = 0; j < d.m; j++) base |= ((bin >> j) & 1ull) << d.mq[j];
+  const u64 per_part = (1ull << nu) >> d.log2_parts;
+  double acc = 0.0, dummy = 0.0;
+  for (u64 u = part * per_part + threadIdx.x; u < (part + 1) * per_part; u += kThreads) {
+    u64 off = 0;
+    for (int j = 0; j < nu; j++) off |= ((u >> j) & 1ull) << d.uq[j];
+    const double2 a = sv[base | off];
+    acc += fma(a.x, a.x, a.y * a.y);
+  }
+  block_sum2(acc, dummy);
+  if (threadIdx.x == 0) partial[(bin << d.log2_parts) + part] = acc;
+}
+
+__global__ void __launch_bounds__(kThreads)
+marginal_finish_kernel(const double* __restrict__ partial, u64 bins, int log2_parts, double* __restrict__ probs) {
+  const u64 bin = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (bin >= bins) return;
+  double acc = 0.0;
+  const u64 parts = 1ull << log2_parts;
+  for (u64 p = 0; p < parts; p++) acc += partial[(bin << log2_parts) + p];
+  probs[bin] = acc;
+}
+
+// ---- sampler ----
+template <bool kAmps>
+__device__ __forceinline__ double load_p(const void* src, u64 i) {
+  if (kAmps) {
+    const double2 a = reinterpret_cast<const double2*>(src)[i];
+    return fma(a.x, a.x, a.y * a.y);
+  }
+  return reinterpret_cast<const double*>(src)[i];
+}
+
+// Exact (numpy cumsum) order: ONE running float64 sum over all bins, left to right.  Warp 0 lane 0 is
+// the adder; the other warps stage the next chunk's probabilities in shared memory meanwhile.  Records
+// the running sum at the end of every chunk.
+template <bool kAmps>
+__global__ void __launch_bounds__(1024)
+cdf_sequential_kernel(const void* __restrict__ src, u64 bins, double* __restrict__ chunk_end) {
+  __shared__ double buf[2][kChunk];
+  const u64 nchunks = (bins + kChunk - 1) / kChunk;
+  const int tid = threadIdx.x;
+  double run = 0.0;
+  // prologue: stage chunk 0
+  for (int i = tid; i < kChunk; i += 1024) buf[0][i] = (u64)i < bins ? load_p<kAmps>(src, i) : 0.0;
+  __syncthreads();
+  for (u64 c = 0; c < nchunks; c++) {
+    const int cur = c & 1;
+    if (tid >= 32) {
+      const u64 nb = (c + 1) * kChunk;
+      if (c + 1 < nchunks)
+        for (int i = tid - 32; i < kChunk; i += 1024 - 32) buf[cur ^ 1][i] = nb + i < bins ? load_p<kAmps>(src, nb + i) : 0.0;
+    } else if (tid == 0) {
+      const u64 left = bins - c * kChunk;
+      const int cnt = left < (u64)kChunk ? (int)left : kChunk;
+      const double* p = buf[cur];
+#pragma unroll 8
+      for (int i = 0; i < cnt; i++) run += p[i];
+      chunk_end[c] = run;
+    }
+    __syncthreads();
+  }
+}
+
+// Blocked order: chunk sums (sequential inside a chunk, one thread per chunk slice is too slow, so a
+// fixed-shape tree per chunk), then an inclusive scan over the chunk sums.
+template <bool kAmps>
+__global__ void __launch_bounds__(kThreads)
+chunk_sum_kernel(const void* __restrict__ src, u64 bins, double* __restrict__ chunk_sum) {
+  const u64 c = blockIdx.x;
+  double acc = 0.0, dummy = 0.0;
+  for (int i = threadIdx.x; i < kChunk; i += kThreads) {
+    const u64 idx = c * kChunk + i;
+    if (idx < bins) acc += load_p<kAmps>(src, idx);
+  }
+  block_sum2(acc, dummy);
+  if (threadIdx.x == 0) chunk_sum[c] = acc;
+}
+
+// In-place inclusive scan of `n` doubles, hierarchical with one thread per 1024-element segment doing a
+// sequential scan (n <= 2^23 chunk sums at 33 qubits -> 2^13 segments -> one more level).
+__global__ void seg_scan_kernel(double* __restrict__ data, u64 n, double* __restrict__ seg_total) {
+  const u64 seg = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  const u64 begin = seg * 1024;
+  if (begin >= n) return;
+  const u64 end = begin + 1024 < n ? begin + 1024 : n;
+  double run = 0.0;
+  for (u64 i = begin; i < end; i++) {
+    run += data[i];
+    data[i] = run;
+  }
+  seg_total[seg] = run;
+}
+
+__global__ void serial_scan_kernel(double* __restrict__ data, u64 n) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    double run = 0.0;
+    for (u64 i = 0; i < n; i++) {
+      run += data[i];
+      data[i] = run;
+    }
+  }
+}
+
+__global__ void seg_add_kernel(double* __restrict__ data, u64 n, const double* __restrict__ seg_incl) {
+  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const u64 seg = i >> 10;
+  if (seg > 0) data[i] += seg_incl[seg - 1];
+}
+
+// One thread per shot: first bin with cdf[bin] / total > u  (searchsorted side='right').
+template <bool kAmps>
+__global__ void __launch_bounds__(kThreads)
+sample_kernel(const void* __restrict__ src, u64 bins, const double* __restrict__ chunk_end, u64 nchunks,
+              const double* __restrict__ uniforms, int shots, long long* __restrict__ out) {
+  const int sidx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (sidx >= shots) return;
+  const double total = chunk_end[nchunks - 1];
+  const double u = uniforms[sidx];
+  // first chunk whose end value exceeds u
+  u64 lo = 0, hi = nchunks;  // answer in [lo, hi]
+  while (lo < hi) {
+    const u64 mid = (lo + hi) >> 1;
+    if (chunk_end[mid] / total > u) hi = mid; else lo = mid + 1;
+  }
+  if (lo >= nchunks) {  // u >= 1 cannot happen for random_sample(); mirror searchsorted -> len
+    out[sidx] = (long long)bins;
+    return;
+  }
+  double run = lo > 0 ? chunk_end[lo - 1] : 0.0;
+  const u64 begin = lo * kChunk;
+  const u64 end = begin + kChunk < bins ? begin + kChunk : bins;
+  u64 ans = end - 1;
+  for (u64 i = begin; i < end; i++) {
+    run += load_p<kAmps>(src, i);
+    if (run / total > u) {
+      ans = i;
+      break;
+    }
+  }
+  out[sidx] = (long long)ans;
+}
+
+struct SampleWs {
+  double* chunk_end;   // nchunks
+  double* seg1;        // ceil(nchunks/1024)
+  double* uniforms;    // shots
+  long long* out;      // shots
+};
+
+static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static size_t sample_ws_layout(int log2_bins, int shots, void* ws, SampleWs* out) {
+  const u64 bins = 1ull << log2_bins;
+  const u64 nchunks = (bins + kChunk - 1) / kChunk;
+  const u64 nseg = (nchunks + 1023) / 1024;
+  size_t off = 0;
+  char* base = reinterpret_cast<char*>(ws);
+  if (out) out->chunk_end = reinterpret_cast<double*>(base + off);
+  off += align_up(nchunks * sizeof(double));
+  if (out) out->seg1 = reinterpret_cast<double*>(base + off);
+  off += align_up(nseg * sizeof(double));
+  if (out) out->uniforms = reinterpret_cast<double*>(base + off);
+  off += align_up((size_t)shots * sizeof(double));
+  if (out) out->out = reinterpret_cast<long long*>(base + off);
+  off += align_up((size_t)shots * sizeof(long long));
+  return off;
+}
+
+template <bool kAmps>
+static int sample_impl(const void* src, int log2_bins, const double* host_uniforms, int shots,
+                       int64_t* host_out, int exact, void* ws, double* host_total, cudaStream_t s) {
+  const u64 bins = 1ull << log2_bins;
+  const u64 nchunks = (bins + kChunk - 1) / kChunk;
+  SampleWs w;
+  sample_ws_layout(log2_bins, shots, ws, &w);
+  QSV_CUDA(cudaMemcpyAsync(w.uniforms, host_uniforms, (size_t)shots * sizeof(double), cudaMemcpyHostToDevice, s));
+  if (exact) {
+    cdf_sequential_kernel<kAmps><<<1, 1024, 0, s>>>(src, bins, w.chunk_end);
+    QSV_LAUNCHED();
+  } else {
+    chunk_sum_kernel<kAmps><<<(unsigned)nchunks, kThreads, 0, s>>>(src, bins, w.chunk_end);
+    QSV_LAUNCHED();
+    const u64 nseg = (nchunks + 1023) / 1024;
+    seg_scan_kernel<<<(unsigned)((nseg + 127) / 128), 128, 0, s>>>(w.chunk_end, nchunks, w.seg1);
+    QSV_LAUNCHED();
+    if (nseg > 1) {
+      serial_scan_kernel<<<1, 32, 0, s>>>(w.seg1, nseg);
+      QSV_LAUNCHED();
+      seg_add_kernel<<<(unsigned)((nchunks + 255) / 256), 256, 0, s>>>(w.chunk_end, nchunks, w.seg1);
+      QSV_LAUNCHED();
+    }
+  }
+  double total = 0.0;
+  QSV_CUDA(cudaMemcpyAsync(&total, w.chunk_end + (nchunks - 1), sizeof(double), cudaMemcpyDeviceToHost, s));
+  QSV_CUDA(cudaStreamSynchronize(s));
+  if (host_total) *host_total = total;
+  // numpy's choice(): "probabilities do not sum to 1" when |sum - 1| > sqrt(eps)
+  if (!(fabs(total - 1.0) <= 1.4901161193847656e-08)) return fail(QSV_ENORM, "probabilities do not sum to 1");
+  sample_kernel<kAmps><<<(shots + kThreads - 1) / kThreads, kThreads, 0, s>>>(src, bins, w.chunk_end, nchunks,
+                                                                              w.uniforms, shots, w.out);
+  QSV_LAUNCHED();
+  QSV_CUDA(cudaMemcpyAsync(host_out, w.out, (size_t)shots * sizeof(long long), cudaMemcpyDeviceToHost, s));
+  QSV_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+}  // namespace qsv
+
+using namespace qsv;
+
+extern "C" {
+
+size_t qsv_reduce_workspace_bytes(void) { return sizeof(double) * 2 * (kReduceBlocks + 1); }
+
+int qsv_prob_qubit(const double* sv, int n, int qubit, void* ws, double* host_out, void* stream) {
+  if (!sv || !ws || !host_out || n < 1 || n > 40 || qubit < 0 || qubit >= n)
+    return fail(QSV_EINVAL, "qsv_prob_qubit: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  const u64 n_amps = 1ull << n;
+  double* partial = reinterpret_cast<double*>(ws);
+  const int blocks = (int)std::max<u64>(1, std::min<u64>((n_amps + kThreads - 1) / kThreads, kReduceBlocks));
+  prob_qubit_kernel<<<blocks, kThreads, 0, s>>>(reinterpret_cast<const double2*>(sv), n_amps, qubit, partial);
+  QSV_LAUNCHED();
+  reduce_pairs_kernel<<<1, kThreads, 0, s>>>(partial, blocks, partial + 2 * kReduceBlocks);
+  QSV_LAUNCHED();
+  QSV_CUDA(cudaMemcpyAsync(host_out, partial + 2 * kReduceBlocks, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  QSV_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int qsv_norm2(const double* sv, int n, void* ws, double* host_out, void* stream) {
+  if (!sv || !ws || !host_out || n < 0 || n > 40) return fail(QSV_EINVAL, "qsv_norm2: bad arguments");
+  double p[2];
+  if (n == 0) {
+    double a[2];
+    QSV_CUDA(cudaMemcpyAsync(a, sv, 16, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    QSV_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    *host_out = a[0] * a[0] + a[1] * a[1];
+    return 0;
+  }
+  const int rc = qsv_prob_qubit(sv, n, 0, ws, p, stream);
+  if (rc) return rc;
+  *host_out = p[0] + p[1];
+  return 0;
+}
+
+static int marginal_log2_parts(int n, int m) {
+  // enough CTAs to fill the machine: bins * parts >= ~4 CTAs per SM, parts <= 2^(n-m) / 256
+  int lp = 0;
+  while (((1ull << m) << lp) < (u64)kNumSMs * 4 && (n - m - lp) > 10) lp++;
+  return lp;
+}
+
+size_t qsv_marginal_workspace_bytes(int n, int m) {
+  if (m < 0 || m > n) return 0;
+  return sizeof(double) * (((size_t)1 << m) << marginal_log2_parts(n, m));
+}
+
+int qsv_marginal(const double* sv, int n, const int32_t* measured_sorted, int m, double* dev_probs, void* ws,
+                 void* stream) {
+  if (!sv || !measured_sorted || !dev_probs || !ws || n < 1 || n > 40 || m < 0 || m > n)
+    return fail(QSV_EINVAL, "qsv_marginal: bad arguments");
+  MargDesc d;
+  memset(&d, 0, sizeof(d));
+  d.n = n;
+  d.m = m;
+  bool meas[64] = {false};
+  for (int j = 0; j < m; j++) {
+    const int q = measured_sorted[j];
+    if (q < 0 || q >= n || meas[q] || (j > 0 && q <= measured_sorted[j - 1]))
+      return fail(QSV_EINVAL, "qsv_marginal: measured qubits must be ascending and unique");
+    meas[q] = true;
+    d.mq[j] = (uint8_t)q;
+  }
+  int nu = 0;
+  for (int q = 0; q < n; q++)
+    if (!meas[q]) d.uq[nu++] = (uint8_t)q;
+  d.log2_parts = marginal_log2_parts(n, m);
+  const u64 bins = 1ull << m;
+  if (bins > (1ull << 31)) return fail(QSV_ERANGE, "qsv_marginal: too many bins");
+  const unsigned gy = (unsigned)std::min<u64>(bins, 32768), gz = (unsigned)(bins / gy);
+  dim3 grid(1u << d.log2_parts, gy, gz);
+  cudaStream_t s = (cudaStream_t)stream;
+  marginal_kernel<<<grid, kThreads, 0, s>>>(reinterpret_cast<const double2*>(sv), d, reinterpret_cast<double*>(ws));
+  QSV_LAUNCHED();
+  marginal_finish_kernel<<<(unsigned)((bins + 255) / 256), 256, 0, s>>>(reinterpret_cast<double*>(ws), bins,
+                                                                        d.log2_parts, dev_probs);
+  QSV_LAUNCHED();
+  return 0;
+}
+
+size_t qsv_sample_workspace_bytes(int log2_bins, int shots) {
+  if (log2_bins < 0 || log2_bins > 40 || shots < 0) return 0;
+  return sample_ws_layout(log2_bins, shots, nullptr, nullptr);
+}
+
+int qsv_sample(const double* src, int from_amplitudes, int log2_bins, const double* host_uniforms, int shots,
+               int64_t* host_out_idx, int exact_order, void* ws, double* host_total, void* stream) {
+  if (!src || !host_uniforms || !host_out_idx || !ws || log2_bins < 0 || log2_bins > 40 || shots < 1)
+    return fail(QSV_EINVAL, "qsv_sample: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (from_amplitudes)
+    return sample_impl<true>(src, log2_bins, host_uniforms, shots, host_out_idx, exact_order, ws, host_total, s);
+  return sample_impl<false>(src, log2_bins, host_uniforms, shots, host_out_idx, exact_order, ws, host_total, s);
+}
+
+}  // extern "C"

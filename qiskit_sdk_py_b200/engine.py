@@ -1,0 +1,232 @@
+"""Device-resident statevector: the qiskit-free engine that drives libqsv through ctypes.
+
+PyTorch is used only as plumbing: it owns the device allocation (one float64 tensor of 2*2^n
+entries = numpy complex128 layout) and the CUDA stream; every arithmetic operation on the state is
+a hand-written sm_100a kernel of libqsv (include/qsv.h).  No CPU fallback: constructing a
+``DeviceState`` without a CUDA device or without libqsv.so raises.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from .lower import GateOp
+from .planner import DEFAULT_TILE_QUBITS, plan_passes
+
+_p_int32 = ctypes.POINTER(ctypes.c_int32)
+
+
+def _int32_array(values):
+    arr = (ctypes.c_int32 * len(values))(*[int(v) for v in values])
+    return arr
+
+
+def _fill_gate(dst, op):
+    """GateOp -> qsv_gate_t."""
+    dst.kind = op.kind
+    dst.q0 = op.qubits[0]
+    dst.q1 = op.qubits[1] if len(op.qubits) > 1 else 0
+    dst.reserved = 0
+    if op.matrix is not None:
+        flat = np.ascontiguousarray(op.matrix, dtype=np.complex128).reshape(-1).view(np.float64)
+        ctypes.memmove(dst.m, flat.ctypes.data, flat.nbytes)
+
+
+class DeviceState:
+    """2^n complex128 amplitudes in HBM plus the small workspaces the kernels need."""
+
+    def __init__(self, n_qubits, device=None, tile_qubits=DEFAULT_TILE_QUBITS):
+        import torch
+
+        self._torch = torch
+        self.lib = _lib.load()  # raises QsvLibraryError if the CUDA library is not built
+        if not torch.cuda.is_available():
+            raise _lib.QsvLibraryError(
+                "no CUDA device available: this backend runs only on a GPU (no CPU fallback)")
+        self.n = int(n_qubits)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.tile_qubits = int(tile_qubits)
+        with torch.cuda.device(self.device):
+            self.state = torch.empty(2 << self.n, dtype=torch.float64, device=self.device)
+            self._reduce_ws = torch.empty(self.lib.qsv_reduce_workspace_bytes() // 8 + 8,
+                                          dtype=torch.float64, device=self.device)
+        self._mat_scratch = None
+        self._sample_ws = None
+        self._marg_ws = None
+        self._probs = None
+        self.passes_launched = 0
+        self.gates_applied = 0
+
+    # -- plumbing --------------------------------------------------------------------
+    @property
+    def ptr(self):
+        return ctypes.c_void_p(self.state.data_ptr())
+
+    @property
+    def stream(self):
+        return ctypes.c_void_p(self._torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _ctx(self):
+        return self._torch.cuda.device(self.device)
+
+    def synchronize(self):
+        self._torch.cuda.synchronize(self.device)
+
+    # -- initialisation --------------------------------------------------------------
+    def init_basis0(self, phase=1.0 + 0.0j):
+        with self._ctx():
+            _lib.check(self.lib.qsv_init_basis0(self.ptr, self.n, phase.real, phase.imag, self.stream),
+                       "qsv_init_basis0")
+
+    def init_identity(self, n_half, phase=1.0 + 0.0j):
+        assert 2 * n_half == self.n
+        with self._ctx():
+            _lib.check(self.lib.qsv_init_identity(self.ptr, n_half, phase.real, phase.imag, self.stream),
+                       "qsv_init_identity")
+
+    def upload(self, amplitudes, phase=1.0 + 0.0j):
+        host = np.ascontiguousarray(amplitudes, dtype=np.complex128).reshape(-1)
+        if host.size != (1 << self.n):
+            raise ValueError("upload: expected %d amplitudes, got %d" % (1 << self.n, host.size))
+        with self._ctx():
+            _lib.check(self.lib.qsv_upload(self.ptr, self.n, ctypes.c_void_p(host.ctypes.data), host.size,
+                                           phase.real, phase.imag, self.stream), "qsv_upload")
+            self.synchronize()  # host buffer may be released by the caller
+
+    def scale(self, factor):
+        factor = complex(factor)
+        with self._ctx():
+            _lib.check(self.lib.qsv_scale(self.ptr, self.n, factor.real, factor.imag, self.stream), "qsv_scale")
+
+    # -- gates -----------------------------------------------------------------------
+    def apply_pass(self, tile_qubits, ops):
+        gates = (_lib.QsvGate * max(1, len(ops)))()
+        for i, op in enumerate(ops):
+            _fill_gate(gates[i], op)
+        tile = _int32_array(tile_qubits)
+        with self._ctx():
+            _lib.check(self.lib.qsv_apply_pass(self.ptr, self.n, tile, len(tile_qubits), gates, len(ops),
+                                               self.stream), "qsv_apply_pass")
+        self.passes_launched += 1
+        self.gates_applied += len(ops)
+
+    def apply_dense(self, qubits, matrix):
+        """One stand-alone k-qubit gate (the `unitary` instruction with k >= 3)."""
+        k = len(qubits)
+        mat = np.ascontiguousarray(matrix, dtype=np.complex128).reshape(2 ** k, 2 ** k)
+        if k > _lib.MAX_DENSE_K:
+            raise _lib.QsvLibraryError("unitary on %d qubits: more than %d qubits is not supported"
+                                       % (k, _lib.MAX_DENSE_K))
+        need = 2 * 4 ** k
+        if k >= 3 and (self._mat_scratch is None or self._mat_scratch.numel() < need):
+            self._mat_scratch = self._torch.empty(need, dtype=self._torch.float64, device=self.device)
+        scratch = ctypes.c_void_p(self._mat_scratch.data_ptr()) if k >= 3 else ctypes.c_void_p(0)
+        with self._ctx():
+            _lib.check(self.lib.qsv_apply_matrix(self.ptr, self.n, _int32_array(qubits), k,
+                                                 ctypes.c_void_p(mat.ctypes.data), scratch, self.stream),
+                       "qsv_apply_matrix")
+            if k >= 3:
+                self.synchronize()  # the pageable host matrix was staged by the async copy; be safe
+        self.passes_launched += 1
+        self.gates_applied += 1
+
+    def apply_ops(self, ops):
+        """Apply a list of GateOps in program order: runs of 1-/2-qubit gates are fused into
+        cache-blocked passes, k>=3 dense gates are stand-alone passes."""
+        run = []
+        for op in ops:
+            if op.kind == "densek":
+                self._flush(run)
+                run = []
+                self.apply_dense(op.qubits, op.matrix)
+            else:
+                run.append(op)
+        self._flush(run)
+
+    def _flush(self, run):
+        if not run:
+            return
+        for p in plan_passes(run, self.n, self.tile_qubits):
+            self.apply_pass(p.tile_qubits, p.ops)
+
+    # -- measurement -----------------------------------------------------------------
+    def prob_qubit(self, qubit):
+        out = (ctypes.c_double * 2)()
+        with self._ctx():
+            _lib.check(self.lib.qsv_prob_qubit(self.ptr, self.n, int(qubit),
+                                               ctypes.c_void_p(self._reduce_ws.data_ptr()), out, self.stream),
+                       "qsv_prob_qubit")
+        return float(out[0]), float(out[1])
+
+    def norm2(self):
+        out = ctypes.c_double(0.0)
+        with self._ctx():
+            _lib.check(self.lib.qsv_norm2(self.ptr, self.n, ctypes.c_void_p(self._reduce_ws.data_ptr()),
+                                          ctypes.byref(out), self.stream), "qsv_norm2")
+        return float(out.value)
+
+    def collapse(self, qubit, outcome, prob, is_reset=False):
+        with self._ctx():
+            _lib.check(self.lib.qsv_collapse(self.ptr, self.n, int(qubit), int(outcome), float(prob),
+                                             1 if is_reset else 0, self.stream), "qsv_collapse")
+        self.passes_launched += 1
+        self.gates_applied += 1
+
+    def marginal(self, measured_sorted):
+        """Device tensor of 2^m marginal probabilities (bit pos <-> measured_sorted[pos])."""
+        torch = self._torch
+        m = len(measured_sorted)
+        ws_bytes = self.lib.qsv_marginal_workspace_bytes(self.n, m)
+        if self._marg_ws is None or self._marg_ws.numel() * 8 < ws_bytes:
+            self._marg_ws = torch.empty(ws_bytes // 8 + 8, dtype=torch.float64, device=self.device)
+        probs = torch.empty(1 << m, dtype=torch.float64, device=self.device)
+        with self._ctx():
+            _lib.check(self.lib.qsv_marginal(self.ptr, self.n, _int32_array(measured_sorted), m,
+                                             ctypes.c_void_p(probs.data_ptr()),
+                                             ctypes.c_void_p(self._marg_ws.data_ptr()), self.stream),
+                       "qsv_marginal")
+        return probs
+
+    def sample(self, measured_sorted, uniforms, exact_order=True):
+        """searchsorted(cumsum(p)/sum(p), uniforms, 'right') over the marginal of the measured qubits.
+        Returns (int64 ndarray of bin indices, total probability)."""
+        torch = self._torch
+        uniforms = np.ascontiguousarray(uniforms, dtype=np.float64)
+        shots = int(uniforms.size)
+        m = len(measured_sorted)
+        if m == self.n:
+            src, from_amps, log2_bins = self.state, 1, self.n
+        else:
+            self._probs = self.marginal(measured_sorted)
+            src, from_amps, log2_bins = self._probs, 0, m
+        ws_bytes = self.lib.qsv_sample_workspace_bytes(log2_bins, shots)
+        if self._sample_ws is None or self._sample_ws.numel() * 8 < ws_bytes:
+            self._sample_ws = torch.empty(ws_bytes // 8 + 8, dtype=torch.float64, device=self.device)
+        out = np.empty(shots, dtype=np.int64)
+        total = ctypes.c_double(0.0)
+        with self._ctx():
+            _lib.check(self.lib.qsv_sample(ctypes.c_void_p(src.data_ptr()), from_amps, log2_bins,
+                                           ctypes.c_void_p(uniforms.ctypes.data), shots,
+                                           ctypes.c_void_p(out.ctypes.data), 1 if exact_order else 0,
+                                           ctypes.c_void_p(self._sample_ws.data_ptr()), ctypes.byref(total),
+                                           self.stream), "qsv_sample")
+        return out, float(total.value)
+
+    # -- readout ---------------------------------------------------------------------
+    def chop(self, threshold):
+        with self._ctx():
+            _lib.check(self.lib.qsv_chop(self.ptr, self.n, float(threshold), self.stream), "qsv_chop")
+
+    def download(self):
+        """Host copy (a fresh complex128 ndarray owned by the caller) of the amplitudes."""
+        host = np.empty(1 << self.n, dtype=np.complex128)
+        with self._ctx():
+            _lib.check(self.lib.qsv_download(self.ptr, self.n, ctypes.c_void_p(host.ctypes.data), self.stream),
+                       "qsv_download")
+        return host
+
+    def snapshot(self):
+        return self.state.clone()
+
+    def restore(self, snap):
+        self.state.copy_(snap)

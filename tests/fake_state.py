@@ -1,0 +1,106 @@
+"""TEST DOUBLE for engine.DeviceState, backed by the numpy oracle.
+
+Lets the CPU test-suite exercise the *host* logic of the product (Qobj lowering, fusion planner,
+classical control flow, RNG consumption, result layout) without a GPU.  It lives under tests/ and is
+never importable from the package: the product's default state factory is the CUDA engine.
+"""
+import numpy as np
+
+from oracle import basicaer_oracle as orc
+from qiskit_sdk_py_b200 import _lib
+from qiskit_sdk_py_b200.planner import plan_passes
+
+
+class FakeState:
+    def __init__(self, n_qubits, tile_qubits=6):
+        self.n = n_qubits
+        self.tile_qubits = tile_qubits
+        self.vec = np.zeros(2 ** n_qubits, dtype=complex)
+        self.passes_launched = 0
+        self.gates_applied = 0
+        self.pass_log = []
+
+    def init_basis0(self, phase=1.0 + 0.0j):
+        self.vec = np.zeros(2 ** self.n, dtype=complex)
+        self.vec[0] = phase
+
+    def init_identity(self, n_half, phase=1.0 + 0.0j):
+        self.vec = (np.eye(2 ** n_half, dtype=complex) * phase).reshape(-1)
+
+    def upload(self, amplitudes, phase=1.0 + 0.0j):
+        self.vec = np.array(amplitudes, dtype=complex).reshape(-1) * phase
+
+    def _apply(self, op):
+        t = self.vec.reshape([2] * self.n) if self.n else self.vec
+        if op.kind in (_lib.GATE_DIAG1, _lib.GATE_DIAG2):
+            mat = np.diag(op.matrix)
+        elif op.kind == _lib.GATE_CX:
+            mat = orc.cx_gate_matrix()
+        else:
+            mat = op.matrix
+        self.vec = orc.apply_unitary(t, mat, list(op.qubits)).reshape(-1)
+
+    def apply_ops(self, ops):
+        run = []
+        for op in ops:
+            if op.kind == "densek":
+                self._flush(run)
+                run = []
+                self._apply(op)
+                self.passes_launched += 1
+                self.gates_applied += 1
+            else:
+                run.append(op)
+        self._flush(run)
+
+    def _flush(self, run):
+        if not run:
+            return
+        for p in plan_passes(run, self.n, self.tile_qubits):
+            assert len(p.tile_qubits) == min(self.n, self.tile_qubits)
+            for op in p.ops:
+                assert set(op.qubits) <= set(p.tile_qubits)
+                self._apply(op)
+            self.passes_launched += 1
+            self.gates_applied += len(p.ops)
+            self.pass_log.append(p)
+
+    def prob_qubit(self, qubit):
+        p = np.abs(self.vec) ** 2
+        idx = np.arange(p.size)
+        mask = ((idx >> qubit) & 1).astype(bool)
+        return float(p[~mask].sum()), float(p[mask].sum())
+
+    def collapse(self, qubit, outcome, prob, is_reset=False):
+        s = 1 / np.sqrt(prob)
+        if is_reset and outcome == 1:
+            mat = [[0, s], [0, 0]]
+        elif outcome == 0:
+            mat = [[s, 0], [0, 0]]
+        else:
+            mat = [[0, 0], [0, s]]
+        self.vec = orc.apply_unitary(self.vec.reshape([2] * self.n), mat, [qubit]).reshape(-1)
+
+    def sample(self, measured_sorted, uniforms, exact_order=True):
+        n = self.n
+        axis = list(range(n))
+        for q in reversed(measured_sorted):
+            axis.remove(n - 1 - q)
+        p = np.reshape(np.sum(np.abs(self.vec.reshape([2] * n)) ** 2, axis=tuple(axis)),
+                       2 ** len(measured_sorted))
+        cdf = p.cumsum()
+        total = cdf[-1]
+        cdf /= total
+        return cdf.searchsorted(uniforms, side="right").astype(np.int64), float(total)
+
+    def chop(self, thr):
+        self.vec[abs(self.vec) < thr] = 0.0
+
+    def download(self):
+        return self.vec.copy()
+
+    def snapshot(self):
+        return self.vec.copy()
+
+    def restore(self, snap):
+        self.vec = snap.copy()

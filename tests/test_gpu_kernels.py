@@ -1,0 +1,253 @@
+"""GPU parity tests of the libqsv kernels against the numpy oracle, through the C-ABI (ctypes)."""
+import itertools
+
+import numpy as np
+import pytest
+
+from oracle import basicaer_oracle as orc
+from qiskit_sdk_py_b200 import _lib, lower
+from qiskit_sdk_py_b200.lower import GateOp
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def rand_state(n, seed):
+    rng = np.random.RandomState(seed)
+    v = rng.standard_normal(2 ** n) + 1j * rng.standard_normal(2 ** n)
+    return v / np.linalg.norm(v)
+
+
+def rand_unitary(k, rng):
+    z = rng.standard_normal((2 ** k, 2 ** k)) + 1j * rng.standard_normal((2 ** k, 2 ** k))
+    q, r = np.linalg.qr(z)
+    return q * (np.diag(r) / np.abs(np.diag(r)))
+
+
+def oracle_apply(vec, op, n):
+    if op.kind in (_lib.GATE_DIAG1, _lib.GATE_DIAG2):
+        mat = np.diag(op.matrix)
+    elif op.kind == _lib.GATE_CX:
+        mat = orc.cx_gate_matrix()
+    else:
+        mat = op.matrix
+    return orc.apply_unitary(vec.reshape([2] * n), mat, list(op.qubits)).reshape(-1)
+
+
+def make_state(n, vec=None, **kw):
+    from qiskit_sdk_py_b200.engine import DeviceState
+
+    st = DeviceState(n, **kw)
+    if vec is not None:
+        st.upload(vec)
+    return st
+
+
+def random_ops(n, count, rng):
+    ops = []
+    for _ in range(count):
+        kind = rng.randint(5)
+        if n == 1 and kind in (1, 3, 4):
+            kind = 0
+        if kind == 0:
+            ops.append(GateOp(_lib.GATE_DENSE1, [rng.randint(n)], rand_unitary(1, rng)))
+        elif kind == 1:
+            a, b = rng.choice(n, 2, replace=False)
+            ops.append(GateOp(_lib.GATE_DENSE2, [a, b], rand_unitary(2, rng)))
+        elif kind == 2:
+            ops.append(GateOp(_lib.GATE_DIAG1, [rng.randint(n)], np.exp(1j * rng.uniform(0, 6, 2))))
+        elif kind == 3:
+            a, b = rng.choice(n, 2, replace=False)
+            ops.append(GateOp(_lib.GATE_DIAG2, [a, b], np.exp(1j * rng.uniform(0, 6, 4))))
+        else:
+            a, b = rng.choice(n, 2, replace=False)
+            ops.append(GateOp(_lib.GATE_CX, [a, b], None))
+    return ops
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 7, 9, 12, 13, 15])
+def test_single_gates_every_qubit(n):
+    """Each gate kind on every qubit / many pairs, one gate per pass (K1-K3)."""
+    rng = np.random.RandomState(n)
+    vec = rand_state(n, 100 + n)
+    st = make_state(n, vec)
+    ref = vec.copy()
+    pairs = list(itertools.permutations(range(n), 2))
+    if len(pairs) > 40:
+        pairs = [pairs[i] for i in rng.choice(len(pairs), 40, replace=False)]
+    ops = []
+    for q in range(n):
+        ops.append(GateOp(_lib.GATE_DENSE1, [q], rand_unitary(1, rng)))
+        ops.append(GateOp(_lib.GATE_DIAG1, [q], np.exp(1j * rng.uniform(0, 6, 2))))
+    for a, b in pairs:
+        ops.append(GateOp(_lib.GATE_DENSE2, [a, b], rand_unitary(2, rng)))
+        ops.append(GateOp(_lib.GATE_CX, [a, b], None))
+        ops.append(GateOp(_lib.GATE_DIAG2, [a, b], np.exp(1j * rng.uniform(0, 6, 4))))
+    for op in ops:
+        tile = _default_tile(n, op.qubits, min(n, 12))
+        st.apply_pass(tile, [op])
+        ref = oracle_apply(ref, op, n)
+    got = st.download()
+    assert np.max(np.abs(got - ref)) < TOL
+
+
+def _default_tile(n, qubits, size):
+    tile = list(qubits)
+    for q in range(n):
+        if len(tile) >= size:
+            break
+        if q not in tile:
+            tile.append(q)
+    return sorted(tile)
+
+
+@pytest.mark.parametrize("n,tile_size", [(3, 3), (6, 4), (10, 5), (10, 10), (14, 8), (14, 12), (14, 13),
+                                         (16, 12), (16, 13), (18, 11)])
+def test_fused_passes_any_tile(n, tile_size):
+    """Runs of gates fused by the planner into cache-blocked passes with arbitrary tile qubit sets (K4)."""
+    rng = np.random.RandomState(1000 + n + tile_size)
+    vec = rand_state(n, 7 + n)
+    st = make_state(n, vec, tile_qubits=tile_size)
+    ops = random_ops(n, 60, rng)
+    st.apply_ops(ops)
+    ref = vec.copy()
+    for op in ops:
+        ref = oracle_apply(ref, op, n)
+    assert st.passes_launched < len(ops)
+    assert np.max(np.abs(st.download() - ref)) < TOL
+
+
+@pytest.mark.parametrize("n", [8, 14])
+def test_explicit_high_tiles(n):
+    """Tiles made only of high qubits (no low qubits): still correct, just not coalesced."""
+    rng = np.random.RandomState(5)
+    vec = rand_state(n, 3)
+    st = make_state(n, vec)
+    ref = vec.copy()
+    tile = list(range(n - 5, n))
+    ops = [GateOp(_lib.GATE_DENSE2, [n - 1, n - 4], rand_unitary(2, rng)),
+           GateOp(_lib.GATE_DENSE1, [n - 5], rand_unitary(1, rng)),
+           GateOp(_lib.GATE_CX, [n - 2, n - 3], None)]
+    st.apply_pass(tile, ops)
+    for op in ops:
+        ref = oracle_apply(ref, op, n)
+    assert np.max(np.abs(st.download() - ref)) < TOL
+
+
+@pytest.mark.parametrize("n,k", [(3, 3), (5, 3), (9, 4), (12, 5), (13, 6), (14, 7), (9, 9), (15, 3)])
+def test_dense_k(n, k):
+    """k-qubit `unitary` instructions, k >= 3 (qasm_simulator.py:543-546)."""
+    rng = np.random.RandomState(n * 31 + k)
+    vec = rand_state(n, n + k)
+    st = make_state(n, vec)
+    ref = vec.copy()
+    for _ in range(3):
+        qubits = [int(q) for q in rng.choice(n, k, replace=False)]
+        mat = rand_unitary(k, rng)
+        st.apply_ops([lower.matrix_op(mat, qubits)])
+        ref = orc.apply_unitary(ref.reshape([2] * n), mat, qubits).reshape(-1)
+    assert np.max(np.abs(st.download() - ref)) < TOL
+
+
+def test_init_scale_chop_identity():
+    st = make_state(10)
+    st.init_basis0(np.exp(0.3j))
+    got = st.download()
+    assert got[0] == np.exp(0.3j) and not np.any(got[1:])
+    st.scale(2j)
+    assert abs(st.download()[0] - 2j * np.exp(0.3j)) < 1e-15
+    vec = rand_state(10, 1)
+    vec[5] = 1e-16
+    vec[6] = 1e-16j
+    vec[7] = 0.9e-15 + 0.1e-15j
+    st.upload(vec)
+    st.chop(1e-15)
+    exp = vec.copy()
+    exp[abs(exp) < 1e-15] = 0.0
+    assert np.array_equal(st.download(), exp)
+    st = make_state(8)
+    st.init_identity(4, 1.0 + 0.0j)
+    assert np.array_equal(st.download().reshape(16, 16), np.eye(16))
+
+
+@pytest.mark.parametrize("n", [1, 2, 5, 10, 16, 21])
+def test_prob_collapse(n):
+    """_get_measure_outcome / _add_qasm_measure / _add_qasm_reset arithmetic (K7, K8)."""
+    vec = rand_state(n, 50 + n)
+    st = make_state(n, vec)
+    p = np.abs(vec) ** 2
+    idx = np.arange(2 ** n)
+    for q in sorted({0, n // 2, n - 1}):
+        p0, p1 = st.prob_qubit(q)
+        mask = ((idx >> q) & 1).astype(bool)
+        assert abs(p0 - p[~mask].sum()) < 1e-13 and abs(p1 - p[mask].sum()) < 1e-13
+    assert abs(st.norm2() - 1.0) < 1e-13
+    q = n // 2
+    for outcome, is_reset in ((0, False), (1, False), (0, True), (1, True)):
+        st.upload(vec)
+        probs = st.prob_qubit(q)
+        st.collapse(q, outcome, probs[outcome], is_reset)
+        s = 1 / np.sqrt(probs[outcome])
+        if is_reset and outcome == 1:
+            mat = [[0, s], [0, 0]]
+        elif outcome == 0:
+            mat = [[s, 0], [0, 0]]
+        else:
+            mat = [[0, 0], [0, s]]
+        ref = orc.apply_unitary(vec.reshape([2] * n), mat, [q]).reshape(-1)
+        assert np.max(np.abs(st.download() - ref)) < TOL
+        assert abs(st.norm2() - 1.0) < 1e-12
+
+
+@pytest.mark.parametrize("n,measured", [(3, [0, 1, 2]), (6, [1, 4]), (10, [0]), (10, [9]), (12, [0, 3, 5, 11]),
+                                        (14, list(range(14))), (14, list(range(1, 14))), (18, [2, 17]),
+                                        (20, list(range(20)))])
+def test_marginal_and_exact_sampling(n, measured):
+    """_add_sample_measure (qasm_simulator.py:184-213): same indices as numpy's choice()."""
+    vec = rand_state(n, 77 + n)
+    st = make_state(n, vec)
+    m = len(measured)
+    axis = list(range(n))
+    for q in reversed(measured):
+        axis.remove(n - 1 - q)
+    p = np.reshape(np.sum(np.abs(vec.reshape([2] * n)) ** 2, axis=tuple(axis)), 2 ** m)
+    if m < n:
+        probs = st.marginal(measured).cpu().numpy()
+        assert np.max(np.abs(probs - p)) < 1e-14
+    shots = 4096
+    rs = np.random.RandomState(123)
+    expected = rs.choice(range(2 ** m), shots, p=p)
+    u = np.random.RandomState(123).random_sample(shots)
+    got, total = st.sample(measured, u, exact_order=True)
+    assert abs(total - 1.0) < 1e-12
+    mism = int(np.sum(got != expected))
+    # identical unless a uniform falls within ~1e-16 of a CDF step (amplitude rounding only)
+    assert mism == 0
+    fast, total2 = st.sample(measured, u, exact_order=False)
+    assert abs(total2 - 1.0) < 1e-12
+    assert np.mean(fast != expected) < 2e-3
+
+
+def test_sampling_edge_cases():
+    # basis state: every sample is that index; zero-probability plateaus are skipped like searchsorted
+    n = 12
+    vec = np.zeros(2 ** n, dtype=complex)
+    vec[1234] = 1.0
+    st = make_state(n, vec)
+    u = np.random.RandomState(0).random_sample(100)
+    got, _ = st.sample(list(range(n)), u)
+    assert np.all(got == 1234)
+    # not normalised -> numpy's ValueError
+    st.scale(1.1)
+    with pytest.raises(ValueError, match="probabilities do not sum to 1"):
+        st.sample(list(range(n)), u)
+
+
+def test_bad_arguments_fail_loudly():
+    st = make_state(6, rand_state(6, 0))
+    with pytest.raises(_lib.QsvLibraryError):
+        st.apply_pass([0, 1, 2], [GateOp(_lib.GATE_DENSE1, [5], np.eye(2))])  # gate qubit not in tile
+    with pytest.raises(_lib.QsvLibraryError):
+        st.apply_pass([0, 1, 1], [])
+    with pytest.raises(_lib.QsvLibraryError):
+        st.apply_pass(list(range(6)) + [7], [])

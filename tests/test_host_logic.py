@@ -1,0 +1,107 @@
+"""CPU tests of the product's host logic (lowering, planner, control flow, RNG order, result layout)
+with the device replaced by tests/fake_state.FakeState (numpy oracle).  The CUDA path itself is
+covered by the ``-m gpu`` tests."""
+import copy
+
+import numpy as np
+import pytest
+
+import golden_io
+import helpers
+from fake_state import FakeState
+from qiskit_sdk_py_b200 import _lib, circuits, lower, simulator
+from qiskit_sdk_py_b200.planner import plan_passes
+
+SMALL = helpers.small_cases(12)
+
+
+def fake_factory(backend):
+    if backend == "qasm_simulator":
+        return simulator.QasmSimulatorB200(state_factory=FakeState, max_qubits=24)
+    if backend == "statevector_simulator":
+        return simulator.StatevectorSimulatorB200(state_factory=FakeState, max_qubits=24)
+    return simulator.UnitarySimulatorB200(state_factory=FakeState, max_qubits=12)
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_host_logic_matches_reference_golden(name):
+    case = golden_io.load_case(name)
+    result = helpers.run_case_with(fake_factory, case)
+    helpers.compare_result(result, case, amp_tol=1e-12)
+
+
+def test_planner_preserves_order_on_shared_qubits():
+    ops = [lower.lower_gate(i["name"], i["qubits"], i.get("params"))
+           for i in circuits.random_basis_instructions(10, 30, 5)]
+    ops = [o for o in ops if o is not None]
+    for tile in (3, 4, 6, 10, 12):
+        passes = plan_passes(ops, 10, tile_qubits=tile)
+        flat = [op for p in passes for op in p.ops]
+        assert sorted(map(id, flat)) == sorted(map(id, ops))
+        # per qubit, the subsequence of gates touching it is unchanged
+        for q in range(10):
+            assert [id(o) for o in flat if q in o.qubits] == [id(o) for o in ops if q in o.qubits]
+        for p in passes:
+            assert len(p.tile_qubits) == min(10, tile)
+            assert len(set(p.tile_qubits)) == len(p.tile_qubits)
+            assert len(p.ops) <= _lib.MAX_PASS_GATES
+            assert sum(o.payload_doubles for o in p.ops) <= _lib.MAX_PASS_MATRIX_DOUBLES
+            for o in p.ops:
+                assert set(o.qubits) <= set(p.tile_qubits)
+            if tile >= 5:
+                assert {0, 1, 2} <= set(p.tile_qubits)
+
+
+def test_planner_fuses_quantum_volume():
+    n = 24
+    ops = [lower.lower_gate(i["name"], i["qubits"], i.get("params"))
+           for i in circuits.quantum_volume_instructions(n, n, 1234)]
+    passes = plan_passes(ops, n, tile_qubits=12)
+    assert len(passes) < len(ops) / 3
+
+
+def test_lowering_kinds():
+    assert lower.lower_gate("u1", [3], [0.5]).kind == _lib.GATE_DIAG1
+    assert lower.lower_gate("rz", [3], [0.5]).kind == _lib.GATE_DIAG1
+    assert lower.lower_gate("u3", [0], [0.1, 0.2, 0.3]).kind == _lib.GATE_DENSE1
+    assert lower.lower_gate("cx", [1, 0], None).kind == _lib.GATE_CX
+    assert lower.lower_gate("id", [1], None) is None
+    assert lower.lower_gate("unitary", [0, 1], [np.diag([1, 1j, -1, -1j])]).kind == _lib.GATE_DIAG2
+    assert lower.lower_gate("unitary", [0, 1, 2], [np.eye(8)]).kind == "densek"
+    for name, params in (("u1", [0.3]), ("u2", [0.1, 0.2]), ("u3", [0.1, 0.2, 0.3]), ("U", [1, 2, 3]),
+                         ("rz", [0.7]), ("sx", []), ("x", [])):
+        from oracle import basicaer_oracle as orc
+        assert np.array_equal(lower.single_gate_matrix(name, params), orc.single_gate_matrix(name, params))
+
+
+def test_errors_mirror_reference_messages():
+    sim = simulator.QasmSimulatorB200(state_factory=FakeState, max_qubits=24)
+    qobj = circuits.bell()
+    with pytest.raises(simulator.BasicAerError, match="initial statevector is not normalized"):
+        sim.run(copy.deepcopy(qobj), initial_statevector=[1, 1, 0, 0])
+    with pytest.raises(simulator.BasicAerError, match="initial statevector is incorrect length: 2 != 4"):
+        sim.run(copy.deepcopy(qobj), initial_statevector=[1, 0])
+    big = circuits.make_qobj(circuits.make_experiment("big", 50, [], 0))
+    with pytest.raises(simulator.BasicAerError, match=r"Number of qubits 50 is greater than maximum \(24\)"):
+        sim.run(big)
+    bad = circuits.make_qobj(circuits.make_experiment("bad", 2, [{"name": "foo", "qubits": [0]}], 0))
+    with pytest.raises(simulator.BasicAerError, match='qasm_simulator encountered unrecognized operation "foo"'):
+        sim.run(bad)
+    usim = simulator.UnitarySimulatorB200(state_factory=FakeState, max_qubits=12)
+    with pytest.raises(simulator.BasicAerError, match="Unsupported"):
+        usim.run(copy.deepcopy(qobj))
+    with pytest.raises(simulator.BasicAerError, match="initial unitary is not unitary"):
+        usim.run(circuits.make_qobj(circuits.make_experiment("u", 1, [], 0)), initial_unitary=[[1, 1], [0, 1]])
+
+
+def test_random_seed_when_absent():
+    sim = simulator.QasmSimulatorB200(state_factory=FakeState, max_qubits=24)
+    res = sim.run(circuits.bell(seed_simulator=None))
+    assert isinstance(res["results"][0]["seed_simulator"], (int, np.integer))
+    assert sum(res["results"][0]["data"]["counts"].values()) == 1024
+
+
+def test_get_simulator_aliases():
+    assert simulator.get_simulator("local_qasm_simulator_py", state_factory=FakeState).name() == "qasm_simulator"
+    with pytest.raises(LookupError):
+        simulator.get_simulator("nope")
