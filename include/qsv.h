@@ -39,7 +39,7 @@ extern "C" {
 #define QSV_ERANGE (-2)   /* size outside what the kernels support */
 #define QSV_ENORM (-3)    /* probabilities do not sum to 1 (numpy choice() ValueError) */
 
-#define QSV_MAX_TILE_QUBITS 13 /* 2^13 amplitudes * 16 B = 128 KiB of shared memory */
+#define QSV_MAX_TILE_QUBITS 12 /* two buffers of 2^12 amplitudes * 16 B = 128 KiB of shared memory */
 #define QSV_MAX_PASS_GATES 48
 #define QSV_MAX_DENSE_K 12
 

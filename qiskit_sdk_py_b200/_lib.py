@@ -20,7 +20,7 @@ GATE_DIAG1 = 3
 GATE_DIAG2 = 4
 GATE_CX = 5
 
-MAX_TILE_QUBITS = 13
+MAX_TILE_QUBITS = 12
 MAX_PASS_GATES = 48
 MAX_PASS_MATRIX_DOUBLES = 1536
 MAX_DENSE_K = 12

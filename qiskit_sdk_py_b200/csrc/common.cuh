@@ -48,21 +48,4 @@ __device__ __forceinline__ void cfma(double2& acc, double2 a, double2 b) {
   acc.y = fma(a.y, b.x, acc.y);
 }
 
-// XOR swizzle of a tile-local amplitude index (16-byte slots).  Bank group = slot & 7; bit j of the
-// index contributes to bank bit (j mod 3), so any three index bits with distinct residues mod 3 are
-// conflict-free across the 8 lanes of a quarter warp (LDS.128 is served per quarter warp).
-__device__ __forceinline__ uint32_t swz(uint32_t li) {
-  uint32_t x = li >> 3;
-  x ^= x >> 3;
-  x ^= x >> 6;
-  return li ^ (x & 7u);
-}
-
-inline __host__ uint32_t swz_host(uint32_t li) {
-  uint32_t x = li >> 3;
-  x ^= x >> 3;
-  x ^= x >> 6;
-  return li ^ (x & 7u);
-}
-
 }  // namespace qsv
