@@ -1,11 +1,27 @@
 // Cache-blocked gate application (K1-K5 of SURVEY 2.5) for sm_100a.
 //
-// One launch = one pass over the state: CTA t stages the 2^b amplitudes of tile t (the amplitudes
+// One launch = one pass over the state: a CTA stages the 2^b amplitudes of a tile (the amplitudes
 // that differ only in the b "tile qubits") in shared memory, applies a run of gates there and writes
 // the tile back.  HBM traffic is exactly one read + one write of the vector per pass, however many
 // gates the pass fuses.  Replaces runs of QasmSimulatorPy._add_unitary calls
 // (/root/reference/qiskit/providers/basicaer/qasm_simulator.py:145-161), each of which is one
 // out-of-place np.einsum over the whole vector.
+//
+// Kernel structure (tile_pass_kernel):
+//   * persistent: one 1024-thread CTA per SM walks tiles c, c+grid, ...; the cp.async loads of the
+//     next tile stream into a second shared-memory buffer while the gates of the current one run;
+//   * the gates of a pass are grouped into STAGES.  In a stage every warp owns a sub-cube of 2^7
+//     amplitudes of the tile (7 "inner" tile bits; the warp id supplies the other 5) and applies all
+//     the stage's gates -- whose qubits are inner bits -- to it with only __syncwarp() between gates.
+//     Warps therefore drift apart and the shared-memory traffic of one warp overlaps the FP64 tensor
+//     work of another; block-wide barriers are needed only between stages;
+//   * dense gates run on the FP64 tensor path (mma.sync m8n8k4 f64, SASS DMMA.8x8x4): a 4x4 complex
+//     gate is the 8x8 real matrix [[Re,-Im],[Im,Re]]; one warp step multiplies 8 groups x 8 real
+//     components (A operand, two k-slices) by the gate (B operand) and every lane receives one complex
+//     output amplitude, i.e. one 16-byte shared-memory store.  (Measured on B200: DMMA 37 TF/s, DFMA
+//     34 TF/s, no gain from mixing them -- tools/fp64_peak.cu -- but DMMA needs 8x fewer instructions
+//     and 2 registers of gate matrix per lane instead of 64.)
+//   * all index maps are linear over GF(2) (XOR masks), including a pass-specific bank swizzle.
 #include <string.h>
 
 #include <algorithm>
@@ -19,27 +35,33 @@ unsigned long long g_launches = 0;
 
 constexpr int kMaxOps = QSV_MAX_PASS_GATES;
 constexpr int kMaxMat = 1536;  // doubles of matrix payload per pass (48 dense 2-qubit gates)
-constexpr int kPT = 512;       // threads of the persistent pass kernel (16 warps, one CTA per SM)
-constexpr int kTidBits = 9;
+constexpr int kPT = 1024;      // threads of the persistent pass kernel (32 warps, one CTA per SM)
+constexpr int kTidBits = 10;
+constexpr int kInner = 7;      // inner bits of a stage: 2^7 amplitudes per warp
+constexpr int kMaxStages = kMaxOps;
 
-// One gate of a pass, lowered to XOR masks.  Every index map in the kernel is linear over GF(2):
-//   slot(w) = XOR_j bit_j(w) * col[j]   is the (bank-swizzled) shared-memory slot of the first
-// amplitude of group w; the other members of the group are slot ^ z0, slot ^ z1, slot ^ z0 ^ z1.
-// The group index is split as  w = lane part (lb bits) | warp id (4 bits) | iteration (rest).
-struct __align__(8) PassOp {
-  uint8_t kind, t0, t1, nbits;  // t0/t1: tile-local gate bits; nbits = b - k (bits of the group index)
-  uint16_t moff;                // offset (doubles) of the matrix in PassDesc::mats
-  uint16_t z0, z1;              // swz(1 << t0), swz(1 << t1)
-  uint8_t lb, pad;              // lane bits: 3 for the DMMA path (8 groups per warp step), else 5
-  uint16_t col[13];             // col[j] = swz(1 << position of group-index bit j)
+struct __align__(4) PassOp {
+  uint8_t kind, t0, t1, ngl;  // t0/t1: tile-local gate bits; ngl = log2(#groups in a warp's sub-cube)
+  uint16_t moff;              // offset (doubles) of the matrix in PassDesc::mats
+  uint16_t z0, z1;            // swz(1 << t0), swz(1 << t1)
+  uint16_t col[5];            // swizzled masks of the free inner bits: col[0..2] vary inside a warp step
+};
+
+struct __align__(4) PassStage {
+  uint8_t first_op, n_ops, n_inner, n_outer;
+  uint8_t ebit[kInner];   // inner tile bits in element order (bit j of the in-warp element index)
+  uint8_t obit[5];        // outer tile bits (bit j of the warp id)
+  uint16_t ecol[kInner];  // swz(1 << ebit[j])
+  uint16_t ocol[5];       // swz(1 << obit[j])
 };
 
 struct PassDesc {
-  int32_t n, b, nops, pad;
+  int32_t n, b, nops, nstages;
   uint32_t n_tiles;
   uint32_t pad2[3];
   uint8_t tb[16];   // ascending physical bit position of each tile-local bit
   uint8_t vec[16];  // bank vector of each tile-local bit (pass-specific XOR swizzle), vec[j] = 1<<j for j<3
+  PassStage stages[kMaxStages];
   PassOp ops[kMaxOps];
   double mats[kMaxMat];
 };
@@ -47,8 +69,7 @@ struct PassDesc {
 // Pass-specific XOR swizzle of a tile-local amplitude index (16-byte slots; bank group = slot & 7).
 // Tile bit j >= 3 toggles the bank bits vec[j]; three index bits whose vectors are linearly independent
 // over GF(2) spread over all 8 bank groups, so the accesses of a quarter warp (LDS/STS.128) or of a
-// half warp reading 8-byte halves (LDS.64) are conflict-free.  The host picks vec[] per pass so that
-// the two gate bits of every dense gate get different vectors.
+// half warp reading 8-byte halves (LDS.64) are conflict-free.  The host picks vec[] per pass.
 __host__ __device__ __forceinline__ uint32_t swz(const uint8_t* vec, int b, uint32_t li) {
   uint32_t f = 0;
   for (int j = 3; j < b; j++)
@@ -80,71 +101,97 @@ __device__ __forceinline__ u64 tile_base(const PassDesc& d, u64 t) {
   return t;
 }
 
-// Persistent, double-buffered pass kernel: CTA c processes tiles c, c+grid, c+2*grid, ...  While the
-// gates of tile i run out of buffer (i & 1), the cp.async loads of tile i+1 stream into the other
-// buffer, so HBM reads overlap the FP64 work; the write-back is plain stores, which retire
-// asynchronously behind the next tile's compute.
-//
-// Dense 2-qubit gates run on the FP64 tensor path: a 4x4 complex gate is the 8x8 real matrix
-// [[Re,-Im],[Im,Re]] acting on (re,im) of the 4 amplitudes of a group; one warp step takes 8 groups
-// as the A operand (8 groups x 4 real components, two k-slices) against the gate as the B operand,
-// and each lane receives one complex output amplitude (re,im) -- a single 16-byte store.
+// Per-op record staged in shared memory (one broadcast 16-byte load per op per warp).
+struct __align__(16) OpRec {
+  uint16_t z0, z1, c3, c4;
+  uint8_t kind, ngl, t0, t1;
+  uint16_t moff, pad;
+};
+
 __global__ void __launch_bounds__(kPT, 1)
 tile_pass_kernel(double2* __restrict__ sv, const __grid_constant__ PassDesc d) {
   extern __shared__ double2 smem[];
-  __shared__ u64 hi_off[8];
-  __shared__ uint16_t swz_it[8];
-  __shared__ uint16_t tab[kMaxOps][56];  // per op: [0,32) lane part, [32,48) warp part, [48,56) iteration part
-  __shared__ double frag[kMaxOps][64];   // per dense op: B fragments of the two k-slices, frag[s*32 + lane]
+  __shared__ u64 hi_off[4];
+  __shared__ uint16_t swz_it[4];
+  __shared__ double frag[kMaxOps][64];       // per dense op: B fragments of the two k-slices, frag[s*32 + lane]
+  __shared__ OpRec oprec[kMaxOps];
+  __shared__ uint32_t opl[kMaxOps][32];      // per op, per lane: (load slot ^ s_w) | (store slot ^ s_w) << 16
+  __shared__ uint32_t st_warp[kMaxStages][32];  // per stage, per warp: li_w | s_w << 16
+  __shared__ uint32_t st_lane[kMaxStages][32];  // per stage, per lane: li part | slot part << 16 (element lane | it<<5, it = 0)
+  __shared__ uint32_t st_it[kMaxStages][4];     // per stage, per element iteration: li part | slot part << 16
 
   const uint32_t tid = threadIdx.x;
   const int b = d.b;
   const uint32_t tile_amps = 1u << b;
+  const int nops = d.nops, nstages = d.nstages;
 
-  // ---- per-kernel setup (amortised over all tiles of this CTA) ----
+  // ---- per-kernel setup (amortised over all tiles of this CTA): every lane/warp dependent index of
+  // the pass is tile-invariant, so it is digested once into shared-memory tables ----
   const int lo_bits = b < kTidBits ? b : kTidBits;
   u64 lo_off = 0;
   for (int j = 0; j < lo_bits; j++) lo_off |= (u64)((tid >> j) & 1u) << d.tb[j];
-  if (tid < 8) {
+  if (tid < 4) {
     u64 off = 0;
     for (int j = kTidBits; j < b; j++) off |= (u64)((tid >> (j - kTidBits)) & 1u) << d.tb[j];
     hi_off[tid] = off;
     swz_it[tid] = (uint16_t)swz(d.vec, b, tid << kTidBits);
   }
-  for (int idx = tid; idx < d.nops * 56; idx += kPT) {
-    const int o = idx / 56, e = idx % 56;
-    const int lb = d.ops[o].lb;
-    uint32_t v = 0;
-    if (e < 32) {
-      for (int j = 0; j < 5; j++)
-        if ((e >> j) & 1) v ^= d.ops[o].col[j];
-    } else if (e < 48) {
-      for (int j = 0; j < 4; j++)
-        if (((e - 32) >> j) & 1) v ^= d.ops[o].col[lb + j];
-    } else {
-      for (int j = 0; j < 3; j++)
-        if (((e - 48) >> j) & 1) v ^= d.ops[o].col[lb + 4 + j];
-    }
-    tab[o][e] = (uint16_t)v;
-  }
-  for (int idx = tid; idx < d.nops * 64; idx += kPT) {
+  for (int idx = tid; idx < nops * 64; idx += kPT) {
     const int o = idx >> 6, e = idx & 63;
-    if (d.ops[o].kind == QSV_GATE_DENSE2) {
+    const PassOp& op = d.ops[o];
+    if (op.kind == QSV_GATE_DENSE2) {
       // B fragment of k-slice s: lane l holds Mreal[n = l >> 2][k = 4 s + (l & 3)]
       const int s = e >> 5, l = e & 31;
       const int nrow = l >> 2, kcol = 4 * s + (l & 3);
       const int r = nrow >> 1, c = kcol >> 1;
-      const double* m = d.mats + d.ops[o].moff + 2 * (4 * r + c);
+      const double* m = d.mats + op.moff + 2 * (4 * r + c);
       double v;
       if ((nrow & 1) == 0) v = (kcol & 1) == 0 ? m[0] : -m[1];
       else v = (kcol & 1) == 0 ? m[1] : m[0];
       frag[o][e] = v;
+    }
+    if (e < 32) {
+      const uint32_t g = e >> 2, c = e & 3u;
+      uint32_t s_g = 0;
+      if (g & 1u) s_g ^= op.col[0];
+      if (g & 2u) s_g ^= op.col[1];
+      if (g & 4u) s_g ^= op.col[2];
+      const uint32_t ld_x = (c & 2u) ? op.z0 : 0u;                                 // amplitude c>>1 of the k-slice
+      const uint32_t st_x = ((c & 1u) ? op.z0 : 0u) ^ ((c & 2u) ? op.z1 : 0u);     // amplitude c of the group
+      opl[o][e] = (s_g ^ ld_x) | ((s_g ^ st_x) << 16);
+    }
+    if (e == 32) {
+      OpRec r;
+      r.z0 = op.z0; r.z1 = op.z1; r.c3 = op.col[3]; r.c4 = op.col[4];
+      r.kind = op.kind; r.ngl = op.ngl; r.t0 = op.t0; r.t1 = op.t1;
+      r.moff = op.moff; r.pad = 0;
+      oprec[o] = r;
+    }
+  }
+  for (int idx = tid; idx < nstages * 96; idx += kPT) {
+    const int sidx = idx / 96, e = idx % 96;
+    const PassStage& st = d.stages[sidx];
+    uint32_t li = 0, sl = 0;
+    if (e < 32) {  // warp part
+      for (int j = 0; j < st.n_outer; j++)
+        if ((e >> j) & 1) { li |= 1u << st.obit[j]; sl ^= st.ocol[j]; }
+      st_warp[sidx][e] = li | (sl << 16);
+    } else if (e < 64) {  // lane part (element bits 0..4)
+      for (int j = 0; j < 5 && j < st.n_inner; j++)
+        if (((e - 32) >> j) & 1) { li |= 1u << st.ebit[j]; sl ^= st.ecol[j]; }
+      st_lane[sidx][e - 32] = li | (sl << 16);
+    } else if (e < 68) {  // element iteration part (element bits 5, 6)
+      for (int j = 0; j < 2; j++)
+        if ((((e - 64) >> j) & 1) && 5 + j < st.n_inner) { li |= 1u << st.ebit[5 + j]; sl ^= st.ecol[5 + j]; }
+      st_it[sidx][e - 64] = li | (sl << 16);
     }
   }
   const uint32_t s_tid = swz(d.vec, b, tid);
   const uint32_t iters = tile_amps > kPT ? tile_amps / kPT : 1;
   const bool active = tid < tile_amps;
   const uint32_t lane = tid & 31u, wid = tid >> 5;
+  const uint32_t g = lane >> 2;
+  const uint32_t half8 = (lane & 1u) * 8u;
   __syncthreads();
 
   const u64 n_tiles = d.n_tiles;
@@ -153,9 +200,9 @@ tile_pass_kernel(double2* __restrict__ sv, const __grid_constant__ PassDesc d) {
   if (t < n_tiles) {
     base_cur = tile_base(d, t);
     if (active) {
-      const double2* g = sv + base_cur + lo_off;
+      const double2* gp = sv + base_cur + lo_off;
 #pragma unroll 4
-      for (uint32_t it = 0; it < iters; it++) cp_async16(smem + (s_tid ^ swz_it[it]), g + hi_off[it]);
+      for (uint32_t it = 0; it < iters; it++) cp_async16(smem + (s_tid ^ swz_it[it]), gp + hi_off[it]);
     }
     cp_async_commit();
   }
@@ -167,103 +214,112 @@ tile_pass_kernel(double2* __restrict__ sv, const __grid_constant__ PassDesc d) {
       base_next = tile_base(d, t_next);
       if (active) {
         double2* dst = smem + (cur ? 0u : tile_amps);
-        const double2* g = sv + base_next + lo_off;
+        const double2* gp = sv + base_next + lo_off;
 #pragma unroll 4
-        for (uint32_t it = 0; it < iters; it++) cp_async16(dst + (s_tid ^ swz_it[it]), g + hi_off[it]);
+        for (uint32_t it = 0; it < iters; it++) cp_async16(dst + (s_tid ^ swz_it[it]), gp + hi_off[it]);
       }
       cp_async_commit();
       cp_async_wait<1>();
     } else {
       cp_async_wait<0>();
     }
-    __syncthreads();
+    const char* tb8 = reinterpret_cast<const char*>(tile) + half8;
 
-    bool elementwise_prev = true;  // cp.async wrote element li = tid + it*512, same owner as DIAG ops
-    for (int o = 0; o < d.nops; o++) {
-      const PassOp& op = d.ops[o];
-      const int kind = op.kind;
-      const bool elementwise = (kind == QSV_GATE_DIAG1 || kind == QSV_GATE_DIAG2);
-      if (o > 0 && !(elementwise && elementwise_prev)) __syncthreads();
-      elementwise_prev = elementwise;
-      const double* m = d.mats + op.moff;
-      const uint32_t ngroups = 1u << op.nbits;
+    int o = 0;
+    for (int sidx = 0; sidx < nstages; sidx++) {
+      __syncthreads();  // stage boundary: warps re-partition the tile
+      const uint32_t n_inner = d.stages[sidx].n_inner, n_outer = d.stages[sidx].n_outer;
+      const int o_end = o + d.stages[sidx].n_ops;
+      const bool warp_on = wid < (1u << n_outer);  // small tiles: fewer sub-cubes than warps
+      const uint32_t wv = st_warp[sidx][wid];
+      const uint32_t s_w = wv >> 16;
+      bool first = true;
+      for (; o < o_end; o++) {
+        if (!warp_on) continue;
+        const OpRec rec = oprec[o];
+        if (!first) __syncwarp();
+        first = false;
 
-      if (kind == QSV_GATE_DENSE2) {
-        // ---- FP64 tensor path: 8 groups per warp step ----
-        const uint32_t g = lane >> 2, c = lane & 3u;
-        const double b0 = frag[o][lane], b1 = frag[o][32 + lane];
-        const uint32_t z0 = op.z0, z1 = op.z1;
-        const uint32_t ld_x = (c & 2u) ? z0 : 0u;                                   // amplitude c>>1 of the slice
-        const uint32_t st_x = ((c & 1u) ? z0 : 0u) ^ ((c & 2u) ? z1 : 0u);          // amplitude c of the group
-        const uint32_t s_lw = (uint32_t)tab[o][g] ^ (uint32_t)tab[o][32 + wid];
-        const uint32_t w_lw = g | (wid << 3);
-        const char* tb8 = reinterpret_cast<const char*>(tile) + (c & 1u) * 8u;
-        const uint32_t n_it = ngroups > 128u ? (ngroups >> 7) : 1u;
-#pragma unroll 4
-        for (uint32_t it = 0; it < n_it; it++) {
-          const uint32_t s = s_lw ^ (uint32_t)tab[o][48 + it];
-          const bool valid = (w_lw | (it << 7)) < ngroups;
-          double x0 = 0.0, x1 = 0.0;
-          if (valid) {
-            const uint32_t sa = s ^ ld_x;
-            x0 = *reinterpret_cast<const double*>(tb8 + (size_t)sa * 16u);
-            x1 = *reinterpret_cast<const double*>(tb8 + (size_t)(sa ^ z1) * 16u);
-          }
-          double d0 = 0.0, d1 = 0.0;
-          dmma884(d0, d1, x0, b0);
-          dmma884(d0, d1, x1, b1);
-          if (valid) tile[s ^ st_x] = make_double2(d0, d1);
-        }
-      } else if (kind == QSV_GATE_DENSE1) {
-        // scalar path, only used when the tile has a single qubit (no partner bit for the tensor path)
-        const double2 m00 = make_double2(m[0], m[1]), m01 = make_double2(m[2], m[3]);
-        const double2 m10 = make_double2(m[4], m[5]), m11 = make_double2(m[6], m[7]);
-        const uint32_t z0 = op.z0;
-        const uint32_t s_w = (uint32_t)tab[o][lane] ^ (uint32_t)tab[o][32 + wid];
-        uint32_t it = 0;
-        for (uint32_t w = tid; w < ngroups; w += kPT, it++) {
-          const uint32_t s0 = s_w ^ (uint32_t)tab[o][48 + it];
-          const uint32_t s1 = s0 ^ z0;
-          const double2 a0 = tile[s0], a1 = tile[s1];
-          double2 r0 = cmul(m00, a0), r1 = cmul(m10, a0);
-          cfma(r0, m01, a1);
-          cfma(r1, m11, a1);
-          tile[s0] = r0;
-          tile[s1] = r1;
-        }
-      } else if (kind == QSV_GATE_DIAG1) {
-        const double2 d0 = make_double2(m[0], m[1]), d1 = make_double2(m[2], m[3]);
-        if (active) {
-          for (uint32_t it = 0; it < iters; it++) {
-            const uint32_t li = tid + it * kPT;
-            const uint32_t s = s_tid ^ swz_it[it];
-            tile[s] = cmul(((li >> op.t0) & 1u) ? d1 : d0, tile[s]);
-          }
-        }
-      } else if (kind == QSV_GATE_DIAG2) {
-        double2 dd[4];
+        if (rec.kind == QSV_GATE_DENSE2) {
+          // ---- FP64 tensor path: 8 groups per warp step, up to 4 steps per sub-cube ----
+          const double b0 = frag[o][lane], b1 = frag[o][32 + lane];
+          const uint32_t v = opl[o][lane];
+          const uint32_t a_ld = (s_w ^ (v & 0xffffu)) << 4;  // byte offsets of 16-byte slots
+          const uint32_t a_st = (s_w ^ (v >> 16)) << 4;
+          const uint32_t z1b = (uint32_t)rec.z1 << 4;
+          if (rec.ngl == 5u) {
+            const uint32_t c3 = (uint32_t)rec.c3 << 4, c4 = (uint32_t)rec.c4 << 4;
+            const uint32_t xo[4] = {0u, c3, c4, c3 ^ c4};
+            double x0[4], x1[4];
 #pragma unroll
-        for (int i = 0; i < 4; i++) dd[i] = make_double2(m[2 * i], m[2 * i + 1]);
-        if (active) {
-          for (uint32_t it = 0; it < iters; it++) {
-            const uint32_t li = tid + it * kPT;
-            const uint32_t s = s_tid ^ swz_it[it];
-            const uint32_t c = ((li >> op.t0) & 1u) | (((li >> op.t1) & 1u) << 1);
-            const double2 f = c == 0 ? dd[0] : (c == 1 ? dd[1] : (c == 2 ? dd[2] : dd[3]));
-            tile[s] = cmul(f, tile[s]);
+            for (int it = 0; it < 4; it++) {
+              const uint32_t a = a_ld ^ xo[it];
+              x0[it] = *reinterpret_cast<const double*>(tb8 + a);
+              x1[it] = *reinterpret_cast<const double*>(tb8 + (a ^ z1b));
+            }
+#pragma unroll
+            for (int it = 0; it < 4; it++) {
+              double d0 = 0.0, d1 = 0.0;
+              dmma884(d0, d1, x0[it], b0);
+              dmma884(d0, d1, x1[it], b1);
+              *reinterpret_cast<double2*>(reinterpret_cast<char*>(tile) + (a_st ^ xo[it])) = make_double2(d0, d1);
+            }
+          } else {
+            const uint32_t ng = 1u << rec.ngl;
+            const uint32_t n_it = ng > 8u ? (ng >> 3) : 1u;
+            for (uint32_t it = 0; it < n_it; it++) {
+              uint32_t xo = 0;
+              if (it & 1u) xo ^= (uint32_t)rec.c3 << 4;
+              if (it & 2u) xo ^= (uint32_t)rec.c4 << 4;
+              const bool valid = (g | (it << 3)) < ng;
+              double x0 = 0.0, x1 = 0.0;
+              if (valid) {
+                const uint32_t a = a_ld ^ xo;
+                x0 = *reinterpret_cast<const double*>(tb8 + a);
+                x1 = *reinterpret_cast<const double*>(tb8 + (a ^ z1b));
+              }
+              double d0 = 0.0, d1 = 0.0;
+              dmma884(d0, d1, x0, b0);
+              dmma884(d0, d1, x1, b1);
+              if (valid) *reinterpret_cast<double2*>(reinterpret_cast<char*>(tile) + (a_st ^ xo)) = make_double2(d0, d1);
+            }
           }
-        }
-      } else if (kind == QSV_GATE_CX) {
-        // control t0 = 1: swap the target-0 and target-1 amplitudes
-        const uint32_t zc = op.z0, zt = op.z1;
-        const uint32_t s_w = (uint32_t)tab[o][lane] ^ (uint32_t)tab[o][32 + wid] ^ zc;
-        uint32_t it = 0;
-        for (uint32_t w = tid; w < ngroups; w += kPT, it++) {
-          const uint32_t s1 = s_w ^ (uint32_t)tab[o][48 + it];
-          const uint32_t s3 = s1 ^ zt;
-          const double2 a = tile[s1], c = tile[s3];
-          tile[s1] = c;
-          tile[s3] = a;
+        } else {
+          // ---- element-wise kinds: each lane owns elements e = lane | it << 5 of the sub-cube ----
+          const uint32_t n_el = 1u << n_inner;
+          const uint32_t lv = wv ^ st_lane[sidx][lane];  // li (low 16) and slot (high 16): disjoint bits, XOR == OR
+          const double* m = d.mats + rec.moff;
+          for (uint32_t it = 0; it < 4u; it++) {
+            if ((lane | (it << 5)) >= n_el) break;
+            const uint32_t ev = lv ^ st_it[sidx][it];
+            const uint32_t li = ev & 0xffffu, s = ev >> 16;
+            if (rec.kind == QSV_GATE_DIAG1) {
+              const double* f = m + 2 * ((li >> rec.t0) & 1u);
+              tile[s] = cmul(make_double2(f[0], f[1]), tile[s]);
+            } else if (rec.kind == QSV_GATE_DIAG2) {
+              const double* f = m + 2 * (((li >> rec.t0) & 1u) | (((li >> rec.t1) & 1u) << 1));
+              tile[s] = cmul(make_double2(f[0], f[1]), tile[s]);
+            } else if (rec.kind == QSV_GATE_CX) {
+              // control t0 set, target t1 clear: swap with the target-set partner (same sub-cube)
+              if (((li >> rec.t0) & 1u) && !((li >> rec.t1) & 1u)) {
+                const uint32_t sp = s ^ rec.z1;
+                const double2 a = tile[s], p = tile[sp];
+                tile[s] = p;
+                tile[sp] = a;
+              }
+            } else if (rec.kind == QSV_GATE_DENSE1) {
+              // scalar 2x2 (only used when the tile has a single qubit): element with t0 clear owns the pair
+              if (!((li >> rec.t0) & 1u)) {
+                const uint32_t sp = s ^ rec.z0;
+                const double2 a0 = tile[s], a1 = tile[sp];
+                double2 r0 = cmul(make_double2(m[0], m[1]), a0), r1 = cmul(make_double2(m[4], m[5]), a0);
+                cfma(r0, make_double2(m[2], m[3]), a1);
+                cfma(r1, make_double2(m[6], m[7]), a1);
+                tile[s] = r0;
+                tile[sp] = r1;
+              }
+            }
+          }
         }
       }
     }
@@ -271,9 +327,9 @@ tile_pass_kernel(double2* __restrict__ sv, const __grid_constant__ PassDesc d) {
 
     // ---- write-back: one HBM write of the tile ----
     if (active) {
-      double2* g = sv + base_cur + lo_off;
+      double2* gp = sv + base_cur + lo_off;
 #pragma unroll 4
-      for (uint32_t it = 0; it < iters; it++) g[hi_off[it]] = tile[s_tid ^ swz_it[it]];
+      for (uint32_t it = 0; it < iters; it++) gp[hi_off[it]] = tile[s_tid ^ swz_it[it]];
     }
     __syncthreads();  // the next iteration prefetches into this buffer
   }
@@ -369,98 +425,57 @@ static int grid_for(u64 n_amps) {
   return (int)std::max<u64>(1, std::min(blocks, cap));
 }
 
-static inline int bank_vec(const PassDesc& d, int bit) { return d.vec[bit] & 7; }
+// ------------------------------------------------------------------------------------------------
+// Host-side lowering of a pass: stages, bank vectors, XOR masks.
+// ------------------------------------------------------------------------------------------------
+struct HostOp {
+  int kind, t0, t1;
+  uint32_t touch;  // every tile bit the gate reads (ordering)
+  uint32_t need;   // tile bits that must be inner bits of the gate's stage
+  int moff;
+};
 
 static inline bool independent3(int a, int b, int c) {
   // three vectors of GF(2)^3 are independent iff none is zero, all differ, and c != a ^ b
   return a && b && c && a != b && a != c && b != c && c != (a ^ b);
 }
 
-// Choose the pass-specific bank vectors: bits 0..2 are the identity; every higher tile bit gets a
-// non-zero vector such that, where possible, the two bits of each dense gate get different vectors.
-static void choose_bank_vectors(PassDesc& d, int n_ops, const uint8_t* t0s, const uint8_t* t1s,
-                                const uint8_t* dense) {
-  const int b = d.b;
-  for (int j = 0; j < 16; j++) d.vec[j] = (uint8_t)(1u << (j % 3));
-  auto conflicts = [&]() {
-    int c = 0;
-    for (int i = 0; i < n_ops; i++)
-      if (dense[i] && d.vec[t0s[i]] == d.vec[t1s[i]]) c++;
-    return c;
-  };
-  int best = conflicts();
-  for (int round = 0; round < 4 && best > 0; round++) {
-    for (int i = 0; i < n_ops && best > 0; i++) {
-      if (!dense[i] || d.vec[t0s[i]] != d.vec[t1s[i]]) continue;
-      const int cand[2] = {t1s[i], t0s[i]};
-      for (int ci = 0; ci < 2 && d.vec[t0s[i]] == d.vec[t1s[i]]; ci++) {
-        const int bit = cand[ci];
-        if (bit < 3 || bit >= b) continue;
-        const uint8_t old = d.vec[bit];
-        uint8_t best_v = old;
-        for (uint8_t v = 1; v < 8; v++) {
-          d.vec[bit] = v;
-          const int c = conflicts();
-          if (c < best) {
-            best = c;
-            best_v = v;
-          }
-        }
-        d.vec[bit] = best_v;
+static inline int popc(uint32_t x) { return __builtin_popcount(x); }
+
+// Greedy staging, same commutation rule as the planner: a gate may be hoisted into the current stage
+// only over gates that touch none of its bits.
+static int build_stages(const HostOp* ops, int n_ops, int b, int* order, PassStage* stages, uint32_t* inner_masks) {
+  const int n_inner = std::min(b, kInner);
+  bool done[kMaxOps] = {false};
+  int n_done = 0, n_stages = 0, pos = 0;
+  while (n_done < n_ops) {
+    uint32_t inner = 0, blocked = 0;
+    const int first = pos;
+    for (int i = 0; i < n_ops; i++) {
+      if (done[i]) continue;
+      const HostOp& op = ops[i];
+      if (!(op.touch & blocked) && popc(inner | op.need) <= n_inner) {
+        inner |= op.need;
+        done[i] = true;
+        n_done++;
+        order[pos++] = i;
+      } else {
+        blocked |= op.touch;
       }
     }
+    // pad the inner set with the lowest unused tile bits
+    for (int j = 0; j < b && popc(inner) < n_inner; j++)
+      if (!((inner >> j) & 1u)) inner |= 1u << j;
+    PassStage& st = stages[n_stages];
+    memset(&st, 0, sizeof(st));
+    st.first_op = (uint8_t)first;
+    st.n_ops = (uint8_t)(pos - first);
+    st.n_inner = (uint8_t)n_inner;
+    st.n_outer = (uint8_t)(b - n_inner);
+    inner_masks[n_stages] = inner;
+    n_stages++;
   }
-}
-
-// Order the free (non-gate) tile bits of an op for its group index and fill op->col / nbits / lb.
-// The first group-index bits are the ones that vary across the lanes served by one shared-memory
-// wavefront, so they are chosen with linearly independent bank vectors:
-//   DMMA dense gate : {f0, t0, t1} independent (STS.128 of a quarter warp: 2 groups x 4 amplitudes)
-//                     {f0, f1, t0} independent (LDS.64 of a half warp: 4 groups x 2 amplitudes)
-//   other gates     : {f0, f1, f2} independent (LDS/STS.128 of a quarter warp: 8 groups)
-static void build_group_map(const PassDesc& d, uint32_t gate_mask, bool dmma, PassOp* op) {
-  const int b = d.b;
-  int freeb[16], nf = 0;
-  for (int j = 0; j < b; j++)
-    if (!((gate_mask >> j) & 1u)) freeb[nf++] = j;
-  int lead[3] = {-1, -1, -1};
-  if (dmma) {
-    const int v0 = bank_vec(d, op->t0), v1 = bank_vec(d, op->t1);
-    for (int i = 0; i < nf && lead[0] < 0; i++)
-      if (independent3(bank_vec(d, freeb[i]), v0, v1)) lead[0] = freeb[i];
-    if (lead[0] < 0) {  // t0/t1 share a vector (or tiny tile): at least avoid t0's vector
-      for (int i = 0; i < nf && lead[0] < 0; i++)
-        if (bank_vec(d, freeb[i]) != v0) lead[0] = freeb[i];
-    }
-    if (lead[0] >= 0) {
-      for (int i = 0; i < nf && lead[1] < 0; i++)
-        if (freeb[i] != lead[0] && independent3(bank_vec(d, lead[0]), bank_vec(d, freeb[i]), v0)) lead[1] = freeb[i];
-    }
-  } else {
-    for (int i0 = 0; i0 < nf && lead[2] < 0; i0++)
-      for (int i1 = i0 + 1; i1 < nf && lead[2] < 0; i1++)
-        for (int i2 = i1 + 1; i2 < nf && lead[2] < 0; i2++)
-          if (independent3(bank_vec(d, freeb[i0]), bank_vec(d, freeb[i1]), bank_vec(d, freeb[i2]))) {
-            lead[0] = freeb[i0];
-            lead[1] = freeb[i1];
-            lead[2] = freeb[i2];
-          }
-  }
-  int order[16], no = 0;
-  bool taken[16] = {false};
-  for (int k = 0; k < 3; k++) {
-    if (lead[k] < 0) continue;
-    bool dup = false;
-    for (int q = 0; q < no; q++) dup |= (order[q] == lead[k]);
-    if (dup) continue;
-    order[no++] = lead[k];
-    taken[lead[k]] = true;
-  }
-  for (int i = 0; i < nf; i++)
-    if (!taken[freeb[i]]) order[no++] = freeb[i];
-  op->nbits = (uint8_t)nf;
-  op->lb = dmma ? 3 : 5;
-  for (int j = 0; j < 13; j++) op->col[j] = j < nf ? (uint16_t)swz(d.vec, b, 1u << order[j]) : 0;
+  return n_stages;
 }
 
 static bool g_attr_set[64] = {false};
@@ -502,32 +517,34 @@ static int launch_pass(double* sv, int n, const int32_t* tile_qubits, int n_tile
 
   static thread_local PassDesc d;
   memset(&d, 0, sizeof(d));
+  const int b = n_tile;
   d.n = n;
-  d.b = n_tile;
+  d.b = b;
   int sorted[16];
-  for (int j = 0; j < n_tile; j++) {
+  for (int j = 0; j < b; j++) {
     if (tile_qubits[j] < 0 || tile_qubits[j] >= n) return fail(QSV_EINVAL, "qsv_apply_pass: tile qubit out of range");
     sorted[j] = tile_qubits[j];
   }
-  std::sort(sorted, sorted + n_tile);
-  for (int j = 0; j + 1 < n_tile; j++)
+  std::sort(sorted, sorted + b);
+  for (int j = 0; j + 1 < b; j++)
     if (sorted[j] == sorted[j + 1]) return fail(QSV_EINVAL, "qsv_apply_pass: duplicate tile qubit");
   int local_of[64];
   for (int q = 0; q < 64; q++) local_of[q] = -1;
-  for (int j = 0; j < n_tile; j++) {
+  for (int j = 0; j < b; j++) {
     d.tb[j] = (uint8_t)sorted[j];
     local_of[sorted[j]] = j;
   }
-  // first pass over the gates: kinds, tile-local bits, matrices (1-qubit dense gates are widened to
-  // I (x) M on a partner bit so that they run on the same FP64 tensor path as 2-qubit gates)
+
+  // ---- gates -> host ops (tile-local bits, matrices) ----
+  HostOp hops[kMaxOps];
+  double mats[kMaxMat];
   int moff = 0;
-  uint8_t t0s[kMaxOps], t1s[kMaxOps], dense[kMaxOps];
   for (int i = 0; i < n_gates; i++) {
     const qsv_gate_t& gsrc = gates[i];
-    PassOp& op = d.ops[i];
+    HostOp& op = hops[i];
     int nq, ndbl;
     switch (gsrc.kind) {
-      case QSV_GATE_DENSE1: nq = 1; ndbl = 8; break;
+      case QSV_GATE_DENSE1: nq = 1; ndbl = b >= 2 ? 32 : 8; break;
       case QSV_GATE_DENSE2: nq = 2; ndbl = 32; break;
       case QSV_GATE_DIAG1: nq = 1; ndbl = 4; break;
       case QSV_GATE_DIAG2: nq = 2; ndbl = 8; break;
@@ -538,48 +555,170 @@ static int launch_pass(double* sv, int n, const int32_t* tile_qubits, int n_tile
       return fail(QSV_EINVAL, "qsv_apply_pass: gate qubit q0 is not a tile qubit");
     if (nq == 2 && (gsrc.q1 < 0 || gsrc.q1 >= n || local_of[gsrc.q1] < 0 || gsrc.q1 == gsrc.q0))
       return fail(QSV_EINVAL, "qsv_apply_pass: gate qubit q1 is not a tile qubit / equals q0");
-    op.kind = (uint8_t)gsrc.kind;
-    op.t0 = (uint8_t)local_of[gsrc.q0];
-    op.t1 = (uint8_t)(nq == 2 ? local_of[gsrc.q1] : 0);
-    op.moff = (uint16_t)moff;
-    if (gsrc.kind == QSV_GATE_DENSE1 && n_tile >= 2) {
-      // partner = the next tile bit (cyclically); matrix index bit 1 = partner: kron(I2, M)
-      op.kind = QSV_GATE_DENSE2;
-      op.t1 = (uint8_t)((op.t0 + 1) % n_tile);
-      ndbl = 32;
-      if (moff + ndbl > kMaxMat) return fail(QSV_ERANGE, "qsv_apply_pass: matrix payload too large");
-      double* m4 = d.mats + moff;
-      for (int r = 0; r < 4; r++)
-        for (int c = 0; c < 4; c++) {
-          const bool same = (r >> 1) == (c >> 1);
-          m4[2 * (4 * r + c)] = same ? gsrc.m[2 * (2 * (r & 1) + (c & 1))] : 0.0;
-          m4[2 * (4 * r + c) + 1] = same ? gsrc.m[2 * (2 * (r & 1) + (c & 1)) + 1] : 0.0;
-        }
+    if (moff + ndbl > kMaxMat) return fail(QSV_ERANGE, "qsv_apply_pass: matrix payload too large");
+    op.kind = gsrc.kind;
+    op.t0 = local_of[gsrc.q0];
+    op.t1 = nq == 2 ? local_of[gsrc.q1] : -1;
+    op.moff = moff;
+    op.touch = 1u << op.t0;
+    if (nq == 2) op.touch |= 1u << op.t1;
+    switch (gsrc.kind) {
+      case QSV_GATE_DENSE2: op.need = op.touch; break;
+      case QSV_GATE_DENSE1: op.need = 1u << op.t0; break;
+      case QSV_GATE_CX: op.need = 1u << op.t1; break;  // target; the control may be any tile bit
+      default: op.need = 0; break;                      // diagonal gates need no particular partition
+    }
+    if (gsrc.kind == QSV_GATE_DENSE1 && b >= 2) {
+      memset(mats + moff, 0, sizeof(double) * 32);  // widened once the partner bit is known
+      memcpy(mats + moff, gsrc.m, sizeof(double) * 8);
     } else {
-      if (moff + ndbl > kMaxMat) return fail(QSV_ERANGE, "qsv_apply_pass: matrix payload too large");
-      memcpy(d.mats + moff, gsrc.m, sizeof(double) * ndbl);
+      memcpy(mats + moff, gsrc.m, sizeof(double) * ndbl);
     }
     moff += ndbl;
-    t0s[i] = op.t0;
-    t1s[i] = op.t1;
-    dense[i] = op.kind == QSV_GATE_DENSE2;
   }
-  choose_bank_vectors(d, n_gates, t0s, t1s, dense);
-  for (int i = 0; i < n_gates; i++) {
-    PassOp& op = d.ops[i];
-    const bool two = !(op.kind == QSV_GATE_DENSE1 || op.kind == QSV_GATE_DIAG1);
-    uint32_t gmask = 1u << op.t0;
-    if (two) gmask |= 1u << op.t1;
-    op.z0 = (uint16_t)swz(d.vec, n_tile, 1u << op.t0);
-    op.z1 = (uint16_t)swz(d.vec, n_tile, 1u << op.t1);
-    build_group_map(d, gmask, op.kind == QSV_GATE_DENSE2, &op);
-  }
-  if (n_gates == 0) choose_bank_vectors(d, 0, t0s, t1s, dense);
+
+  // ---- stages ----
+  int order[kMaxOps];
+  uint32_t inner_masks[kMaxStages];
+  const int n_stages = build_stages(hops, n_gates, b, order, d.stages, inner_masks);
+  d.nstages = n_stages;
   d.nops = n_gates;
 
+  // ops in stage order; 1-qubit dense gates are widened to I (x) M on a partner inner bit so that they
+  // run on the same FP64 tensor path as 2-qubit gates
+  int stage_of[kMaxOps];
+  for (int s = 0; s < n_stages; s++)
+    for (int k = d.stages[s].first_op; k < d.stages[s].first_op + d.stages[s].n_ops; k++) stage_of[k] = s;
+  HostOp sops[kMaxOps];
+  for (int k = 0; k < n_gates; k++) {
+    sops[k] = hops[order[k]];
+    HostOp& op = sops[k];
+    if (op.kind == QSV_GATE_DENSE1 && b >= 2) {
+      const uint32_t inner = inner_masks[stage_of[k]];
+      int partner = -1;
+      for (int j = 0; j < b && partner < 0; j++)
+        if (((inner >> j) & 1u) && j != op.t0) partner = j;
+      double m2[8];
+      memcpy(m2, mats + op.moff, sizeof(m2));
+      double* m4 = mats + op.moff;
+      for (int r = 0; r < 4; r++)
+        for (int cc = 0; cc < 4; cc++) {
+          const bool same = (r >> 1) == (cc >> 1);
+          m4[2 * (4 * r + cc)] = same ? m2[2 * (2 * (r & 1) + (cc & 1))] : 0.0;
+          m4[2 * (4 * r + cc) + 1] = same ? m2[2 * (2 * (r & 1) + (cc & 1)) + 1] : 0.0;
+        }
+      op.kind = QSV_GATE_DENSE2;
+      op.t1 = partner;
+    }
+  }
+  memcpy(d.mats, mats, sizeof(double) * moff);
+
+  // ---- bank vectors: the two bits of every dense gate should differ ----
+  for (int j = 0; j < 16; j++) d.vec[j] = (uint8_t)(1u << (j % 3));
+  {
+    auto conflicts = [&]() {
+      int cnt = 0;
+      for (int k = 0; k < n_gates; k++)
+        if (sops[k].kind == QSV_GATE_DENSE2 && d.vec[sops[k].t0] == d.vec[sops[k].t1]) cnt++;
+      return cnt;
+    };
+    int best = conflicts();
+    for (int round = 0; round < 4 && best > 0; round++) {
+      for (int k = 0; k < n_gates && best > 0; k++) {
+        if (sops[k].kind != QSV_GATE_DENSE2 || d.vec[sops[k].t0] != d.vec[sops[k].t1]) continue;
+        const int cand[2] = {sops[k].t1, sops[k].t0};
+        for (int ci = 0; ci < 2 && d.vec[sops[k].t0] == d.vec[sops[k].t1]; ci++) {
+          const int bit = cand[ci];
+          if (bit < 3) continue;
+          uint8_t best_v = d.vec[bit];
+          for (uint8_t v = 1; v < 8; v++) {
+            d.vec[bit] = v;
+            const int cnt = conflicts();
+            if (cnt < best) {
+              best = cnt;
+              best_v = v;
+            }
+          }
+          d.vec[bit] = best_v;
+        }
+      }
+    }
+  }
+  auto bvec = [&](int bit) { return (int)(d.vec[bit] & 7); };
+  auto sw1 = [&](int bit) { return (uint16_t)swz(d.vec, b, 1u << bit); };
+
+  // ---- per-stage element order and per-op group order ----
+  for (int s = 0; s < n_stages; s++) {
+    PassStage& st = d.stages[s];
+    const uint32_t inner = inner_masks[s];
+    int ib[16], ni = 0, ob[16], no = 0;
+    for (int j = 0; j < b; j++) {
+      if ((inner >> j) & 1u) ib[ni++] = j;
+      else ob[no++] = j;
+    }
+    // element order: three inner bits with independent bank vectors first (quarter-warp accesses)
+    int lead[3] = {-1, -1, -1};
+    for (int i0 = 0; i0 < ni && lead[2] < 0; i0++)
+      for (int i1 = i0 + 1; i1 < ni && lead[2] < 0; i1++)
+        for (int i2 = i1 + 1; i2 < ni && lead[2] < 0; i2++)
+          if (independent3(bvec(ib[i0]), bvec(ib[i1]), bvec(ib[i2]))) {
+            lead[0] = ib[i0];
+            lead[1] = ib[i1];
+            lead[2] = ib[i2];
+          }
+    int eo[16], ne = 0;
+    for (int k = 0; k < 3; k++)
+      if (lead[k] >= 0) eo[ne++] = lead[k];
+    for (int i = 0; i < ni; i++) {
+      bool dup = false;
+      for (int q = 0; q < ne; q++) dup |= (eo[q] == ib[i]);
+      if (!dup) eo[ne++] = ib[i];
+    }
+    for (int j = 0; j < kInner; j++) {
+      st.ebit[j] = (uint8_t)(j < ni ? eo[j] : 0);
+      st.ecol[j] = j < ni ? sw1(eo[j]) : 0;
+    }
+    for (int j = 0; j < 5; j++) {
+      st.obit[j] = (uint8_t)(j < no ? ob[j] : 0);
+      st.ocol[j] = j < no ? sw1(ob[j]) : 0;
+    }
+    for (int k = st.first_op; k < st.first_op + st.n_ops; k++) {
+      const HostOp& h = sops[k];
+      PassOp& op = d.ops[k];
+      op.kind = (uint8_t)h.kind;
+      op.t0 = (uint8_t)h.t0;
+      op.t1 = (uint8_t)(h.t1 < 0 ? 0 : h.t1);
+      op.moff = (uint16_t)h.moff;
+      op.z0 = sw1(h.t0);
+      op.z1 = h.t1 < 0 ? 0 : sw1(h.t1);
+      if (h.kind != QSV_GATE_DENSE2) continue;
+      // free inner bits of the gate: f0 with {f0,t0,t1} independent (STS.128: 2 groups x 4 amplitudes per
+      // quarter warp), f1 with {f0,f1,t0} independent (LDS.64: 4 groups x 2 amplitudes per half warp)
+      int fb[16], nf = 0;
+      for (int i = 0; i < ni; i++)
+        if (ib[i] != h.t0 && ib[i] != h.t1) fb[nf++] = ib[i];
+      const int v0 = bvec(h.t0), v1 = bvec(h.t1);
+      int f0 = -1, f1 = -1;
+      for (int i = 0; i < nf && f0 < 0; i++)
+        if (independent3(bvec(fb[i]), v0, v1)) f0 = fb[i];
+      for (int i = 0; i < nf && f0 < 0; i++)
+        if (bvec(fb[i]) != v0) f0 = fb[i];
+      if (f0 >= 0)
+        for (int i = 0; i < nf && f1 < 0; i++)
+          if (fb[i] != f0 && independent3(bvec(f0), bvec(fb[i]), v0)) f1 = fb[i];
+      int fo[16], nfo = 0;
+      if (f0 >= 0) fo[nfo++] = f0;
+      if (f1 >= 0) fo[nfo++] = f1;
+      for (int i = 0; i < nf; i++)
+        if (fb[i] != f0 && fb[i] != f1) fo[nfo++] = fb[i];
+      op.ngl = (uint8_t)nf;
+      for (int j = 0; j < 5; j++) op.col[j] = j < nf ? sw1(fo[j]) : 0;
+    }
+  }
+
   if (int rc = ensure_attrs()) return rc;
-  const size_t smem = 2 * (sizeof(double2) << n_tile);
-  d.n_tiles = 1u << (n - n_tile);
+  const size_t smem = 2 * (sizeof(double2) << b);
+  d.n_tiles = 1u << (n - b);
   const unsigned grid = std::min<unsigned>(d.n_tiles, (unsigned)sm_count());
   tile_pass_kernel<<<grid, kPT, smem, stream>>>(reinterpret_cast<double2*>(sv), d);
   QSV_LAUNCHED();
