@@ -8,10 +8,11 @@
 // out-of-place np.einsum over the whole vector.
 //
 // Kernel structure (tile_pass_kernel):
-//   * persistent: one 1024-thread CTA per SM walks tiles c, c+grid, ...; the cp.async loads of the
-//     next tile stream into a second shared-memory buffer while the gates of the current one run;
-//   * the gates of a pass are grouped into STAGES.  In a stage every warp owns a sub-cube of 2^7
-//     amplitudes of the tile (7 "inner" tile bits; the warp id supplies the other 5) and applies all
+//   * persistent: 2-4 CTAs per SM (one warp per 2^8 amplitudes of the tile), each walking a contiguous
+//     range of tiles with one tile buffer; while one CTA waits for HBM (cp.async load, write-back) the
+//     others run their gates, so memory phases overlap FP64 / shared-memory phases across CTAs;
+//   * the gates of a pass are grouped into STAGES.  In a stage every warp owns a sub-cube of 2^8
+//     amplitudes of the tile (8 "inner" tile bits; the warp id supplies the others) and applies all
 //     the stage's gates -- whose qubits are inner bits -- to it with only __syncwarp() between gates.
 //     Warps therefore drift apart and the shared-memory traffic of one warp overlaps the FP64 tensor
 //     work of another; block-wide barriers are needed only between stages;
@@ -22,6 +23,7 @@
 //     34 TF/s, no gain from mixing them -- tools/fp64_peak.cu -- but DMMA needs 8x fewer instructions
 //     and 2 registers of gate matrix per lane instead of 64.)
 //   * all index maps are linear over GF(2) (XOR masks), including a pass-specific bank swizzle.
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -35,24 +37,24 @@ unsigned long long g_launches = 0;
 
 constexpr int kMaxOps = QSV_MAX_PASS_GATES;
 constexpr int kMaxMat = 1536;  // doubles of matrix payload per pass (48 dense 2-qubit gates)
-constexpr int kPT = 1024;      // threads of the persistent pass kernel (32 warps, one CTA per SM)
-constexpr int kTidBits = 10;
-constexpr int kInner = 7;      // inner bits of a stage: 2^7 amplitudes per warp
+constexpr int kMaxPT = 512;    // threads of the pass kernel: 2^(b-3), at most 512 (one warp per 2^8 amplitudes)
+constexpr int kWarps = kMaxPT / 32;
+constexpr int kInner = 8;      // inner bits of a stage: 2^8 amplitudes per warp
 constexpr int kMaxStages = kMaxOps;
 
 struct __align__(4) PassOp {
   uint8_t kind, t0, t1, ngl;  // t0/t1: tile-local gate bits; ngl = log2(#groups in a warp's sub-cube)
   uint16_t moff;              // offset (doubles) of the matrix in PassDesc::mats
   uint16_t z0, z1;            // swz(1 << t0), swz(1 << t1)
-  uint16_t col[5];            // swizzled masks of the free inner bits: col[0..2] vary inside a warp step
+  uint16_t col[6];            // swizzled masks of the free inner bits: col[0..2] vary inside a warp step
 };
 
 struct __align__(4) PassStage {
   uint8_t first_op, n_ops, n_inner, n_outer;
   uint8_t ebit[kInner];   // inner tile bits in element order (bit j of the in-warp element index)
-  uint8_t obit[5];        // outer tile bits (bit j of the warp id)
+  uint8_t obit[4];        // outer tile bits (bit j of the warp id)
   uint16_t ecol[kInner];  // swz(1 << ebit[j])
-  uint16_t ocol[5];       // swz(1 << obit[j])
+  uint16_t ocol[4];       // swz(1 << obit[j])
 };
 
 struct PassDesc {
@@ -103,34 +105,46 @@ __device__ __forceinline__ u64 tile_base(const PassDesc& d, u64 t) {
 
 // Per-op record staged in shared memory (one broadcast 16-byte load per op per warp).
 struct __align__(16) OpRec {
-  uint16_t z0, z1, c3, c4;
+  uint16_t z0, z1, c3, c4, c5;
   uint8_t kind, ngl, t0, t1;
-  uint16_t moff, pad;
+  uint16_t moff;
 };
 
-__global__ void __launch_bounds__(kPT, 1)
+// Persistent kernel, two 512-thread CTAs per SM, one 64 KiB tile buffer each: while one CTA waits for
+// HBM (cp.async load of its next tile, write-back of the last) the other one runs its gates, so the
+// memory phases of one overlap the FP64 / shared-memory phases of the other.  A CTA owns a contiguous
+// range of tiles.
+__global__ void __launch_bounds__(kMaxPT, 2)
 tile_pass_kernel(double2* __restrict__ sv, const __grid_constant__ PassDesc d) {
-  extern __shared__ double2 smem[];
-  __shared__ u64 hi_off[4];
-  __shared__ uint16_t swz_it[4];
-  __shared__ double frag[kMaxOps][64];       // per dense op: B fragments of the two k-slices, frag[s*32 + lane]
-  __shared__ OpRec oprec[kMaxOps];
-  __shared__ uint32_t opl[kMaxOps][32];      // per op, per lane: (load slot ^ s_w) | (store slot ^ s_w) << 16
-  __shared__ uint32_t st_warp[kMaxStages][32];  // per stage, per warp: li_w | s_w << 16
-  __shared__ uint32_t st_lane[kMaxStages][32];  // per stage, per lane: li part | slot part << 16 (element lane | it<<5, it = 0)
-  __shared__ uint32_t st_it[kMaxStages][4];     // per stage, per element iteration: li part | slot part << 16
+  // dynamic shared memory: the tile, then the per-pass tables (sized by the pass, so that short passes
+  // leave room for more resident CTAs)
+  extern __shared__ double2 tile[];
+  __shared__ u64 hi_off[8];
+  __shared__ uint16_t swz_it[8];
+  const int nops_all = d.nops, nst_all = d.nstages;
+  double (*frag)[64] = reinterpret_cast<double (*)[64]>(tile + (1u << d.b));   // [nops][64] B fragments
+  OpRec* oprec = reinterpret_cast<OpRec*>(frag + nops_all);                     // [nops]
+  uint32_t (*opl)[32] = reinterpret_cast<uint32_t (*)[32]>(oprec + nops_all);   // [nops][32] lane slots
+  uint32_t (*st_warp)[kWarps] = reinterpret_cast<uint32_t (*)[kWarps]>(opl + nops_all);  // [nstages][16]
+  uint32_t (*st_lane)[32] = reinterpret_cast<uint32_t (*)[32]>(st_warp + nst_all);       // [nstages][32]
+  uint32_t (*st_it)[8] = reinterpret_cast<uint32_t (*)[8]>(st_lane + nst_all);           // [nstages][8]
 
   const uint32_t tid = threadIdx.x;
   const int b = d.b;
   const uint32_t tile_amps = 1u << b;
-  const int nops = d.nops, nstages = d.nstages;
+  const uint32_t dbg = d.pad2[0];  // QSV_DEBUG_FLAGS (profiling experiments): 1 = no write-back, 2 = no loads, 4 = no gates
+  const int nops = d.nops, nstages = (dbg & 4u) ? 0 : d.nstages;
 
   // ---- per-kernel setup (amortised over all tiles of this CTA): every lane/warp dependent index of
   // the pass is tile-invariant, so it is digested once into shared-memory tables ----
+  const uint32_t kPT = blockDim.x;
+  const int kTidBits = 31 - __clz(kPT);
   const int lo_bits = b < kTidBits ? b : kTidBits;
   u64 lo_off = 0;
   for (int j = 0; j < lo_bits; j++) lo_off |= (u64)((tid >> j) & 1u) << d.tb[j];
-  if (tid < 4) {
+  u64 tile_mask = 0;  // physical bit mask of the tile qubits
+  for (int j = 0; j < b; j++) tile_mask |= 1ull << d.tb[j];
+  if (tid < 8) {
     u64 off = 0;
     for (int j = kTidBits; j < b; j++) off |= (u64)((tid >> (j - kTidBits)) & 1u) << d.tb[j];
     hi_off[tid] = off;
@@ -162,72 +176,58 @@ tile_pass_kernel(double2* __restrict__ sv, const __grid_constant__ PassDesc d) {
     }
     if (e == 32) {
       OpRec r;
-      r.z0 = op.z0; r.z1 = op.z1; r.c3 = op.col[3]; r.c4 = op.col[4];
+      r.z0 = op.z0; r.z1 = op.z1; r.c3 = op.col[3]; r.c4 = op.col[4]; r.c5 = op.col[5];
       r.kind = op.kind; r.ngl = op.ngl; r.t0 = op.t0; r.t1 = op.t1;
-      r.moff = op.moff; r.pad = 0;
+      r.moff = op.moff;
       oprec[o] = r;
     }
   }
-  for (int idx = tid; idx < nstages * 96; idx += kPT) {
-    const int sidx = idx / 96, e = idx % 96;
+  for (int idx = tid; idx < nstages * 64; idx += kPT) {
+    const int sidx = idx >> 6, e = idx & 63;
     const PassStage& st = d.stages[sidx];
     uint32_t li = 0, sl = 0;
-    if (e < 32) {  // warp part
+    if (e < kWarps) {  // warp part
       for (int j = 0; j < st.n_outer; j++)
         if ((e >> j) & 1) { li |= 1u << st.obit[j]; sl ^= st.ocol[j]; }
       st_warp[sidx][e] = li | (sl << 16);
-    } else if (e < 64) {  // lane part (element bits 0..4)
+    } else if (e >= 24 && e < 32) {  // element iteration part (element bits 5, 6, 7)
+      for (int j = 0; j < 3; j++)
+        if ((((e - 24) >> j) & 1) && 5 + j < st.n_inner) { li |= 1u << st.ebit[5 + j]; sl ^= st.ecol[5 + j]; }
+      st_it[sidx][e - 24] = li | (sl << 16);
+    } else if (e >= 32) {  // lane part (element bits 0..4)
       for (int j = 0; j < 5 && j < st.n_inner; j++)
         if (((e - 32) >> j) & 1) { li |= 1u << st.ebit[j]; sl ^= st.ecol[j]; }
       st_lane[sidx][e - 32] = li | (sl << 16);
-    } else if (e < 68) {  // element iteration part (element bits 5, 6)
-      for (int j = 0; j < 2; j++)
-        if ((((e - 64) >> j) & 1) && 5 + j < st.n_inner) { li |= 1u << st.ebit[5 + j]; sl ^= st.ecol[5 + j]; }
-      st_it[sidx][e - 64] = li | (sl << 16);
     }
   }
   const uint32_t s_tid = swz(d.vec, b, tid);
   const uint32_t iters = tile_amps > kPT ? tile_amps / kPT : 1;
   const bool active = tid < tile_amps;
+  const bool ld_on = active && !(dbg & 2u), st_on = active && !(dbg & 1u);
   const uint32_t lane = tid & 31u, wid = tid >> 5;
   const uint32_t g = lane >> 2;
-  const uint32_t half8 = (lane & 1u) * 8u;
+  const char* tb8 = reinterpret_cast<const char*>(tile) + (lane & 1u) * 8u;
   __syncthreads();
 
+  // contiguous range of tiles for this CTA; the tile base walks the non-tile bits: next = ((base | M) + 1) & ~M
   const u64 n_tiles = d.n_tiles;
-  u64 t = blockIdx.x;
-  u64 base_cur = 0, base_next = 0;
-  if (t < n_tiles) {
-    base_cur = tile_base(d, t);
-    if (active) {
-      const double2* gp = sv + base_cur + lo_off;
-#pragma unroll 4
-      for (uint32_t it = 0; it < iters; it++) cp_async16(smem + (s_tid ^ swz_it[it]), gp + hi_off[it]);
+  const u64 per = (n_tiles + gridDim.x - 1) / gridDim.x;
+  const u64 t_begin = (u64)blockIdx.x * per;
+  const u64 t_end = t_begin + per < n_tiles ? t_begin + per : n_tiles;
+  u64 base = t_begin < n_tiles ? tile_base(d, t_begin) : 0;
+  for (u64 t = t_begin; t < t_end; t++, base = ((base | tile_mask) + 1) & ~tile_mask) {
+    // ---- load: one HBM read of the tile ----
+    if (ld_on) {
+      const double2* gp = sv + base + lo_off;
+#pragma unroll 8
+      for (uint32_t it = 0; it < iters; it++) cp_async16(tile + (s_tid ^ swz_it[it]), gp + hi_off[it]);
     }
     cp_async_commit();
-  }
-  uint32_t cur = 0;
-  for (; t < n_tiles; t += gridDim.x, cur ^= 1u, base_cur = base_next) {
-    double2* tile = smem + (cur ? tile_amps : 0u);
-    const u64 t_next = t + gridDim.x;
-    if (t_next < n_tiles) {
-      base_next = tile_base(d, t_next);
-      if (active) {
-        double2* dst = smem + (cur ? 0u : tile_amps);
-        const double2* gp = sv + base_next + lo_off;
-#pragma unroll 4
-        for (uint32_t it = 0; it < iters; it++) cp_async16(dst + (s_tid ^ swz_it[it]), gp + hi_off[it]);
-      }
-      cp_async_commit();
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
-    const char* tb8 = reinterpret_cast<const char*>(tile) + half8;
+    cp_async_wait<0>();
 
     int o = 0;
     for (int sidx = 0; sidx < nstages; sidx++) {
-      __syncthreads();  // stage boundary: warps re-partition the tile
+      __syncthreads();  // stage boundary: warps re-partition the tile (the first one also publishes the loads)
       const uint32_t n_inner = d.stages[sidx].n_inner, n_outer = d.stages[sidx].n_outer;
       const int o_end = o + d.stages[sidx].n_ops;
       const bool warp_on = wid < (1u << n_outer);  // small tiles: fewer sub-cubes than warps
@@ -241,36 +241,41 @@ tile_pass_kernel(double2* __restrict__ sv, const __grid_constant__ PassDesc d) {
         first = false;
 
         if (rec.kind == QSV_GATE_DENSE2) {
-          // ---- FP64 tensor path: 8 groups per warp step, up to 4 steps per sub-cube ----
+          // ---- FP64 tensor path: 8 groups per warp step, up to 8 steps per sub-cube ----
           const double b0 = frag[o][lane], b1 = frag[o][32 + lane];
           const uint32_t v = opl[o][lane];
           const uint32_t a_ld = (s_w ^ (v & 0xffffu)) << 4;  // byte offsets of 16-byte slots
           const uint32_t a_st = (s_w ^ (v >> 16)) << 4;
           const uint32_t z1b = (uint32_t)rec.z1 << 4;
-          if (rec.ngl == 5u) {
-            const uint32_t c3 = (uint32_t)rec.c3 << 4, c4 = (uint32_t)rec.c4 << 4;
-            const uint32_t xo[4] = {0u, c3, c4, c3 ^ c4};
-            double x0[4], x1[4];
+          const uint32_t c3 = (uint32_t)rec.c3 << 4, c4 = (uint32_t)rec.c4 << 4, c5 = (uint32_t)rec.c5 << 4;
+          if (rec.ngl == 6u) {
 #pragma unroll
-            for (int it = 0; it < 4; it++) {
-              const uint32_t a = a_ld ^ xo[it];
-              x0[it] = *reinterpret_cast<const double*>(tb8 + a);
-              x1[it] = *reinterpret_cast<const double*>(tb8 + (a ^ z1b));
-            }
+            for (int hb = 0; hb < 2; hb++) {
+              const uint32_t xh = hb ? c5 : 0u;
+              const uint32_t xo[4] = {xh, xh ^ c3, xh ^ c4, xh ^ c3 ^ c4};
+              double x0[4], x1[4];
 #pragma unroll
-            for (int it = 0; it < 4; it++) {
-              double d0 = 0.0, d1 = 0.0;
-              dmma884(d0, d1, x0[it], b0);
-              dmma884(d0, d1, x1[it], b1);
-              *reinterpret_cast<double2*>(reinterpret_cast<char*>(tile) + (a_st ^ xo[it])) = make_double2(d0, d1);
+              for (int it = 0; it < 4; it++) {
+                const uint32_t a = a_ld ^ xo[it];
+                x0[it] = *reinterpret_cast<const double*>(tb8 + a);
+                x1[it] = *reinterpret_cast<const double*>(tb8 + (a ^ z1b));
+              }
+#pragma unroll
+              for (int it = 0; it < 4; it++) {
+                double d0 = 0.0, d1 = 0.0;
+                dmma884(d0, d1, x0[it], b0);
+                dmma884(d0, d1, x1[it], b1);
+                *reinterpret_cast<double2*>(reinterpret_cast<char*>(tile) + (a_st ^ xo[it])) = make_double2(d0, d1);
+              }
             }
           } else {
             const uint32_t ng = 1u << rec.ngl;
             const uint32_t n_it = ng > 8u ? (ng >> 3) : 1u;
             for (uint32_t it = 0; it < n_it; it++) {
               uint32_t xo = 0;
-              if (it & 1u) xo ^= (uint32_t)rec.c3 << 4;
-              if (it & 2u) xo ^= (uint32_t)rec.c4 << 4;
+              if (it & 1u) xo ^= c3;
+              if (it & 2u) xo ^= c4;
+              if (it & 4u) xo ^= c5;
               const bool valid = (g | (it << 3)) < ng;
               double x0 = 0.0, x1 = 0.0;
               if (valid) {
@@ -289,7 +294,7 @@ tile_pass_kernel(double2* __restrict__ sv, const __grid_constant__ PassDesc d) {
           const uint32_t n_el = 1u << n_inner;
           const uint32_t lv = wv ^ st_lane[sidx][lane];  // li (low 16) and slot (high 16): disjoint bits, XOR == OR
           const double* m = d.mats + rec.moff;
-          for (uint32_t it = 0; it < 4u; it++) {
+          for (uint32_t it = 0; it < 8u; it++) {
             if ((lane | (it << 5)) >= n_el) break;
             const uint32_t ev = lv ^ st_it[sidx][it];
             const uint32_t li = ev & 0xffffu, s = ev >> 16;
@@ -325,13 +330,13 @@ tile_pass_kernel(double2* __restrict__ sv, const __grid_constant__ PassDesc d) {
     }
     __syncthreads();
 
-    // ---- write-back: one HBM write of the tile ----
-    if (active) {
-      double2* gp = sv + base_cur + lo_off;
-#pragma unroll 4
+    // ---- write-back: one HBM write of the tile.  Every thread reads exactly the slots its own
+    // cp.async of the next tile will overwrite, so no barrier is needed after this phase ----
+    if (st_on) {
+      double2* gp = sv + base + lo_off;
+#pragma unroll 8
       for (uint32_t it = 0; it < iters; it++) gp[hi_off[it]] = tile[s_tid ^ swz_it[it]];
     }
-    __syncthreads();  // the next iteration prefetches into this buffer
   }
 }
 
@@ -499,7 +504,8 @@ static int ensure_attrs() {
   if (dev < 0 || dev >= 64) return fail(QSV_ERANGE, "device ordinal out of range");
   if (!g_attr_set[dev]) {
     QSV_CUDA(cudaFuncSetAttribute(tile_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)(2 * (sizeof(double2) << QSV_MAX_TILE_QUBITS))));
+                                  (int)((sizeof(double2) << QSV_MAX_TILE_QUBITS) + 48 * 1024)));
+    QSV_CUDA(cudaFuncSetAttribute(tile_pass_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     QSV_CUDA(cudaFuncSetAttribute(dense_k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(2 * (sizeof(double2) << 12) + 4096 * sizeof(uint32_t))));
     g_attr_set[dev] = true;
@@ -678,7 +684,7 @@ static int launch_pass(double* sv, int n, const int32_t* tile_qubits, int n_tile
       st.ebit[j] = (uint8_t)(j < ni ? eo[j] : 0);
       st.ecol[j] = j < ni ? sw1(eo[j]) : 0;
     }
-    for (int j = 0; j < 5; j++) {
+    for (int j = 0; j < 4; j++) {
       st.obit[j] = (uint8_t)(j < no ? ob[j] : 0);
       st.ocol[j] = j < no ? sw1(ob[j]) : 0;
     }
@@ -712,15 +718,22 @@ static int launch_pass(double* sv, int n, const int32_t* tile_qubits, int n_tile
       for (int i = 0; i < nf; i++)
         if (fb[i] != f0 && fb[i] != f1) fo[nfo++] = fb[i];
       op.ngl = (uint8_t)nf;
-      for (int j = 0; j < 5; j++) op.col[j] = j < nf ? sw1(fo[j]) : 0;
+      for (int j = 0; j < 6; j++) op.col[j] = j < nf ? sw1(fo[j]) : 0;
     }
   }
 
   if (int rc = ensure_attrs()) return rc;
-  const size_t smem = 2 * (sizeof(double2) << b);
+  const size_t smem = (sizeof(double2) << b) + (size_t)n_gates * (64 * sizeof(double) + sizeof(OpRec) + 32 * 4) +
+                      (size_t)n_stages * ((kWarps + 32 + 8) * 4);
   d.n_tiles = 1u << (n - b);
-  const unsigned grid = std::min<unsigned>(d.n_tiles, (unsigned)sm_count());
-  tile_pass_kernel<<<grid, kPT, smem, stream>>>(reinterpret_cast<double2*>(sv), d);
+  if (const char* e = getenv("QSV_DEBUG_FLAGS")) d.pad2[0] = (uint32_t)atoi(e);
+  // one warp per 2^8 amplitudes: 512 threads for b = 12, 256 for b = 11, ...; at least one warp
+  const int threads = std::max(32, std::min(kMaxPT, 1 << std::max(0, b - 3)));
+  int per_sm = 1;
+  QSV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tile_pass_kernel, threads, smem));
+  if (per_sm < 1) return fail(QSV_ERANGE, "qsv_apply_pass: pass does not fit in shared memory");
+  const unsigned grid = std::min<unsigned>(d.n_tiles, (unsigned)per_sm * (unsigned)sm_count());
+  tile_pass_kernel<<<grid, threads, smem, stream>>>(reinterpret_cast<double2*>(sv), d);
   QSV_LAUNCHED();
   return 0;
 }

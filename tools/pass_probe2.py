@@ -1,0 +1,31 @@
+#!/usr/bin/env python
+"""Breakdown experiment: run the probe under QSV_DEBUG_FLAGS (1 no stores, 2 no loads, 4 no gates)."""
+import os, subprocess, sys
+n = sys.argv[1] if len(sys.argv) > 1 else "30"
+code = r'''
+import sys, os
+sys.path.insert(0, os.getcwd())
+import numpy as np, torch
+from qiskit_sdk_py_b200 import _lib
+from qiskit_sdk_py_b200.engine import DeviceState
+from qiskit_sdk_py_b200.lower import GateOp
+n = int(sys.argv[1]); st = DeviceState(n); st.init_basis0(); rng = np.random.RandomState(0)
+def ru(k):
+    z = rng.standard_normal((2**k, 2**k)) + 1j * rng.standard_normal((2**k, 2**k)); q, r = np.linalg.qr(z); return q * (np.diag(r) / np.abs(np.diag(r)))
+def timeit(tile, ops, reps=5):
+    for _ in range(2): st.apply_pass(tile, ops)
+    torch.cuda.synchronize(); e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): st.apply_pass(tile, ops)
+    e1.record(); torch.cuda.synchronize(); return e0.elapsed_time(e1) / reps
+pairs = [(3, 4), (5, 6), (7, 8), (9, 10), (11, 0), (1, 2), (3, 5), (4, 6)]
+tile = list(range(12))
+out = []
+for k in (0, 4, 8):
+    ops = [GateOp(_lib.GATE_DENSE2, list(p), ru(2)) for p in pairs[:k]]
+    out.append("%d gates %.3f ms" % (k, timeit(tile, ops)))
+print(os.environ.get("QSV_DEBUG_FLAGS", "0"), " | ".join(out))
+'''
+for flags in ("0", "1", "2", "3", "4"):
+    env = dict(os.environ, QSV_DEBUG_FLAGS=flags)
+    subprocess.run([sys.executable, "-c", code, n], env=env, check=True)
