@@ -9,15 +9,16 @@ program order, the set of gates for each pass:
   * a gate may join the pass if its qubits fit in the remaining tile budget and none of its qubits
     has been touched by an earlier gate that was left for a later pass (so the relative order of
     gates that share a qubit never changes -- only gates on disjoint qubits are commuted);
-  * the low qubits 0..2 are always tile qubits, so every global-memory access of the pass is a full
-    128-byte line (SURVEY 2.5 K4 / "Hard parts: low-qubit gates").
+  * the low qubits 0..3 are always tile qubits, so every global-memory access of the pass is part of a
+    256-byte contiguous run (SURVEY 2.5 K4 / "Hard parts: low-qubit gates"; measured copy rates of the
+    pass kernel on B200: 128-byte runs 4.06 TB/s, 256-byte runs 5.03 TB/s, fully contiguous 5.27 TB/s).
 
 Pure host logic, no device access: unit-tested on CPU.
 """
 from . import _lib
 
-DEFAULT_TILE_QUBITS = 12
-LOW_QUBITS = 3  # 8 amplitudes = 128 B contiguous
+DEFAULT_TILE_QUBITS = 11
+LOW_QUBITS = 4  # 16 amplitudes = 256 B contiguous runs (measured: 128 B runs 4.06 TB/s, 256 B 5.03, contiguous 5.27)
 
 
 class Pass:

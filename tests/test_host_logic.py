@@ -48,8 +48,8 @@ def test_planner_preserves_order_on_shared_qubits():
             assert sum(o.payload_doubles for o in p.ops) <= _lib.MAX_PASS_MATRIX_DOUBLES
             for o in p.ops:
                 assert set(o.qubits) <= set(p.tile_qubits)
-            if tile >= 5:
-                assert {0, 1, 2} <= set(p.tile_qubits)
+            if tile >= 6:
+                assert {0, 1, 2, 3} <= set(p.tile_qubits)
 
 
 def test_planner_fuses_quantum_volume():

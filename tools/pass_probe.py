@@ -54,3 +54,11 @@ print(" 8 cx gates: %.3f ms  marginal %.3f ms/gate" % (t, (t - t0) / 8))
 tile_hi = [0, 1, 2] + list(range(n - 9, n))
 t = timeit(tile_hi, [])
 print("copy only, tile = {0,1,2}+top 9: %.3f ms  %.0f GB/s" % (t, gb / t * 1e3))
+for low in (3, 4, 5, 6):
+    for b in (10, 11, 12):
+        tl = list(range(low)) + list(range(n - (b - low), n))
+        t = timeit(tl, [])
+        print("copy only, b=%d tile = low %d + top %d: %.3f ms  %.0f GB/s" % (b, low, b - low, t, gb / t * 1e3))
+for b in (10, 11, 12):
+    t = timeit(list(range(b)), [])
+    print("copy only, b=%d contiguous: %.3f ms  %.0f GB/s" % (b, t, gb / t * 1e3))
