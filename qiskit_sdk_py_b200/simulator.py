@@ -49,11 +49,13 @@ class BasicAerError(Exception):
 
 def max_qubits_for_device(bytes_per_amp=16, default=33):
     """Largest n with 16*2^n bytes fitting the current GPU (33 on a 180 GB B200); the reference's
-    analogue is MAX_QUBITS_MEMORY from host RAM (qasm_simulator.py:59,64)."""
+    analogue is MAX_QUBITS_MEMORY from host RAM (qasm_simulator.py:59,64).  Never creates a CUDA
+    context (Terra may fork worker processes after the backend object exists): before CUDA is
+    initialised the B200 value is returned."""
     try:
         import torch
 
-        if torch.cuda.is_available():
+        if torch.cuda.is_available() and torch.cuda.is_initialized():
             total = torch.cuda.get_device_properties(torch.cuda.current_device()).total_memory
             return int(log2(max(1, total - HBM_RESERVE_BYTES) / bytes_per_amp))
     except Exception:  # pragma: no cover
