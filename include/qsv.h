@@ -120,9 +120,10 @@ int qsv_marginal(const double* sv, int n_qubits, const int32_t* measured_sorted,
  * for the caller-supplied uniforms u (RandomState.random_sample(shots)).
  *   src            : from_amplitudes != 0 -> 2^log2_bins complex amplitudes, p_i = |psi_i|^2
  *                    (all qubits measured); else 2^log2_bins doubles (a marginal from qsv_marginal).
- *   exact_order    : != 0 -> the CDF is accumulated strictly left to right in float64, like
- *                    numpy's cumsum, so samples equal the reference's bit for bit (serial, meant for
- *                    log2_bins <= ~26); 0 -> blocked parallel scan (any size).
+ *   exact_order    : flags.  Bit 0 set -> the CDF is accumulated strictly left to right in float64,
+ *                    like numpy's cumsum, so samples equal the reference's bit for bit (serial, meant
+ *                    for log2_bins <= ~26); clear -> blocked parallel scan (any size).  Bit 1 set ->
+ *                    skip the sum-to-1 check (a shard of a multi-GPU state sums to less than 1).
  *   host_total     : receives cdf[-1] before normalisation (must be ~1).
  * Returns QSV_ENORM if |total - 1| > sqrt(eps) as numpy's choice() does.  Synchronises the stream. */
 size_t qsv_sample_workspace_bytes(int log2_bins, int shots);

@@ -260,7 +260,8 @@ static size_t sample_ws_layout(int log2_bins, int shots, void* ws, SampleWs* out
 
 template <bool kAmps>
 static int sample_impl(const void* src, int log2_bins, const double* host_uniforms, int shots,
-                       int64_t* host_out, int exact, void* ws, double* host_total, cudaStream_t s) {
+                       int64_t* host_out, int flags, void* ws, double* host_total, cudaStream_t s) {
+  const bool exact = (flags & 1) != 0, check_norm = (flags & 2) == 0;
   const u64 bins = 1ull << log2_bins;
   const u64 nchunks = (bins + kChunk - 1) / kChunk;
   SampleWs w;
@@ -287,7 +288,9 @@ static int sample_impl(const void* src, int log2_bins, const double* host_unifor
   QSV_CUDA(cudaStreamSynchronize(s));
   if (host_total) *host_total = total;
   // numpy's choice(): "probabilities do not sum to 1" when |sum - 1| > sqrt(eps)
-  if (!(fabs(total - 1.0) <= 1.4901161193847656e-08)) return fail(QSV_ENORM, "probabilities do not sum to 1");
+  if (check_norm && !(fabs(total - 1.0) <= 1.4901161193847656e-08))
+    return fail(QSV_ENORM, "probabilities do not sum to 1");
+  if (!(total > 0.0)) return fail(QSV_ENORM, "probabilities sum to zero");
   sample_kernel<kAmps><<<(shots + kThreads - 1) / kThreads, kThreads, 0, s>>>(src, bins, w.chunk_end, nchunks,
                                                                               w.uniforms, shots, w.out);
   QSV_LAUNCHED();

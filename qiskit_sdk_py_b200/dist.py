@@ -1,0 +1,410 @@
+"""Multi-GPU statevector: one process per GPU, the state sharded by its high-order qubits.
+
+The reference has no multi-device path (qasm_simulator.py keeps one numpy array in host memory, capped
+at 24 qubits); this is the B200 extension BASELINE config 5 asks for.  Layout:
+
+  * W = 2^g ranks; rank r holds the 2^(n-g) amplitudes whose top g *physical* index bits equal r.
+  * ``pos[q]`` maps logical qubit q to its physical bit.  Physical bits < n_local are local, the others
+    are "global" (rank bits).
+  * Gates whose non-diagonal action touches only local bits run with no communication, on every rank,
+    through the same fused pass kernel as the single-GPU path.  Diagonal gates and CX controls on a
+    global qubit also need no communication (the rank's bit selects a factor / enables the X).
+  * A dense gate (or a CX target) on a global qubit triggers a **qubit swap**: global bit j <-> local
+    bit L.  Each rank exchanges, with partner r ^ 2^j, the half of its shard whose bit L differs from
+    its own bit j -- pack (qsv_pack_half) -> NCCL send/recv over NVLink -> unpack (qsv_unpack_half),
+    chunked through two staging buffers.  The victim L is the local qubit whose next use lies furthest
+    in the future.
+  * Reductions (P(qubit), norm, sampler totals) are all-reduces / all-gathers of a few doubles.
+
+The transport is ``torch.distributed`` (NCCL on GPUs; gloo in the CPU tests, where the shard is the numpy
+test double) -- plumbing only; every operation on amplitudes is a libqsv kernel.
+"""
+import math
+import os
+
+import numpy as np
+
+from . import _lib
+from .lower import GateOp
+
+DEFAULT_CHUNK_AMPS = 1 << 26  # 1 GiB staging buffers
+
+
+class ShardedState:
+    """A 2^n statevector sharded over ``world`` ranks.  ``shard`` is an engine.DeviceState (or a test
+    double with the same interface) holding this rank's 2^(n - log2(world)) amplitudes."""
+
+    def __init__(self, n_qubits, shard_factory, rank=None, world=None, chunk_amps=DEFAULT_CHUNK_AMPS,
+                 group=None):
+        import torch
+        import torch.distributed as dist
+
+        self._torch = torch
+        self._dist = dist
+        self.group = group
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world is None else world
+        self.g = int(round(math.log2(self.world)))
+        if (1 << self.g) != self.world:
+            raise ValueError("world size must be a power of two")
+        self.n = int(n_qubits)
+        self.n_local = self.n - self.g
+        if self.n_local < 2:
+            raise ValueError("need at least two local qubits per rank")
+        self.shard = shard_factory(self.n_local)
+        self.pos = list(range(self.n))          # logical qubit -> physical bit
+        self.chunk_amps = int(chunk_amps)
+        self._send = None
+        self._recv = None
+        self.swaps = 0
+        self.swap_bytes = 0
+
+    # -- helpers -----------------------------------------------------------------------
+    def _logical_at(self, phys):
+        return self.pos.index(phys)
+
+    def _rank_bit(self, phys):
+        return (self.rank >> (phys - self.n_local)) & 1
+
+    def _staging(self, amps):
+        torch = self._torch
+        dev = self.shard.comm_device()
+        if self._send is None or self._send.numel() < 2 * amps:
+            self._send = torch.empty(2 * amps, dtype=torch.float64, device=dev)
+            self._recv = torch.empty(2 * amps, dtype=torch.float64, device=dev)
+        return self._send[: 2 * amps], self._recv[: 2 * amps]
+
+    # -- initialisation ----------------------------------------------------------------
+    def init_basis0(self, phase=1.0 + 0.0j):
+        self.pos = list(range(self.n))
+        if self.rank == 0:
+            self.shard.init_basis0(phase)
+        else:
+            self.shard.init_basis0(0.0 + 0.0j)
+
+    # -- the exchange step -------------------------------------------------------------
+    def swap_global_local(self, phys_global, phys_local):
+        """Swap physical bits (global j, local L): exchange the half with bit L != my bit j."""
+        dist = self._dist
+        j = phys_global - self.n_local
+        beta = (self.rank >> j) & 1
+        peer = self.rank ^ (1 << j)
+        half = 1 << (self.n_local - 1)
+        chunk = min(self.chunk_amps, half)
+        send, recv = self._staging(chunk)
+        for begin in range(0, half, chunk):
+            cnt = min(chunk, half - begin)
+            self.shard.pack_half(phys_local, 1 - beta, send, begin, cnt)
+            ops = [dist.P2POp(dist.isend, send[: 2 * cnt], peer, self.group),
+                   dist.P2POp(dist.irecv, recv[: 2 * cnt], peer, self.group)]
+            if self.rank > peer:
+                ops.reverse()
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+            self.shard.unpack_half(phys_local, 1 - beta, recv, begin, cnt)
+        qa, qb = self._logical_at(phys_global), self._logical_at(phys_local)
+        self.pos[qa], self.pos[qb] = phys_local, phys_global
+        self.swaps += 1
+        self.swap_bytes += 16 * half
+
+    # -- gates -------------------------------------------------------------------------
+    def _localise(self, op):
+        """Return the op rewritten on physical local bits, ``None`` if it is a no-op on this rank, or
+        ``False`` if it needs a qubit swap first."""
+        phys = [self.pos[q] for q in op.qubits]
+        is_global = [p >= self.n_local for p in phys]
+        if not any(is_global):
+            return GateOp(op.kind, phys, op.matrix)
+        if op.kind == _lib.GATE_DIAG1:
+            f = op.matrix[self._rank_bit(phys[0])]
+            return ("scale", complex(f))
+        if op.kind == _lib.GATE_DIAG2:
+            d = np.asarray(op.matrix).reshape(2, 2)  # d[bit1][bit0]
+            if all(is_global):
+                return ("scale", complex(d[self._rank_bit(phys[1])][self._rank_bit(phys[0])]))
+            if is_global[0]:
+                return GateOp(_lib.GATE_DIAG1, [phys[1]], d[:, self._rank_bit(phys[0])].copy())
+            return GateOp(_lib.GATE_DIAG1, [phys[0]], d[self._rank_bit(phys[1]), :].copy())
+        if op.kind == _lib.GATE_CX and not is_global[1]:
+            if self._rank_bit(phys[0]):
+                return GateOp(_lib.GATE_DENSE1, [phys[1]], np.array([[0, 1], [1, 0]], dtype=complex))
+            return None
+        return False
+
+    def apply_ops(self, ops):
+        """Apply GateOps (logical qubits, program order).  Gates that need no exchange are fused into
+        local passes -- commuting over deferred gates on disjoint qubits only -- then the global qubits
+        the deferred gates need are swapped in, and so on."""
+        remaining = [op for op in ops]
+        for op in remaining:
+            if op.kind == "densek":
+                raise _lib.QsvLibraryError("k >= 3 qubit unitaries are not supported on a sharded state")
+        while remaining:
+            run, deferred, blocked = [], [], set()
+            for op in remaining:
+                qs = set(op.qubits)
+                loc = False if (qs & blocked) else self._localise(op)
+                if loc is False:
+                    blocked |= qs
+                    deferred.append(op)
+                elif loc is not None:
+                    run.append(loc)
+            self._apply_local(run)
+            if deferred:
+                self._swap_in_for(deferred)
+            remaining = deferred
+
+    def _apply_local(self, run):
+        batch = []
+        for item in run:
+            if isinstance(item, tuple):  # ("scale", factor): a diagonal gate on global qubits
+                if batch:
+                    self.shard.apply_ops(batch)
+                    batch = []
+                if item[1] != 1.0:
+                    self.shard.scale(item[1])
+            else:
+                batch.append(item)
+        if batch:
+            self.shard.apply_ops(batch)
+
+    def _swap_in_for(self, deferred):
+        """Bring the global qubits the deferred gates need into local bits."""
+        first_use, order = {}, []
+        for idx, op in enumerate(deferred):
+            for q in op.qubits:
+                if q not in first_use:
+                    first_use[q] = idx
+                    order.append(q)
+        need = []
+        for op in deferred:
+            for k, q in enumerate(op.qubits):
+                if self.pos[q] < self.n_local or q in need:
+                    continue
+                diag_ok = op.kind in (_lib.GATE_DIAG1, _lib.GATE_DIAG2) or (op.kind == _lib.GATE_CX and k == 0)
+                if not diag_ok:
+                    need.append(q)
+        need.sort(key=lambda q: first_use[q])
+        never = len(deferred) + 1
+        for q in need[: self.g]:
+            if self.pos[q] < self.n_local:
+                continue
+            # victim: local logical qubit used furthest in the future (and later than q itself)
+            partners = set()
+            for op in deferred:
+                if q in op.qubits:
+                    partners = set(op.qubits)
+                    break
+            best, best_use = None, -1
+            for lq in range(self.n):
+                if self.pos[lq] >= self.n_local or lq in need or lq in partners:
+                    continue
+                use = first_use.get(lq, never)
+                if use > best_use:
+                    best, best_use = lq, use
+            if best is None:
+                raise RuntimeError("no local qubit available to swap out")
+            self.swap_global_local(self.pos[q], self.pos[best])
+            first_use[best] = -1  # do not pick the same victim twice in this round
+
+    def ensure_local(self, qubit):
+        """Make logical ``qubit`` a local bit (used before measure / reset on it)."""
+        if self.pos[qubit] < self.n_local:
+            return
+        # swap with the top local bit's occupant
+        self.swap_global_local(self.pos[qubit], self.n_local - 1)
+
+    def restore_identity_layout(self):
+        """Undo every remap so that logical qubit q sits at physical bit q again (needed before the
+        state is read out or sampled in logical index order)."""
+        for phys in range(self.n_local, self.n):
+            q_home = phys  # logical qubit whose home is this global bit
+            if self.pos[q_home] == phys:
+                continue
+            if self.pos[q_home] >= self.n_local:
+                # it sits in another global bit: bring it local first
+                self.swap_global_local(self.pos[q_home], self.n_local - 1)
+            self.swap_global_local(phys, self.pos[q_home])
+        # now fix the local permutation with SWAP gates
+        swap = np.array([[1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=complex)
+        ops = []
+        pos = list(self.pos)
+        for q in range(self.n_local):
+            if pos[q] == q:
+                continue
+            other = pos.index(q)  # logical qubit currently sitting at physical bit q
+            ops.append(GateOp(_lib.GATE_DENSE2, [pos[q], q], swap))
+            pos[other], pos[q] = pos[q], q
+        if ops:
+            self.shard.apply_ops(ops)
+        self.pos = pos
+        assert self.pos == list(range(self.n))
+
+    # -- measurement -------------------------------------------------------------------
+    def _allreduce(self, values):
+        torch = self._torch
+        t = torch.tensor(values, dtype=torch.float64, device=self.shard.comm_device())
+        self._dist.all_reduce(t, op=self._dist.ReduceOp.SUM, group=self.group)
+        return t.cpu().tolist()
+
+    def prob_qubit(self, qubit):
+        phys = self.pos[qubit]
+        if phys < self.n_local:
+            p0, p1 = self.shard.prob_qubit(phys)
+        else:
+            nrm = self.shard.norm2()
+            p0, p1 = (0.0, nrm) if self._rank_bit(phys) else (nrm, 0.0)
+        return tuple(self._allreduce([p0, p1]))
+
+    def norm2(self):
+        return self._allreduce([self.shard.norm2()])[0]
+
+    def collapse(self, qubit, outcome, prob, is_reset=False):
+        self.ensure_local(qubit)
+        self.shard.collapse(self.pos[qubit], outcome, prob, is_reset)
+
+    def sample_all(self, uniforms):
+        """Blocked-order sampling of all n qubits in *physical* index order (rank-major), returned as
+        logical indices.  Every rank gets the full result."""
+        torch = self._torch
+        dist = self._dist
+        uniforms = np.ascontiguousarray(uniforms, dtype=np.float64)
+        shots = uniforms.size
+        local_total = self.shard.norm2()
+        totals = torch.zeros(self.world, dtype=torch.float64, device=self.shard.comm_device())
+        totals[self.rank] = local_total
+        dist.all_reduce(totals, op=dist.ReduceOp.SUM, group=self.group)
+        totals = totals.cpu().numpy()
+        cdf = np.cumsum(totals)
+        total = float(cdf[-1])
+        owner = np.searchsorted(cdf / total, uniforms, side="right")
+        owner = np.minimum(owner, self.world - 1)
+        mine = np.nonzero(owner == self.rank)[0]
+        out = torch.zeros(shots, dtype=torch.int64, device=self.shard.comm_device())
+        if mine.size and local_total > 0.0:
+            before = cdf[self.rank] - totals[self.rank]
+            u_local = (uniforms[mine] * total - before) / totals[self.rank]
+            u_local = np.clip(u_local, 0.0, np.nextafter(1.0, 0.0))
+            idx, _ = self.shard.sample(list(range(self.n_local)), u_local, exact_order=False,
+                                       check_norm=False)
+            phys_idx = idx + (self.rank << self.n_local)
+            out[torch.as_tensor(mine, device=out.device)] = torch.as_tensor(phys_idx, device=out.device)
+        dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self.group)
+        phys = out.cpu().numpy()
+        # physical index -> logical index
+        logical = np.zeros_like(phys)
+        for q in range(self.n):
+            logical |= ((phys >> self.pos[q]) & 1) << q
+        return logical, total
+
+    def gather_statevector(self):
+        """Full logical-order statevector on every rank (small n only; tests)."""
+        torch = self._torch
+        self.restore_identity_layout()
+        local = torch.as_tensor(self.shard.download().view(np.float64), device=self.shard.comm_device())
+        parts = [torch.empty_like(local) for _ in range(self.world)]
+        self._dist.all_gather(parts, local, group=self.group)
+        return np.concatenate([p.cpu().numpy().view(np.complex128) for p in parts])
+
+
+# ------------------------------------------------------------------------------------------------
+def bench_main(args, metric, unit, measured_peaks, clock_sampler_cls):
+    """bench.py leg for N > 1 GPUs: weak scaling, args.qubits local qubits per GPU."""
+    import json
+
+    import torch
+    import torch.distributed as dist
+
+    from . import circuits, lower
+    from .engine import DeviceState
+
+    world = int(os.environ["WORLD_SIZE"])
+    rank = int(os.environ["RANK"])
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    g = int(round(math.log2(world)))
+    free, _ = torch.cuda.mem_get_info()
+    n_local = args.qubits
+    chunk = DEFAULT_CHUNK_AMPS
+    while n_local > 20 and (16 << n_local) + 4 * 16 * min(chunk, 1 << (n_local - 1)) + (2 << 30) > free:
+        n_local -= 1
+    nl = torch.tensor([n_local], device="cuda")
+    dist.all_reduce(nl, op=dist.ReduceOp.MIN)
+    n_local = int(nl.item())
+    n = n_local + g
+    depth = args.depth or n
+    tile = args.tile or None
+    shots, qv_seed, sim_seed = 8192, 1234, 42
+    ins = [i for i in circuits.quantum_volume_instructions(n, depth, qv_seed) if i["name"] == "unitary"]
+    ops = [lower.lower_gate(i["name"], i["qubits"], i.get("params")) for i in ins]
+    n_gates = len(ops)
+    factory = (lambda k: DeviceState(k, tile_qubits=tile)) if tile else DeviceState
+    st = ShardedState(n, factory, chunk_amps=min(chunk, 1 << (n_local - 1)))
+    uniforms = np.random.RandomState(sim_seed).random_sample(shots)
+
+    def step():
+        st.init_basis0()
+        st.apply_ops(ops)
+        return st.sample_all(uniforms)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    clocks = clock_sampler_cls(local_rank)
+    if rank == 0:
+        clocks.start()
+    launches0 = _lib.launch_count()
+    swaps0, bytes0 = st.swaps, st.swap_bytes
+    passes0 = st.shard.passes_launched
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0.record()
+    for _ in range(args.steps):
+        samples, total = step()
+    e1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    step_ms = float(ms.item()) / args.steps
+    launches = torch.tensor([_lib.launch_count() - launches0], device="cuda", dtype=torch.int64)
+    dist.all_reduce(launches, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        clock_info = clocks.stop()
+        bytes_per_gate_pass = 32.0 * 2 ** n
+        value = n_gates * bytes_per_gate_pass / (step_ms * 1e-3) / 1e9
+        passes = (st.shard.passes_launched - passes0) / args.steps
+        swaps = (st.swaps - swaps0) / args.steps
+        swap_gb = (st.swap_bytes - bytes0) / args.steps / 1e9
+        peak, peak_src = measured_peaks()
+        line = {
+            "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": "QuantumVolume(%d, depth %d, seed %d): %d SU(4) gates + %d-shot sampling, complex128 "
+                            "statevector sharded over %d B200 (%d local qubits, %.1f GiB per GPU) -- BASELINE "
+                            "config 5" % (n, depth, qv_seed, n_gates, shots, world, n_local, 16 * 2 ** n_local / 2 ** 30),
+                "n_qubits": n, "local_qubits": n_local, "depth": depth, "gates": n_gates, "shots": shots,
+                "parallelism": "state sharded by the %d high-order qubits; qubit swaps over NCCL send/recv" % g,
+                "local_passes_per_step": passes, "qubit_swaps_per_step": swaps,
+                "swap_GB_per_gpu_per_step": swap_gb, "circuit_s": step_ms * 1e-3,
+                "l2": "shards (%.1f GiB) are far larger than the 126 MB L2" % (16 * 2 ** n_local / 2 ** 30),
+            },
+            "roofline": {"bound": "hbm", "kernel": "tile_pass_kernel", "achieved": None, "peak": peak, "unit": "GB/s",
+                         "frac": None, "traffic": None, "peak_source": peak_src,
+                         "note": "per-kernel roofline is reported by the N=1 run"},
+            "cpu_baseline": None,
+            "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": int(n_gates * 256 + shots * 8),
+                    "d2h_bytes_per_step": int(shots * 8 + 8 * world),
+                    "note": "the sharded path is driven from host op lists; uniforms in, sample indices out are "
+                            "inside the timed region"},
+            "gpu_launches": int(launches.item()),
+            "clocks": clock_info,
+            "check": {"sample_total_prob": total},
+        }
+        print(json.dumps(line))
+    dist.destroy_process_group()

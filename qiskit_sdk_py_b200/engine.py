@@ -187,7 +187,7 @@ class DeviceState:
                        "qsv_marginal")
         return probs
 
-    def sample(self, measured_sorted, uniforms, exact_order=True):
+    def sample(self, measured_sorted, uniforms, exact_order=True, check_norm=True):
         """searchsorted(cumsum(p)/sum(p), uniforms, 'right') over the marginal of the measured qubits.
         Returns (int64 ndarray of bin indices, total probability)."""
         torch = self._torch
@@ -207,7 +207,8 @@ class DeviceState:
         with self._ctx():
             _lib.check(self.lib.qsv_sample(ctypes.c_void_p(src.data_ptr()), from_amps, log2_bins,
                                            ctypes.c_void_p(uniforms.ctypes.data), shots,
-                                           ctypes.c_void_p(out.ctypes.data), 1 if exact_order else 0,
+                                           ctypes.c_void_p(out.ctypes.data),
+                                           (1 if exact_order else 0) | (0 if check_norm else 2),
                                            ctypes.c_void_p(self._sample_ws.data_ptr()), ctypes.byref(total),
                                            self.stream), "qsv_sample")
         return out, float(total.value)
@@ -224,6 +225,23 @@ class DeviceState:
             _lib.check(self.lib.qsv_download(self.ptr, self.n, ctypes.c_void_p(host.ctypes.data), self.stream),
                        "qsv_download")
         return host
+
+    # -- multi-GPU staging (dist.py) ---------------------------------------------------
+    def comm_device(self):
+        return self.device
+
+    def pack_half(self, local_qubit, bit_value, buf, begin, count):
+        """buf[0:2*count] <- the amplitudes [begin, begin+count) of the half with bit local_qubit == bit_value."""
+        with self._ctx():
+            _lib.check(self.lib.qsv_pack_half(self.ptr, self.n, int(local_qubit), int(bit_value),
+                                              ctypes.c_void_p(buf.data_ptr()), int(begin), int(count),
+                                              self.stream), "qsv_pack_half")
+
+    def unpack_half(self, local_qubit, bit_value, buf, begin, count):
+        with self._ctx():
+            _lib.check(self.lib.qsv_unpack_half(self.ptr, self.n, int(local_qubit), int(bit_value),
+                                                ctypes.c_void_p(buf.data_ptr()), int(begin), int(count),
+                                                self.stream), "qsv_unpack_half")
 
     def snapshot(self):
         return self.state.clone()

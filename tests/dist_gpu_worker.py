@@ -1,0 +1,66 @@
+"""torchrun worker: sharded CUDA state (NCCL) against the numpy oracle.  Launched by
+tests/test_gpu_dist.py (needs >= 2 GPUs) or by hand:
+    torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/dist_gpu_worker.py"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+from oracle import basicaer_oracle as orc  # noqa: E402
+from qiskit_sdk_py_b200 import _lib, circuits, lower  # noqa: E402
+from qiskit_sdk_py_b200.dist import ShardedState  # noqa: E402
+from qiskit_sdk_py_b200.engine import DeviceState  # noqa: E402
+
+
+def main():
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    for n, seed in ((12, 3), (16, 4), (19, 5)):
+        ins = circuits.random_basis_instructions(n, 8, seed) + circuits.quantum_volume_instructions(n, 4, seed)
+        ops = [lower.lower_gate(i["name"], i["qubits"], i.get("params")) for i in ins]
+        ops = [o for o in ops if o is not None]
+        st = ShardedState(n, DeviceState, chunk_amps=1 << 9)
+        st.init_basis0(np.exp(0.3j))
+        st.apply_ops(ops)
+        ref = np.zeros(2 ** n, dtype=complex)
+        ref[0] = np.exp(0.3j)
+        for o in ops:
+            if o.kind in (_lib.GATE_DIAG1, _lib.GATE_DIAG2):
+                mat = np.diag(o.matrix)
+            elif o.kind == _lib.GATE_CX:
+                mat = orc.cx_gate_matrix()
+            else:
+                mat = o.matrix
+            ref = orc.apply_unitary(ref.reshape([2] * n), mat, list(o.qubits)).reshape(-1)
+        p = np.abs(ref) ** 2
+        idx = np.arange(2 ** n)
+        for q in (0, n // 2, n - 1):
+            p0, p1 = st.prob_qubit(q)
+            mask = ((idx >> q) & 1).astype(bool)
+            assert abs(p0 - p[~mask].sum()) < 1e-12 and abs(p1 - p[mask].sum()) < 1e-12
+        u = np.random.RandomState(1).random_sample(20000)
+        samples, total = st.sample_all(u)
+        assert abs(total - 1.0) < 1e-12
+        top = np.argsort(p)[-8:]
+        hist = np.bincount(samples, minlength=2 ** n) / 20000.0
+        assert np.all(np.abs(hist[top] - p[top]) < 5 * np.sqrt(p[top] / 20000.0) + 1e-3)
+        swaps = st.swaps
+        full = st.gather_statevector()
+        err = float(np.max(np.abs(full - ref)))
+        assert err < 1e-12, err
+        if rank == 0:
+            print("dist ok: world=%d n=%d swaps=%d max-abs err %.2e" % (world, n, swaps, err), flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -81,7 +81,31 @@ class FakeState:
             mat = [[0, 0], [0, s]]
         self.vec = orc.apply_unitary(self.vec.reshape([2] * self.n), mat, [qubit]).reshape(-1)
 
-    def sample(self, measured_sorted, uniforms, exact_order=True):
+    def scale(self, factor):
+        self.vec = self.vec * complex(factor)
+
+    def norm2(self):
+        return float(np.sum(np.abs(self.vec) ** 2))
+
+    def comm_device(self):
+        return "cpu"
+
+    def _half_index(self, local_qubit, bit_value, begin, count):
+        h = np.arange(begin, begin + count, dtype=np.int64)
+        low = h & ((1 << local_qubit) - 1)
+        return ((h >> local_qubit) << (local_qubit + 1)) | (bit_value << local_qubit) | low
+
+    def pack_half(self, local_qubit, bit_value, buf, begin, count):
+        import torch
+
+        idx = self._half_index(local_qubit, bit_value, begin, count)
+        buf[: 2 * count] = torch.from_numpy(np.ascontiguousarray(self.vec[idx]).view(np.float64).copy())
+
+    def unpack_half(self, local_qubit, bit_value, buf, begin, count):
+        idx = self._half_index(local_qubit, bit_value, begin, count)
+        self.vec[idx] = buf[: 2 * count].numpy().copy().view(np.complex128)
+
+    def sample(self, measured_sorted, uniforms, exact_order=True, check_norm=True):
         n = self.n
         axis = list(range(n))
         for q in reversed(measured_sorted):
