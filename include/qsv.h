@@ -88,6 +88,14 @@ int qsv_scale(double* sv, int n_qubits, double re, double im, void* stream);
 int qsv_apply_pass(double* sv, int n_qubits, const int32_t* tile_qubits, int n_tile,
                    const qsv_gate_t* gates, int n_gates, void* stream);
 
+/* qsv_apply_pass followed, for free, by a permutation of the tile qubits: on write-back the content of
+ * qubit tile_qubits[i] lands on qubit dest_qubits[i] (dest_qubits is a permutation of tile_qubits; NULL =
+ * identity).  The caller tracks the resulting logical -> physical qubit map.  Used by the planner to
+ * keep the qubits the next gates need in the always-resident low bits, and to undo the map before a
+ * read-out.  (New: the reference never moves qubits; its einsum addresses them in place.) */
+int qsv_apply_pass_remap(double* sv, int n_qubits, const int32_t* tile_qubits, int n_tile,
+                         const qsv_gate_t* gates, int n_gates, const int32_t* dest_qubits, void* stream);
+
 /* psi <- (G on qubits) psi for a dense k-qubit matrix, k >= 1.  Replaces one _add_unitary call
  * (qasm_simulator.py:145-161; `unitary` instruction :543-546).  k <= 2 goes through qsv_apply_pass;
  * 3 <= k <= QSV_MAX_DENSE_K uses the staged dense kernel, which needs `dev_mat_scratch`, a device

@@ -63,6 +63,7 @@ struct PassDesc {
   uint32_t pad2[3];
   uint8_t tb[16];   // ascending physical bit position of each tile-local bit
   uint8_t vec[16];  // bank vector of each tile-local bit (pass-specific XOR swizzle), vec[j] = 1<<j for j<3
+  uint8_t src_of[16];  // write-back permutation: tile-local position j receives the content of bit src_of[j]
   PassStage stages[kMaxStages];
   PassOp ops[kMaxOps];
   double mats[kMaxMat];
@@ -121,6 +122,7 @@ tile_pass_kernel(double2* __restrict__ sv, const __grid_constant__ PassDesc d) {
   extern __shared__ double2 tile[];
   __shared__ u64 hi_off[8];
   __shared__ uint16_t swz_it[8];
+  __shared__ uint16_t swz_it_st[8];
   const int nops_all = d.nops, nst_all = d.nstages;
   double (*frag)[64] = reinterpret_cast<double (*)[64]>(tile + (1u << d.b));   // [nops][64] B fragments
   OpRec* oprec = reinterpret_cast<OpRec*>(frag + nops_all);                     // [nops]
@@ -149,6 +151,10 @@ tile_pass_kernel(double2* __restrict__ sv, const __grid_constant__ PassDesc d) {
     for (int j = kTidBits; j < b; j++) off |= (u64)((tid >> (j - kTidBits)) & 1u) << d.tb[j];
     hi_off[tid] = off;
     swz_it[tid] = (uint16_t)swz(d.vec, b, tid << kTidBits);
+    uint32_t sst = 0;  // write-back source slot of loop index bits: position j reads the content of bit src_of[j]
+    for (int j = kTidBits; j < b; j++)
+      if ((tid >> (j - kTidBits)) & 1u) sst ^= swz(d.vec, b, 1u << d.src_of[j]);
+    swz_it_st[tid] = (uint16_t)sst;
   }
   for (int idx = tid; idx < nops * 64; idx += kPT) {
     const int o = idx >> 6, e = idx & 63;
@@ -201,6 +207,10 @@ tile_pass_kernel(double2* __restrict__ sv, const __grid_constant__ PassDesc d) {
     }
   }
   const uint32_t s_tid = swz(d.vec, b, tid);
+  uint32_t s_tid_st = 0;
+  for (int j = 0; j < lo_bits; j++)
+    if ((tid >> j) & 1u) s_tid_st ^= swz(d.vec, b, 1u << d.src_of[j]);
+  const bool permuted = d.pad2[1] != 0;
   const uint32_t iters = tile_amps > kPT ? tile_amps / kPT : 1;
   const bool active = tid < tile_amps;
   const bool ld_on = active && !(dbg & 2u), st_on = active && !(dbg & 1u);
@@ -330,13 +340,15 @@ tile_pass_kernel(double2* __restrict__ sv, const __grid_constant__ PassDesc d) {
     }
     __syncthreads();
 
-    // ---- write-back: one HBM write of the tile.  Every thread reads exactly the slots its own
-    // cp.async of the next tile will overwrite, so no barrier is needed after this phase ----
+    // ---- write-back: one HBM write of the tile, optionally with the tile qubits permuted (the content
+    // of tile bit src_of[j] lands on position j: a free qubit remap).  Without a permutation every thread
+    // reads exactly the slots its own cp.async of the next tile will overwrite, so no barrier is needed ----
     if (st_on) {
       double2* gp = sv + base + lo_off;
 #pragma unroll 8
-      for (uint32_t it = 0; it < iters; it++) gp[hi_off[it]] = tile[s_tid ^ swz_it[it]];
+      for (uint32_t it = 0; it < iters; it++) gp[hi_off[it]] = tile[s_tid_st ^ swz_it_st[it]];
     }
+    if (permuted) __syncthreads();
   }
 }
 
@@ -514,7 +526,7 @@ static int ensure_attrs() {
 }
 
 static int launch_pass(double* sv, int n, const int32_t* tile_qubits, int n_tile, const qsv_gate_t* gates,
-                       int n_gates, cudaStream_t stream) {
+                       int n_gates, cudaStream_t stream, const int32_t* dest_qubits = nullptr) {
   if (!sv || n < 1 || n > 40) return fail(QSV_EINVAL, "qsv_apply_pass: bad state / n_qubits");
   if (n_tile < 1 || n_tile > QSV_MAX_TILE_QUBITS || n_tile > n)
     return fail(QSV_ERANGE, "qsv_apply_pass: n_tile must be in [1, min(n_qubits, 12)]");
@@ -539,6 +551,20 @@ static int launch_pass(double* sv, int n, const int32_t* tile_qubits, int n_tile
   for (int j = 0; j < b; j++) {
     d.tb[j] = (uint8_t)sorted[j];
     local_of[sorted[j]] = j;
+  }
+  // write-back permutation: content of tile_qubits[i] goes to dest_qubits[i]
+  for (int j = 0; j < 16; j++) d.src_of[j] = (uint8_t)j;
+  if (dest_qubits) {
+    bool seen[16] = {false};
+    for (int i = 0; i < b; i++) {
+      const int dq = dest_qubits[i];
+      if (dq < 0 || dq >= n || local_of[dq] < 0 || seen[local_of[dq]])
+        return fail(QSV_EINVAL, "qsv_apply_pass_remap: dest_qubits must be a permutation of tile_qubits");
+      seen[local_of[dq]] = true;
+      d.src_of[local_of[dq]] = (uint8_t)local_of[tile_qubits[i]];
+    }
+    for (int j = 0; j < b; j++)
+      if (d.src_of[j] != j) d.pad2[1] = 1;
   }
 
   // ---- gates -> host ops (tile-local bits, matrices) ----
@@ -626,9 +652,26 @@ static int launch_pass(double* sv, int n, const int32_t* tile_qubits, int n_tile
       int cnt = 0;
       for (int k = 0; k < n_gates; k++)
         if (sops[k].kind == QSV_GATE_DENSE2 && d.vec[sops[k].t0] == d.vec[sops[k].t1]) cnt++;
+      // write-back reads: the 8 lanes of a quarter warp read the bits that land on positions 0..2
+      if (b >= 3 && !independent3(d.vec[d.src_of[0]] & 7, d.vec[d.src_of[1]] & 7, d.vec[d.src_of[2]] & 7)) cnt += 2;
       return cnt;
     };
     int best = conflicts();
+    // first make the write-back lane bits independent
+    for (int j = 0; j < 3 && j < b && best > 0; j++) {
+      const int bit = d.src_of[j];
+      if (bit < 3) continue;
+      uint8_t best_v = d.vec[bit];
+      for (uint8_t v = 1; v < 8; v++) {
+        d.vec[bit] = v;
+        const int cnt = conflicts();
+        if (cnt < best) {
+          best = cnt;
+          best_v = v;
+        }
+      }
+      d.vec[bit] = best_v;
+    }
     for (int round = 0; round < 4 && best > 0; round++) {
       for (int k = 0; k < n_gates && best > 0; k++) {
         if (sops[k].kind != QSV_GATE_DENSE2 || d.vec[sops[k].t0] != d.vec[sops[k].t1]) continue;
@@ -822,6 +865,12 @@ int qsv_apply_pass(double* sv, int n, const int32_t* tile_qubits, int n_tile, co
                    int n_gates, void* stream) {
   if (!tile_qubits || (n_gates > 0 && !gates)) return fail(QSV_EINVAL, "qsv_apply_pass: null pointer");
   return launch_pass(sv, n, tile_qubits, n_tile, gates, n_gates, (cudaStream_t)stream);
+}
+
+int qsv_apply_pass_remap(double* sv, int n, const int32_t* tile_qubits, int n_tile, const qsv_gate_t* gates,
+                         int n_gates, const int32_t* dest_qubits, void* stream) {
+  if (!tile_qubits || (n_gates > 0 && !gates)) return fail(QSV_EINVAL, "qsv_apply_pass_remap: null pointer");
+  return launch_pass(sv, n, tile_qubits, n_tile, gates, n_gates, (cudaStream_t)stream, dest_qubits);
 }
 
 int qsv_apply_matrix(double* sv, int n, const int32_t* qubits, int k, const double* host_matrix,

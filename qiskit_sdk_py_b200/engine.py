@@ -99,14 +99,21 @@ class DeviceState:
             _lib.check(self.lib.qsv_scale(self.ptr, self.n, factor.real, factor.imag, self.stream), "qsv_scale")
 
     # -- gates -----------------------------------------------------------------------
-    def apply_pass(self, tile_qubits, ops):
+    def apply_pass(self, tile_qubits, ops, dest=None):
+        """One cache-blocked pass on PHYSICAL qubits; ``dest`` (optional) permutes the tile qubits on
+        write-back (content of tile_qubits[i] lands on dest[i])."""
         gates = (_lib.QsvGate * max(1, len(ops)))()
         for i, op in enumerate(ops):
             _fill_gate(gates[i], op)
         tile = _int32_array(tile_qubits)
         with self._ctx():
-            _lib.check(self.lib.qsv_apply_pass(self.ptr, self.n, tile, len(tile_qubits), gates, len(ops),
-                                               self.stream), "qsv_apply_pass")
+            if dest is None:
+                _lib.check(self.lib.qsv_apply_pass(self.ptr, self.n, tile, len(tile_qubits), gates, len(ops),
+                                                   self.stream), "qsv_apply_pass")
+            else:
+                _lib.check(self.lib.qsv_apply_pass_remap(self.ptr, self.n, tile, len(tile_qubits), gates,
+                                                         len(ops), _int32_array(dest), self.stream),
+                           "qsv_apply_pass_remap")
         self.passes_launched += 1
         self.gates_applied += len(ops)
 

@@ -16,71 +16,198 @@ program order, the set of gates for each pass:
 Pure host logic, no device access: unit-tested on CPU.
 """
 from . import _lib
+from .lower import GateOp
 
 DEFAULT_TILE_QUBITS = 11
 LOW_QUBITS = 4  # 16 amplitudes = 256 B contiguous runs (measured: 128 B runs 4.06 TB/s, 256 B 5.03, contiguous 5.27)
 
 
 class Pass:
-    __slots__ = ("tile_qubits", "ops")
+    """One launch of the pass kernel: ``tile_qubits`` and the qubits of ``ops`` are PHYSICAL bit positions
+    at the start of the pass; ``dest`` (or None) says where each tile qubit's content lands on
+    write-back (``dest[i]`` for ``tile_qubits[i]``)."""
 
-    def __init__(self, tile_qubits, ops):
+    __slots__ = ("tile_qubits", "ops", "dest")
+
+    def __init__(self, tile_qubits, ops, dest=None):
         self.tile_qubits = tuple(tile_qubits)
         self.ops = list(ops)
+        self.dest = None if dest is None else tuple(dest)
 
     def __repr__(self):
-        return "Pass(tile=%r, %d ops)" % (self.tile_qubits, len(self.ops))
+        return "Pass(tile=%r, %d ops%s)" % (self.tile_qubits, len(self.ops), ", remap" if self.dest else "")
 
 
-def _fill_tile(n_qubits, used, tile_size):
-    """used gate qubits + the lowest other qubits, up to tile_size."""
-    tile = set(used)
-    q = 0
-    while len(tile) < tile_size and q < n_qubits:
-        tile.add(q)
-        q += 1
-    return sorted(tile)
+def _relabel(op, layout):
+    return GateOp(op.kind, [layout[q] for q in op.qubits], op.matrix)
 
 
 def plan_passes(ops, n_qubits, tile_qubits=DEFAULT_TILE_QUBITS, max_gates=_lib.MAX_PASS_GATES,
-                max_payload=_lib.MAX_PASS_MATRIX_DOUBLES, window=4096):
-    """Group ``ops`` (GateOps with <= 2 qubits each) into passes.  Returns a list of Pass."""
+                max_payload=_lib.MAX_PASS_MATRIX_DOUBLES, layout=None, remap=False):
+    """Group ``ops`` (GateOps on LOGICAL qubits, <= 2 qubits each) into passes.
+
+    Frontier-greedy over the gate dependency DAG: a gate is *ready* when it is the first pending gate
+    on each of its qubits; among the ready gates that still fit the tile, the one that adds the fewest
+    new tile qubits is taken next (ties: program order), until nothing fits.  Only gates on disjoint
+    qubits are ever commuted.  (On QuantumVolume(33) this yields 7.3 gates per 11-qubit pass against
+    5.7 for a plain program-order scan.)
+
+    ``layout[q]`` is the physical bit of logical qubit q (identity if None); it is updated in place when
+    given.  With ``remap`` the write-back of each pass moves the tile qubits that the following gates
+    need first into the always-resident low bits (qsv_apply_pass_remap)."""
+    from collections import deque
+
+    if layout is None:
+        layout = list(range(n_qubits))
     tile_size = min(n_qubits, tile_qubits, _lib.MAX_TILE_QUBITS)
-    low = set(range(min(LOW_QUBITS, n_qubits)))
+    n_low = min(LOW_QUBITS, n_qubits)
     for op in ops:
         if len(op.qubits) > 2 or op.kind == "densek":
             raise ValueError("plan_passes only fuses 1- and 2-qubit gates")
-        if len(set(op.qubits) | low) > tile_size:
-            # cannot keep the low qubits in the tile for this gate (tiny tile sizes only)
-            low = set()
-    remaining = list(ops)
+    if tile_size < n_low + 2:
+        n_low = 0  # tiny tiles (tests): no pinned low bits
+    remap = remap and n_qubits > tile_size and n_low > 0
+
+    queues = {}
+    for idx, op in enumerate(ops):
+        for q in op.qubits:
+            queues.setdefault(q, deque()).append(idx)
+
+    def is_ready(idx):
+        return all(queues[q][0] == idx for q in ops[idx].qubits)
+
+    frontier = set(idx for idx in range(len(ops)) if is_ready(idx))
+    n_left = len(ops)
     passes = []
-    while remaining:
-        used = set(low)
-        blocked = set()
+    while n_left:
+        inv = [0] * n_qubits
+        for q, ph in enumerate(layout):
+            inv[ph] = q
+        low_log = [inv[ph] for ph in range(n_low)]  # logical qubits sitting in the pinned low bits
+        used = set(low_log)
         chosen = []
         payload = 0
-        keep = []
-        scanned = 0
-        for idx, op in enumerate(remaining):
-            qs = set(op.qubits)
-            take = False
-            if scanned < window and not (qs & blocked) and len(chosen) < max_gates:
-                if len(used | qs) <= tile_size and payload + op.payload_doubles <= max_payload:
-                    take = True
-            scanned += 1
-            if take:
-                used |= qs
-                chosen.append(op)
-                payload += op.payload_doubles
-            else:
-                blocked |= qs
-                keep.append(op)
-                if len(blocked) >= n_qubits or scanned >= window:
-                    keep.extend(remaining[idx + 1:])
-                    break
-        if not chosen:  # cannot happen: the first op always fits
+        while len(chosen) < max_gates:
+            best, best_cost = None, 99
+            for idx in frontier:
+                op = ops[idx]
+                cost = sum(1 for q in op.qubits if q not in used)
+                if len(used) + cost > tile_size or payload + op.payload_doubles > max_payload:
+                    continue
+                if cost < best_cost or (cost == best_cost and idx < best):
+                    best, best_cost = idx, cost
+            if best is None:
+                break
+            op = ops[best]
+            frontier.discard(best)
+            chosen.append(op)
+            used.update(op.qubits)
+            payload += op.payload_doubles
+            n_left -= 1
+            for q in op.qubits:
+                queues[q].popleft()
+            for q in op.qubits:
+                if queues[q] and is_ready(queues[q][0]):
+                    frontier.add(queues[q][0])
+        if not chosen:  # cannot happen: a ready gate always fits an empty tile
             raise RuntimeError("planner made no progress")
-        passes.append(Pass(_fill_tile(n_qubits, used, tile_size), chosen))
-        remaining = keep
+        # next pending gate of every qubit (position in program order)
+        next_use = {q: dq[0] for q, dq in queues.items() if dq}
+        far = len(ops) + 1
+        # fill the tile: qubits needed soonest first (they can be made resident), then the lowest bits
+        if len(used) < tile_size:
+            cand = sorted((q for q in range(n_qubits) if q not in used),
+                          key=lambda q: (next_use.get(q, far), layout[q]))
+            used |= set(cand[: tile_size - len(used)])
+        tile_log = sorted(used, key=lambda q: layout[q])
+        tile_phys = [layout[q] for q in tile_log]
+        dest = None
+        if remap and n_left:
+            # the n_low tile qubits needed soonest become the residents of the low bits
+            order = sorted(tile_log, key=lambda q: (next_use.get(q, far), layout[q] >= n_low, layout[q]))
+            sticky = set(order[:n_low])
+            incoming = [q for q in tile_log if q in sticky and layout[q] >= n_low]
+            evicted = [q for q in low_log if q not in sticky]
+            assert len(incoming) == len(evicted)
+            new_pos = {q: layout[q] for q in tile_log}
+            for qi, qe in zip(incoming, evicted):
+                new_pos[qi], new_pos[qe] = layout[qe], layout[qi]
+            if incoming:
+                dest = [new_pos[q] for q in tile_log]
+        passes.append(Pass(tile_phys, [_relabel(op, layout) for op in chosen], dest))
+        if dest is not None:
+            for q, d in zip(tile_log, dest):
+                layout[q] = d
+    return passes
+
+
+def plan_restore(layout, n_qubits, tile_qubits=DEFAULT_TILE_QUBITS):
+    """Passes (no gates, only write-back permutations) that bring ``layout`` back to the identity, i.e.
+    every logical qubit q to physical bit q.  ``layout`` is updated in place."""
+    tile_size = min(n_qubits, tile_qubits, _lib.MAX_TILE_QUBITS)
+    n_low = min(LOW_QUBITS, n_qubits)
+    if tile_size < n_low + 2:
+        n_low = 0
+    passes = []
+    guard = 0
+    while any(layout[q] != q for q in range(n_qubits)):
+        guard += 1
+        if guard > 4 * n_qubits:
+            raise RuntimeError("plan_restore does not converge")
+        inv = [0] * n_qubits
+        for q, ph in enumerate(layout):
+            inv[ph] = q  # content of position ph is logical qubit inv[ph]; its home is position inv[ph]
+        members = list(range(n_low))
+        in_tile = set(members)
+        dest = {}
+        starts = [ph for ph in range(n_qubits) if inv[ph] != ph]
+        starts.sort(key=lambda ph: (ph not in in_tile, ph))
+        for start in starts:
+            if start in dest:
+                continue
+            if start not in in_tile and len(in_tile) + 2 > tile_size:
+                continue
+            chain = [start]
+            extra = 0 if start in in_tile else 1
+            nxt = inv[start]
+            closed = False
+            while True:
+                if nxt == start:
+                    closed = True
+                    break
+                if nxt in dest or nxt in chain:
+                    break
+                cost = 0 if nxt in in_tile else 1
+                if len(in_tile) + extra + cost > tile_size:
+                    break
+                chain.append(nxt)
+                extra += cost
+                nxt = inv[nxt]
+            if len(chain) < 2:
+                continue
+            for i, ph in enumerate(chain):
+                if i + 1 < len(chain):
+                    dest[ph] = chain[i + 1]
+                else:
+                    dest[ph] = start if not closed else inv[ph]
+            for ph in chain:
+                if ph not in in_tile:
+                    in_tile.add(ph)
+                    members.append(ph)
+        if not dest:
+            raise RuntimeError("plan_restore made no progress")
+        for ph in members:
+            dest.setdefault(ph, ph)
+        # fill the tile up to its size with untouched positions (keeps the kernel's tile shape uniform)
+        ph = 0
+        while len(members) < tile_size and ph < n_qubits:
+            if ph not in in_tile:
+                in_tile.add(ph)
+                members.append(ph)
+                dest[ph] = ph
+            ph += 1
+        members.sort()
+        passes.append(Pass(members, [], [dest[ph] for ph in members]))
+        for ph in members:
+            layout[inv[ph]] = dest[ph]
     return passes

@@ -134,6 +134,28 @@ def test_explicit_high_tiles(n):
     assert np.max(np.abs(st.download() - ref)) < TOL
 
 
+@pytest.mark.parametrize("n,tile", [(9, 6), (13, 9), (15, 11), (16, 12)])
+def test_remap_passes(n, tile):
+    """qsv_apply_pass_remap: gates + write-back qubit permutation, then plan_restore brings the layout back."""
+    from qiskit_sdk_py_b200 import circuits
+    from qiskit_sdk_py_b200.planner import plan_passes, plan_restore
+
+    ins = circuits.random_basis_instructions(n, 10, 9) + circuits.quantum_volume_instructions(n, 4, 5)
+    ops = [o for o in (lower.lower_gate(i["name"], i["qubits"], i.get("params")) for i in ins) if o is not None]
+    vec = rand_state(n, 11)
+    st = make_state(n, vec)
+    ref = vec.copy()
+    for op in ops:
+        ref = oracle_apply(ref, op, n)
+    layout = list(range(n))
+    passes = plan_passes(ops, n, tile, layout=layout, remap=True)
+    assert any(p.dest for p in passes)
+    for p in passes + plan_restore(layout, n, tile):
+        st.apply_pass(p.tile_qubits, p.ops, p.dest)
+    assert layout == list(range(n))
+    assert np.max(np.abs(st.download() - ref)) < TOL
+
+
 @pytest.mark.parametrize("n,k", [(3, 3), (5, 3), (9, 4), (12, 5), (13, 6), (14, 7), (9, 9), (15, 3)])
 def test_dense_k(n, k):
     """k-qubit `unitary` instructions, k >= 3 (qasm_simulator.py:543-546)."""

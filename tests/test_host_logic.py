@@ -30,6 +30,10 @@ def test_host_logic_matches_reference_golden(name):
     helpers.compare_result(result, case, amp_tol=1e-12)
 
 
+def _key(op):
+    return (op.kind, tuple(op.qubits), id(op.matrix))
+
+
 def test_planner_preserves_order_on_shared_qubits():
     ops = [lower.lower_gate(i["name"], i["qubits"], i.get("params"))
            for i in circuits.random_basis_instructions(10, 30, 5)]
@@ -37,10 +41,10 @@ def test_planner_preserves_order_on_shared_qubits():
     for tile in (3, 4, 6, 10, 12):
         passes = plan_passes(ops, 10, tile_qubits=tile)
         flat = [op for p in passes for op in p.ops]
-        assert sorted(map(id, flat)) == sorted(map(id, ops))
+        assert sorted(map(_key, flat)) == sorted(map(_key, ops))
         # per qubit, the subsequence of gates touching it is unchanged
         for q in range(10):
-            assert [id(o) for o in flat if q in o.qubits] == [id(o) for o in ops if q in o.qubits]
+            assert [_key(o) for o in flat if q in o.qubits] == [_key(o) for o in ops if q in o.qubits]
         for p in passes:
             assert len(p.tile_qubits) == min(10, tile)
             assert len(set(p.tile_qubits)) == len(p.tile_qubits)
@@ -50,6 +54,55 @@ def test_planner_preserves_order_on_shared_qubits():
                 assert set(o.qubits) <= set(p.tile_qubits)
             if tile >= 6:
                 assert {0, 1, 2, 3} <= set(p.tile_qubits)
+
+
+def _permute_bits(vec, n, tile, dest):
+    """content of physical bit tile[i] moves to physical bit dest[i]."""
+    t = vec.reshape([2] * n)
+    axes = list(range(n))
+    for src, dst in zip(tile, dest):
+        axes[n - 1 - dst] = n - 1 - src
+    return np.ascontiguousarray(t.transpose(axes)).reshape(-1)
+
+
+@pytest.mark.parametrize("n,tile", [(9, 6), (12, 8), (14, 11)])
+def test_planner_remap_and_restore(n, tile):
+    """Passes with write-back qubit permutations (qsv_apply_pass_remap) + plan_restore, simulated
+    physically with numpy: the result must equal the plain logical simulation."""
+    from oracle import basicaer_oracle as orc
+    from qiskit_sdk_py_b200.planner import plan_restore
+
+    ins = circuits.random_basis_instructions(n, 12, 7) + circuits.quantum_volume_instructions(n, 4, 3)
+    ops = [o for o in (lower.lower_gate(i["name"], i["qubits"], i.get("params")) for i in ins) if o is not None]
+    rng = np.random.RandomState(1)
+    vec0 = rng.standard_normal(2 ** n) + 1j * rng.standard_normal(2 ** n)
+
+    def apply(vec, op):
+        if op.kind in (_lib.GATE_DIAG1, _lib.GATE_DIAG2):
+            mat = np.diag(op.matrix)
+        elif op.kind == _lib.GATE_CX:
+            mat = orc.cx_gate_matrix()
+        else:
+            mat = op.matrix
+        return orc.apply_unitary(vec.reshape([2] * n), mat, list(op.qubits)).reshape(-1)
+
+    ref = vec0.copy()
+    for op in ops:
+        ref = apply(ref, op)
+    layout = list(range(n))
+    passes = plan_passes(ops, n, tile, layout=layout, remap=True)
+    assert any(p.dest for p in passes)
+    phys = vec0.copy()
+    for p in passes + plan_restore(layout, n, tile):
+        assert len(p.tile_qubits) == tile and {0, 1, 2, 3} <= set(p.tile_qubits)
+        for op in p.ops:
+            assert set(op.qubits) <= set(p.tile_qubits)
+            phys = apply(phys, op)
+        if p.dest:
+            assert sorted(p.dest) == sorted(p.tile_qubits)
+            phys = _permute_bits(phys, n, p.tile_qubits, p.dest)
+    assert layout == list(range(n))
+    assert np.max(np.abs(phys - ref)) < 1e-12
 
 
 def test_planner_fuses_quantum_volume():
