@@ -139,6 +139,14 @@ int qsv_sample(const double* src, int from_amplitudes, int log2_bins, const doub
                int shots, int64_t* host_out_idx, int exact_order, void* ws, double* host_total,
                void* stream);
 
+/* <psi| P |psi> for the Pauli string with Z (or Y) on the bits of z_mask and X (or Y) on the bits of x_mask,
+ * times (phase_re + i phase_im) for the with-X case.  Replaces the serial Cython loops
+ * expval_pauli_no_x / expval_pauli_with_x (qiskit/quantum_info/states/cython/exp_value.pyx:37-94, called
+ * from Statevector.expectation_value, states/statevector.py:377-408) -- SURVEY 8(f) rank 4.  `ws` as for
+ * qsv_prob_qubit.  Synchronises the stream. */
+int qsv_expval_pauli(const double* sv, int n_qubits, uint64_t z_mask, uint64_t x_mask, double phase_re,
+                     double phase_im, void* ws, double* host_out, void* stream);
+
 /* psi[abs(psi) < threshold] = 0 (qasm_simulator.py:330-334, unitary_simulator.py:201-207). */
 int qsv_chop(double* sv, int n_qubits, double threshold, void* stream);
 

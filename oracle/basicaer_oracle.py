@@ -615,3 +615,53 @@ class OracleUnitarySimulator:
             "time_taken": end - start,
             "header": header,
         }
+
+
+# --------------------------------------------------------------------------------------
+# Pauli expectation values (SURVEY 8(f) rank 4 -- the reference's only native code near the path)
+# --------------------------------------------------------------------------------------
+def _parity(values):
+    v = values.astype(np.uint64)
+    for shift in (32, 16, 8, 4, 2, 1):
+        v ^= v >> np.uint64(shift)
+    return (v & np.uint64(1)).astype(bool)
+
+
+def expval_pauli(data, label):
+    """<psi|P|psi> for a Pauli label ("XIZY": leftmost character = highest qubit).
+
+    Restates Statevector._expectation_value_pauli (qiskit/quantum_info/states/statevector.py:377-408)
+    with the Cython loops expval_pauli_no_x / expval_pauli_with_x
+    (qiskit/quantum_info/states/cython/exp_value.pyx:37-49, :52-94) vectorised in numpy.  For a Pauli
+    built from a plain label the group phase is 0, so only the (-i)^(#Y) factor inside the loop remains.
+    Note the reference's quirk for the identity: it returns the norm, not the squared norm (:397-398)."""
+    data = np.asarray(data, dtype=complex).reshape(-1)
+    n = len(label)
+    assert data.size == 2 ** n
+    z_mask = x_mask = n_y = 0
+    for q, c in enumerate(reversed(label.upper())):
+        if c in "ZY":
+            z_mask |= 1 << q
+        if c in "XY":
+            x_mask |= 1 << q
+        n_y += c == "Y"
+    if x_mask + z_mask == 0:
+        return float(np.linalg.norm(data))
+    idx = np.arange(data.size, dtype=np.uint64)
+    if x_mask == 0:
+        p = data.real * data.real + data.imag * data.imag
+        sign = np.where(_parity(idx & np.uint64(z_mask)), -1.0, 1.0)
+        return float(np.sum(sign * p))
+    phase = (-1j) ** n_y
+    x_max = x_mask.bit_length() - 1
+    i = np.arange(data.size // 2, dtype=np.uint64)
+    mask_u = np.uint64(~((2 << x_max) - 1) & (2 ** 64 - 1))
+    mask_l = np.uint64((1 << x_max) - 1)
+    i0 = ((i << np.uint64(1)) & mask_u) | (i & mask_l)
+    i1 = i0 ^ np.uint64(x_mask)
+    d0, d1 = data[i0.astype(np.int64)], data[i1.astype(np.int64)]
+    v0 = (phase * (d1 * np.conj(d0))).real
+    v1 = (phase * (d0 * np.conj(d1))).real
+    s0 = np.where(_parity(i0 & np.uint64(z_mask)), -1.0, 1.0)
+    s1 = np.where(_parity(i1 & np.uint64(z_mask)), -1.0, 1.0)
+    return float(np.sum(s0 * v0) + np.sum(s1 * v1))

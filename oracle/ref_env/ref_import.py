@@ -75,6 +75,10 @@ def _install_stubs():
         fj.JsonSchemaException = exc.JsonSchemaException
     if "constraint" not in sys.modules:
         _stub_module("constraint")
+    # the reference's expectation-value extension, if oracle/build_ref.py compiled it into oracle/_ref/
+    real = _load_compiled_exp_value()
+    if real is not None:
+        sys.modules["qiskit.quantum_info.states.cython.exp_value"] = real
     # Cython extensions (not built in the read-only tree, none on the BasicAer path)
     for name in (
         "qiskit.quantum_info.states.cython.exp_value",
@@ -83,6 +87,23 @@ def _install_stubs():
     ):
         if name not in sys.modules:
             _stub_module(name)
+
+
+def _load_compiled_exp_value():
+    import glob
+    import importlib.machinery
+    import importlib.util
+
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cands = glob.glob(os.path.join(here, "_ref", "exp_value*.so"))
+    if not cands:
+        return None
+    name = "qiskit.quantum_info.states.cython.exp_value"
+    loader = importlib.machinery.ExtensionFileLoader(name, cands[0])
+    spec = importlib.util.spec_from_file_location(name, cands[0], loader=loader)
+    mod = importlib.util.module_from_spec(spec)
+    loader.exec_module(mod)
+    return mod
 
 
 def import_reference():

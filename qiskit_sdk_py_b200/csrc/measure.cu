@@ -74,6 +74,42 @@ reduce_pairs_kernel(const double* __restrict__ partial, int nblocks, double* __r
   }
 }
 
+// ---- Pauli expectation value <psi| P |psi> for a Pauli string given by its z / x bit masks.  Restates
+// /root/reference/qiskit/quantum_info/states/cython/exp_value.pyx: expval_pauli_no_x (:37-49) when
+// x_mask == 0, expval_pauli_with_x (:52-94) otherwise; the serial loop becomes a grid-stride reduction
+// with the same two-stage deterministic summation as prob_qubit. ----
+__global__ void __launch_bounds__(kThreads)
+expval_pauli_kernel(const double2* __restrict__ sv, u64 n_amps, u64 z_mask, u64 x_mask, int x_max, double2 phase,
+                    double* __restrict__ partial) {
+  double acc = 0.0, dummy = 0.0;
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  if (x_mask == 0) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_amps; i += stride) {
+      const double2 a = sv[i];
+      const double p = a.x * a.x + a.y * a.y;
+      acc += (__popcll(i & z_mask) & 1) ? -p : p;
+    }
+  } else {
+    const u64 mask_u = ~((2ull << x_max) - 1ull), mask_l = (1ull << x_max) - 1ull;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < (n_amps >> 1); i += stride) {
+      const u64 i0 = ((i << 1) & mask_u) | (i & mask_l);
+      const u64 i1 = i0 ^ x_mask;
+      const double2 d0 = sv[i0], d1 = sv[i1];
+      // Re(phase * d1 * conj(d0)) and Re(phase * d0 * conj(d1))
+      const double re = d1.x * d0.x + d1.y * d0.y, im = d1.y * d0.x - d1.x * d0.y;
+      const double v0 = phase.x * re - phase.y * im;
+      const double v1 = phase.x * re + phase.y * im;
+      acc += (__popcll(i0 & z_mask) & 1) ? -v0 : v0;
+      acc += (__popcll(i1 & z_mask) & 1) ? -v1 : v1;
+    }
+  }
+  block_sum2(acc, dummy);
+  if (threadIdx.x == 0) {
+    partial[2 * blockIdx.x] = acc;
+    partial[2 * blockIdx.x + 1] = 0.0;
+  }
+}
+
 // ---- marginal over m measured qubits: grid = (parts, bins) ----
 struct MargDesc {
   int32_t n, m, log2_parts, pad;
@@ -336,6 +372,30 @@ int qsv_norm2(const double* sv, int n, void* ws, double* host_out, void* stream)
   const int rc = qsv_prob_qubit(sv, n, 0, ws, p, stream);
   if (rc) return rc;
   *host_out = p[0] + p[1];
+  return 0;
+}
+
+int qsv_expval_pauli(const double* sv, int n, uint64_t z_mask, uint64_t x_mask, double phase_re, double phase_im,
+                     void* ws, double* host_out, void* stream) {
+  if (!sv || !ws || !host_out || n < 1 || n > 40) return fail(QSV_EINVAL, "qsv_expval_pauli: bad arguments");
+  const u64 n_amps = 1ull << n;
+  if ((z_mask | x_mask) >= n_amps) return fail(QSV_EINVAL, "qsv_expval_pauli: mask has bits beyond n_qubits");
+  cudaStream_t s = (cudaStream_t)stream;
+  int x_max = 0;
+  for (int j = 0; j < n; j++)
+    if ((x_mask >> j) & 1ull) x_max = j;
+  double* partial = reinterpret_cast<double*>(ws);
+  const u64 work = x_mask ? (n_amps >> 1) : n_amps;
+  const int blocks = (int)std::max<u64>(1, std::min<u64>((work + kThreads - 1) / kThreads, kReduceBlocks));
+  expval_pauli_kernel<<<blocks, kThreads, 0, s>>>(reinterpret_cast<const double2*>(sv), n_amps, z_mask, x_mask, x_max,
+                                                  make_double2(phase_re, phase_im), partial);
+  QSV_LAUNCHED();
+  reduce_pairs_kernel<<<1, kThreads, 0, s>>>(partial, blocks, partial + 2 * kReduceBlocks);
+  QSV_LAUNCHED();
+  double out[2];
+  QSV_CUDA(cudaMemcpyAsync(out, partial + 2 * kReduceBlocks, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  QSV_CUDA(cudaStreamSynchronize(s));
+  *host_out = out[0];
   return 0;
 }
 

@@ -45,48 +45,83 @@ constexpr int kMaxStages = kMaxOps;
 struct __align__(4) PassOp {
   uint8_t kind, t0, t1, ngl;  // t0/t1: tile-local gate bits; ngl = log2(#groups in a warp's sub-cube)
   uint16_t moff;              // offset (doubles) of the matrix in PassDesc::mats
-  uint16_t z0, z1;            // swz(1 << t0), swz(1 << t1)
-  uint16_t col[6];            // swizzled masks of the free inner bits: col[0..2] vary inside a warp step
+  uint16_t z0, z1;            // slot increments of the gate bits: cj[t0], cj[t1]
+  uint16_t col[6];            // slot increments of the free inner bits: col[0..2] vary inside a warp step
 };
 
 struct __align__(4) PassStage {
   uint8_t first_op, n_ops, n_inner, n_outer;
   uint8_t ebit[kInner];   // inner tile bits in element order (bit j of the in-warp element index)
   uint8_t obit[4];        // outer tile bits (bit j of the warp id)
-  uint16_t ecol[kInner];  // swz(1 << ebit[j])
-  uint16_t ocol[4];       // swz(1 << obit[j])
+  uint16_t ecol[kInner];  // cj[ebit[j]]
+  uint16_t ocol[4];       // cj[obit[j]]
 };
 
 struct PassDesc {
   int32_t n, b, nops, nstages;
   uint32_t n_tiles;
-  uint32_t pad2[3];
-  uint8_t tb[16];   // ascending physical bit position of each tile-local bit
-  uint8_t vec[16];  // bank vector of each tile-local bit (pass-specific XOR swizzle), vec[j] = 1<<j for j<3
-  uint8_t src_of[16];  // write-back permutation: tile-local position j receives the content of bit src_of[j]
+  uint32_t flags;       // QSV_DEBUG_FLAGS (profiling experiments)
+  uint32_t pb_ld;       // log2(amplitudes per bulk-load piece): contiguous low tile bits, at most 3 (128 B)
+  uint32_t pb_st;       // same for the write-back (smaller if the write-back permutes low bits)
+  uint8_t tb[16];       // physical bit of tile-local position j (positions 0..2 = the three lowest tile qubits)
+  uint8_t tbs[16];      // the tile's physical bits in ascending order (tile base computation)
+  uint16_t cj[16];      // shared-memory slot increment of tile-local bit j (see slot layout below)
+  uint8_t src_of[16];   // write-back permutation: tile-local position j receives the content of bit src_of[j]
   PassStage stages[kMaxStages];
   PassOp ops[kMaxOps];
   double mats[kMaxMat];
 };
 
-// Pass-specific XOR swizzle of a tile-local amplitude index (16-byte slots; bank group = slot & 7).
-// Tile bit j >= 3 toggles the bank bits vec[j]; three index bits whose vectors are linearly independent
-// over GF(2) spread over all 8 bank groups, so the accesses of a quarter warp (LDS/STS.128) or of a
-// half warp reading 8-byte halves (LDS.64) are conflict-free.  The host picks vec[] per pass.
-__host__ __device__ __forceinline__ uint32_t swz(const uint8_t* vec, int b, uint32_t li) {
-  uint32_t f = 0;
-  for (int j = 3; j < b; j++)
-    if ((li >> j) & 1u) f ^= vec[j];
-  return li ^ f;
+// Shared-memory slot layout (16-byte slots; bank group = slot & 7).  Amplitude li of the tile lives at
+//     slot(li) = sum_j bit_j(li) * cj[j],   cj[j] = 2^j for j < 3,   cj[j] = 2^j + pad_j for j >= 3,
+// i.e. the 128-byte pieces (8 amplitudes, low three bits) stay contiguous -- they are moved by single
+// TMA bulk copies -- and padding slots are inserted between pieces.  pad_j is super-increasing
+// (1,2,4,9,18,36,73,146,292: pieces never overlap) with pad_j mod 8 = 2^(j mod 3), so bit j shifts the
+// bank group by 2^(j mod 3): any three index bits of pairwise different class j mod 3 spread over all 8
+// bank groups, which makes the accesses of a quarter warp (LDS/STS.128) or of a half warp reading
+// 8-byte halves (LDS.64) conflict-free.  The host orders the tile qubits so that the two bits of every
+// dense gate fall in different classes.  Every index map of the kernel is a sum of per-bit increments.
+__host__ __device__ __forceinline__ uint32_t pad_of_bit(int j) {
+  const uint32_t pads[13] = {0, 0, 0, 1, 2, 4, 9, 18, 36, 73, 146, 292, 585};
+  return pads[j];
 }
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+// ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) and their mbarrier ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// global -> shared, completion counted on the mbarrier
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                   smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// shared -> global, tracked by the thread's bulk async-group
+__device__ __forceinline__ void bulk_store(void* gdst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(smem_u32(smem_src)),
+               "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
 // D(8x8) += A(8x4) * B(4x8) on the FP64 tensor path (SASS: DMMA.8x8x4).
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
@@ -98,7 +133,7 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 // physical base address (in amplitudes) of tile t: spread t over the non-tile bits
 __device__ __forceinline__ u64 tile_base(const PassDesc& d, u64 t) {
   for (int j = 0; j < d.b; j++) {
-    const int p = d.tb[j];
+    const int p = d.tbs[j];
     t = ((t >> p) << (p + 1)) | (t & ((1ull << p) - 1ull));
   }
   return t;
@@ -111,20 +146,23 @@ struct __align__(16) OpRec {
   uint16_t moff;
 };
 
-// Persistent kernel, two 512-thread CTAs per SM, one 64 KiB tile buffer each: while one CTA waits for
-// HBM (cp.async load of its next tile, write-back of the last) the other one runs its gates, so the
-// memory phases of one overlap the FP64 / shared-memory phases of the other.  A CTA owns a contiguous
-// range of tiles.
+// Persistent kernel, 2-4 CTAs per SM (one warp per 2^8 amplitudes of the tile), one tile buffer each:
+// while one CTA waits for HBM (TMA bulk load of its next tile, bulk write-back of the last) the others
+// run their gates, so the memory phases of one overlap the FP64 / shared-memory phases of the others.
+// A CTA owns a contiguous range of tiles.  The tile moves between HBM and shared memory with TMA bulk
+// copies of 128-byte pieces (one per thread), which bypass the LSU/L1TEX pipe that the gates saturate.
 __global__ void __launch_bounds__(kMaxPT, 2)
 tile_pass_kernel(double2* __restrict__ sv, const __grid_constant__ PassDesc d) {
-  // dynamic shared memory: the tile, then the per-pass tables (sized by the pass, so that short passes
-  // leave room for more resident CTAs)
+  // dynamic shared memory: the (padded) tile, then the per-pass tables (sized by the pass, so that short
+  // passes leave room for more resident CTAs)
   extern __shared__ double2 tile[];
-  __shared__ u64 hi_off[8];
-  __shared__ uint16_t swz_it[8];
-  __shared__ uint16_t swz_it_st[8];
+  __shared__ __align__(8) uint64_t ld_bar;
   const int nops_all = d.nops, nst_all = d.nstages;
-  double (*frag)[64] = reinterpret_cast<double (*)[64]>(tile + (1u << d.b));   // [nops][64] B fragments
+  const int b = d.b;
+  const uint32_t tile_amps = 1u << b;
+  uint32_t tile_slots = tile_amps;
+  for (int j = 3; j < b; j++) tile_slots += pad_of_bit(j);
+  double (*frag)[64] = reinterpret_cast<double (*)[64]>(tile + tile_slots);    // [nops][64] B fragments
   OpRec* oprec = reinterpret_cast<OpRec*>(frag + nops_all);                     // [nops]
   uint32_t (*opl)[32] = reinterpret_cast<uint32_t (*)[32]>(oprec + nops_all);   // [nops][32] lane slots
   uint32_t (*st_warp)[kWarps] = reinterpret_cast<uint32_t (*)[kWarps]>(opl + nops_all);  // [nstages][16]
@@ -132,30 +170,15 @@ tile_pass_kernel(double2* __restrict__ sv, const __grid_constant__ PassDesc d) {
   uint32_t (*st_it)[8] = reinterpret_cast<uint32_t (*)[8]>(st_lane + nst_all);           // [nstages][8]
 
   const uint32_t tid = threadIdx.x;
-  const int b = d.b;
-  const uint32_t tile_amps = 1u << b;
-  const uint32_t dbg = d.pad2[0];  // QSV_DEBUG_FLAGS (profiling experiments): 1 = no write-back, 2 = no loads, 4 = no gates
+  const uint32_t dbg = d.flags;  // 1 = no write-back, 2 = no loads, 4 = no gates
   const int nops = d.nops, nstages = (dbg & 4u) ? 0 : d.nstages;
+  const uint32_t kPT = blockDim.x;
 
   // ---- per-kernel setup (amortised over all tiles of this CTA): every lane/warp dependent index of
-  // the pass is tile-invariant, so it is digested once into shared-memory tables ----
-  const uint32_t kPT = blockDim.x;
-  const int kTidBits = 31 - __clz(kPT);
-  const int lo_bits = b < kTidBits ? b : kTidBits;
-  u64 lo_off = 0;
-  for (int j = 0; j < lo_bits; j++) lo_off |= (u64)((tid >> j) & 1u) << d.tb[j];
+  // the pass is tile-invariant, so it is digested once into shared-memory tables / registers ----
   u64 tile_mask = 0;  // physical bit mask of the tile qubits
   for (int j = 0; j < b; j++) tile_mask |= 1ull << d.tb[j];
-  if (tid < 8) {
-    u64 off = 0;
-    for (int j = kTidBits; j < b; j++) off |= (u64)((tid >> (j - kTidBits)) & 1u) << d.tb[j];
-    hi_off[tid] = off;
-    swz_it[tid] = (uint16_t)swz(d.vec, b, tid << kTidBits);
-    uint32_t sst = 0;  // write-back source slot of loop index bits: position j reads the content of bit src_of[j]
-    for (int j = kTidBits; j < b; j++)
-      if ((tid >> (j - kTidBits)) & 1u) sst ^= swz(d.vec, b, 1u << d.src_of[j]);
-    swz_it_st[tid] = (uint16_t)sst;
-  }
+  if (tid == 0) mbar_init(&ld_bar, kPT);
   for (int idx = tid; idx < nops * 64; idx += kPT) {
     const int o = idx >> 6, e = idx & 63;
     const PassOp& op = d.ops[o];
@@ -173,12 +196,12 @@ tile_pass_kernel(double2* __restrict__ sv, const __grid_constant__ PassDesc d) {
     if (e < 32) {
       const uint32_t g = e >> 2, c = e & 3u;
       uint32_t s_g = 0;
-      if (g & 1u) s_g ^= op.col[0];
-      if (g & 2u) s_g ^= op.col[1];
-      if (g & 4u) s_g ^= op.col[2];
+      if (g & 1u) s_g += op.col[0];
+      if (g & 2u) s_g += op.col[1];
+      if (g & 4u) s_g += op.col[2];
       const uint32_t ld_x = (c & 2u) ? op.z0 : 0u;                                 // amplitude c>>1 of the k-slice
-      const uint32_t st_x = ((c & 1u) ? op.z0 : 0u) ^ ((c & 2u) ? op.z1 : 0u);     // amplitude c of the group
-      opl[o][e] = (s_g ^ ld_x) | ((s_g ^ st_x) << 16);
+      const uint32_t st_x = ((c & 1u) ? op.z0 : 0u) + ((c & 2u) ? op.z1 : 0u);     // amplitude c of the group
+      opl[o][e] = (s_g + ld_x) | ((s_g + st_x) << 16);
     }
     if (e == 32) {
       OpRec r;
@@ -194,29 +217,37 @@ tile_pass_kernel(double2* __restrict__ sv, const __grid_constant__ PassDesc d) {
     uint32_t li = 0, sl = 0;
     if (e < kWarps) {  // warp part
       for (int j = 0; j < st.n_outer; j++)
-        if ((e >> j) & 1) { li |= 1u << st.obit[j]; sl ^= st.ocol[j]; }
+        if ((e >> j) & 1) { li |= 1u << st.obit[j]; sl += st.ocol[j]; }
       st_warp[sidx][e] = li | (sl << 16);
     } else if (e >= 24 && e < 32) {  // element iteration part (element bits 5, 6, 7)
       for (int j = 0; j < 3; j++)
-        if ((((e - 24) >> j) & 1) && 5 + j < st.n_inner) { li |= 1u << st.ebit[5 + j]; sl ^= st.ecol[5 + j]; }
+        if ((((e - 24) >> j) & 1) && 5 + j < st.n_inner) { li |= 1u << st.ebit[5 + j]; sl += st.ecol[5 + j]; }
       st_it[sidx][e - 24] = li | (sl << 16);
     } else if (e >= 32) {  // lane part (element bits 0..4)
       for (int j = 0; j < 5 && j < st.n_inner; j++)
-        if (((e - 32) >> j) & 1) { li |= 1u << st.ebit[j]; sl ^= st.ecol[j]; }
+        if (((e - 32) >> j) & 1) { li |= 1u << st.ebit[j]; sl += st.ecol[j]; }
       st_lane[sidx][e - 32] = li | (sl << 16);
     }
   }
-  const uint32_t s_tid = swz(d.vec, b, tid);
-  uint32_t s_tid_st = 0;
-  for (int j = 0; j < lo_bits; j++)
-    if ((tid >> j) & 1u) s_tid_st ^= swz(d.vec, b, 1u << d.src_of[j]);
-  const bool permuted = d.pad2[1] != 0;
-  const uint32_t iters = tile_amps > kPT ? tile_amps / kPT : 1;
-  const bool active = tid < tile_amps;
-  const bool ld_on = active && !(dbg & 2u), st_on = active && !(dbg & 1u);
+  // bulk-copy pieces of this thread: piece p covers tile-local bits [0, pb); its index bits are the
+  // tile-local bits pb.. ; thread t owns pieces t, t + kPT, ...
+  const uint32_t pb_ld = d.pb_ld, pb_st = d.pb_st;
+  const uint32_t np_ld = tile_amps >> pb_ld, np_st = tile_amps >> pb_st;
+  const uint32_t ld_bytes = 16u << pb_ld, st_bytes = 16u << pb_st;
+  uint32_t my_ld_bytes = 0;
+  for (uint32_t pc = tid; pc < np_ld; pc += kPT) my_ld_bytes += ld_bytes;
+  // the common case (128-byte pieces, one per thread) keeps its two offsets in registers
+  u64 g_ld0 = 0, g_st0 = 0;
+  uint32_t s_ld0 = 0, s_st0 = 0;
+  for (int j = 0; j + (int)pb_ld < b; j++)
+    if ((tid >> j) & 1u) { g_ld0 |= 1ull << d.tb[pb_ld + j]; s_ld0 += d.cj[pb_ld + j]; }
+  for (int j = 0; j + (int)pb_st < b; j++)
+    if ((tid >> j) & 1u) { g_st0 |= 1ull << d.tb[pb_st + j]; s_st0 += d.cj[d.src_of[pb_st + j]]; }
+  const bool ld_on = !(dbg & 2u), st_on = !(dbg & 1u);
   const uint32_t lane = tid & 31u, wid = tid >> 5;
   const uint32_t g = lane >> 2;
   const char* tb8 = reinterpret_cast<const char*>(tile) + (lane & 1u) * 8u;
+  fence_proxy_async();  // make the mbarrier initialisation visible to the async proxy
   __syncthreads();
 
   // contiguous range of tiles for this CTA; the tile base walks the non-tile bits: next = ((base | M) + 1) & ~M
@@ -225,19 +256,30 @@ tile_pass_kernel(double2* __restrict__ sv, const __grid_constant__ PassDesc d) {
   const u64 t_begin = (u64)blockIdx.x * per;
   const u64 t_end = t_begin + per < n_tiles ? t_begin + per : n_tiles;
   u64 base = t_begin < n_tiles ? tile_base(d, t_begin) : 0;
+  uint32_t parity = 0;
   for (u64 t = t_begin; t < t_end; t++, base = ((base | tile_mask) + 1) & ~tile_mask) {
-    // ---- load: one HBM read of the tile ----
-    if (ld_on) {
-      const double2* gp = sv + base + lo_off;
-#pragma unroll 8
-      for (uint32_t it = 0; it < iters; it++) cp_async16(tile + (s_tid ^ swz_it[it]), gp + hi_off[it]);
+    // ---- load: one HBM read of the tile (TMA bulk copies, completion on the mbarrier) ----
+    if (t != t_begin) {
+      bulk_wait_read();   // my write-back pieces of the previous tile have left shared memory
+      __syncthreads();    // ... and so have everybody else's
     }
-    cp_async_commit();
-    cp_async_wait<0>();
+    if (ld_on) {
+      mbar_arrive_expect_tx(&ld_bar, my_ld_bytes);
+      if (tid < np_ld) bulk_load(tile + s_ld0, sv + base + g_ld0, ld_bytes, &ld_bar);
+      for (uint32_t pc = tid + kPT; pc < np_ld; pc += kPT) {  // small pieces only (tile without the low qubits)
+        u64 go = 0;
+        uint32_t so = 0;
+        for (int j = 0; j + (int)pb_ld < b; j++)
+          if ((pc >> j) & 1u) { go |= 1ull << d.tb[pb_ld + j]; so += d.cj[pb_ld + j]; }
+        bulk_load(tile + so, sv + base + go, ld_bytes, &ld_bar);
+      }
+      mbar_wait(&ld_bar, parity);
+      parity ^= 1u;
+    }
 
     int o = 0;
     for (int sidx = 0; sidx < nstages; sidx++) {
-      __syncthreads();  // stage boundary: warps re-partition the tile (the first one also publishes the loads)
+      if (sidx > 0) __syncthreads();  // stage boundary: warps re-partition the tile
       const uint32_t n_inner = d.stages[sidx].n_inner, n_outer = d.stages[sidx].n_outer;
       const int o_end = o + d.stages[sidx].n_ops;
       const bool warp_on = wid < (1u << n_outer);  // small tiles: fewer sub-cubes than warps
@@ -254,28 +296,28 @@ tile_pass_kernel(double2* __restrict__ sv, const __grid_constant__ PassDesc d) {
           // ---- FP64 tensor path: 8 groups per warp step, up to 8 steps per sub-cube ----
           const double b0 = frag[o][lane], b1 = frag[o][32 + lane];
           const uint32_t v = opl[o][lane];
-          const uint32_t a_ld = (s_w ^ (v & 0xffffu)) << 4;  // byte offsets of 16-byte slots
-          const uint32_t a_st = (s_w ^ (v >> 16)) << 4;
+          const uint32_t a_ld = (s_w + (v & 0xffffu)) << 4;  // byte offsets of 16-byte slots
+          const uint32_t a_st = (s_w + (v >> 16)) << 4;
           const uint32_t z1b = (uint32_t)rec.z1 << 4;
           const uint32_t c3 = (uint32_t)rec.c3 << 4, c4 = (uint32_t)rec.c4 << 4, c5 = (uint32_t)rec.c5 << 4;
           if (rec.ngl == 6u) {
 #pragma unroll
             for (int hb = 0; hb < 2; hb++) {
               const uint32_t xh = hb ? c5 : 0u;
-              const uint32_t xo[4] = {xh, xh ^ c3, xh ^ c4, xh ^ c3 ^ c4};
+              const uint32_t xo[4] = {xh, xh + c3, xh + c4, xh + c3 + c4};
               double x0[4], x1[4];
 #pragma unroll
               for (int it = 0; it < 4; it++) {
-                const uint32_t a = a_ld ^ xo[it];
+                const uint32_t a = a_ld + xo[it];
                 x0[it] = *reinterpret_cast<const double*>(tb8 + a);
-                x1[it] = *reinterpret_cast<const double*>(tb8 + (a ^ z1b));
+                x1[it] = *reinterpret_cast<const double*>(tb8 + (a + z1b));
               }
 #pragma unroll
               for (int it = 0; it < 4; it++) {
                 double d0 = 0.0, d1 = 0.0;
                 dmma884(d0, d1, x0[it], b0);
                 dmma884(d0, d1, x1[it], b1);
-                *reinterpret_cast<double2*>(reinterpret_cast<char*>(tile) + (a_st ^ xo[it])) = make_double2(d0, d1);
+                *reinterpret_cast<double2*>(reinterpret_cast<char*>(tile) + (a_st + xo[it])) = make_double2(d0, d1);
               }
             }
           } else {
@@ -283,73 +325,109 @@ tile_pass_kernel(double2* __restrict__ sv, const __grid_constant__ PassDesc d) {
             const uint32_t n_it = ng > 8u ? (ng >> 3) : 1u;
             for (uint32_t it = 0; it < n_it; it++) {
               uint32_t xo = 0;
-              if (it & 1u) xo ^= c3;
-              if (it & 2u) xo ^= c4;
-              if (it & 4u) xo ^= c5;
+              if (it & 1u) xo += c3;
+              if (it & 2u) xo += c4;
+              if (it & 4u) xo += c5;
               const bool valid = (g | (it << 3)) < ng;
               double x0 = 0.0, x1 = 0.0;
               if (valid) {
-                const uint32_t a = a_ld ^ xo;
+                const uint32_t a = a_ld + xo;
                 x0 = *reinterpret_cast<const double*>(tb8 + a);
-                x1 = *reinterpret_cast<const double*>(tb8 + (a ^ z1b));
+                x1 = *reinterpret_cast<const double*>(tb8 + (a + z1b));
               }
               double d0 = 0.0, d1 = 0.0;
               dmma884(d0, d1, x0, b0);
               dmma884(d0, d1, x1, b1);
-              if (valid) *reinterpret_cast<double2*>(reinterpret_cast<char*>(tile) + (a_st ^ xo)) = make_double2(d0, d1);
+              if (valid) *reinterpret_cast<double2*>(reinterpret_cast<char*>(tile) + (a_st + xo)) = make_double2(d0, d1);
             }
           }
         } else {
           // ---- element-wise kinds: each lane owns elements e = lane | it << 5 of the sub-cube ----
           const uint32_t n_el = 1u << n_inner;
-          const uint32_t lv = wv ^ st_lane[sidx][lane];  // li (low 16) and slot (high 16): disjoint bits, XOR == OR
-          const double* m = d.mats + rec.moff;
-          for (uint32_t it = 0; it < 8u; it++) {
-            if ((lane | (it << 5)) >= n_el) break;
-            const uint32_t ev = lv ^ st_it[sidx][it];
-            const uint32_t li = ev & 0xffffu, s = ev >> 16;
-            if (rec.kind == QSV_GATE_DIAG1) {
-              const double* f = m + 2 * ((li >> rec.t0) & 1u);
-              tile[s] = cmul(make_double2(f[0], f[1]), tile[s]);
-            } else if (rec.kind == QSV_GATE_DIAG2) {
-              const double* f = m + 2 * (((li >> rec.t0) & 1u) | (((li >> rec.t1) & 1u) << 1));
-              tile[s] = cmul(make_double2(f[0], f[1]), tile[s]);
-            } else if (rec.kind == QSV_GATE_CX) {
-              // control t0 set, target t1 clear: swap with the target-set partner (same sub-cube)
-              if (((li >> rec.t0) & 1u) && !((li >> rec.t1) & 1u)) {
-                const uint32_t sp = s ^ rec.z1;
-                const double2 a = tile[s], p = tile[sp];
-                tile[s] = p;
-                tile[sp] = a;
+          const uint32_t lv = wv + st_lane[sidx][lane];  // li (low 16 bits) and slot (high 16): no carries between them
+          const bool is_diag = rec.kind == QSV_GATE_DIAG1 || rec.kind == QSV_GATE_DIAG2;
+          if (is_diag) {
+            // a run of consecutive diagonal gates of the stage is applied in one read-modify-write
+            int o_last = o;
+            while (o_last + 1 < o_end && (oprec[o_last + 1].kind == QSV_GATE_DIAG1 || oprec[o_last + 1].kind == QSV_GATE_DIAG2))
+              o_last++;
+            // the lane's (up to 8) elements stay in registers while the run's factors stream by
+            double2 a[8];
+            uint32_t evs[8];
+#pragma unroll
+            for (int it = 0; it < 8; it++) {
+              evs[it] = lv + st_it[sidx][it];
+              if ((lane | ((uint32_t)it << 5)) < n_el) a[it] = tile[evs[it] >> 16];
+            }
+            for (int q = o; q <= o_last; q++) {
+              const OpRec rq = oprec[q];
+              const double* m = d.mats + rq.moff;
+              const double2 m0 = make_double2(m[0], m[1]), m1 = make_double2(m[2], m[3]);
+              if (rq.kind == QSV_GATE_DIAG1) {
+#pragma unroll
+                for (int it = 0; it < 8; it++) a[it] = cmul(((evs[it] >> rq.t0) & 1u) ? m1 : m0, a[it]);
+              } else {
+                const double2 m2 = make_double2(m[4], m[5]), m3 = make_double2(m[6], m[7]);
+#pragma unroll
+                for (int it = 0; it < 8; it++) {
+                  const uint32_t b0 = (evs[it] >> rq.t0) & 1u, b1 = (evs[it] >> rq.t1) & 1u;
+                  a[it] = cmul(b1 ? (b0 ? m3 : m2) : (b0 ? m1 : m0), a[it]);
+                }
               }
-            } else if (rec.kind == QSV_GATE_DENSE1) {
-              // scalar 2x2 (only used when the tile has a single qubit): element with t0 clear owns the pair
-              if (!((li >> rec.t0) & 1u)) {
-                const uint32_t sp = s ^ rec.z0;
-                const double2 a0 = tile[s], a1 = tile[sp];
-                double2 r0 = cmul(make_double2(m[0], m[1]), a0), r1 = cmul(make_double2(m[4], m[5]), a0);
-                cfma(r0, make_double2(m[2], m[3]), a1);
-                cfma(r1, make_double2(m[6], m[7]), a1);
-                tile[s] = r0;
-                tile[sp] = r1;
+            }
+#pragma unroll
+            for (int it = 0; it < 8; it++)
+              if ((lane | ((uint32_t)it << 5)) < n_el) tile[evs[it] >> 16] = a[it];
+            o = o_last;
+          } else {
+            const double* m = d.mats + rec.moff;
+            for (uint32_t it = 0; it < 8u; it++) {
+              if ((lane | (it << 5)) >= n_el) break;
+              const uint32_t ev = lv + st_it[sidx][it];
+              const uint32_t li = ev & 0xffffu, sl = ev >> 16;
+              if (rec.kind == QSV_GATE_CX) {
+                // control t0 set, target t1 clear: swap with the target-set partner (same sub-cube)
+                if (((li >> rec.t0) & 1u) && !((li >> rec.t1) & 1u)) {
+                  const uint32_t sp = sl + rec.z1;
+                  const double2 a = tile[sl], pp = tile[sp];
+                  tile[sl] = pp;
+                  tile[sp] = a;
+                }
+              } else if (rec.kind == QSV_GATE_DENSE1) {
+                // scalar 2x2 (only used when the tile has a single qubit): element with t0 clear owns the pair
+                if (!((li >> rec.t0) & 1u)) {
+                  const uint32_t sp = sl + rec.z0;
+                  const double2 a0 = tile[sl], a1 = tile[sp];
+                  double2 r0 = cmul(make_double2(m[0], m[1]), a0), r1 = cmul(make_double2(m[4], m[5]), a0);
+                  cfma(r0, make_double2(m[2], m[3]), a1);
+                  cfma(r1, make_double2(m[6], m[7]), a1);
+                  tile[sl] = r0;
+                  tile[sp] = r1;
+                }
               }
             }
           }
         }
       }
     }
-    __syncthreads();
 
-    // ---- write-back: one HBM write of the tile, optionally with the tile qubits permuted (the content
-    // of tile bit src_of[j] lands on position j: a free qubit remap).  Without a permutation every thread
-    // reads exactly the slots its own cp.async of the next tile will overwrite, so no barrier is needed ----
+    // ---- write-back: one HBM write of the tile (TMA bulk copies), optionally with the tile qubits
+    // permuted: position j receives the content of tile bit src_of[j] (a free qubit remap) ----
+    fence_proxy_async();  // the gates' generic-proxy stores must be visible to the async proxy
+    __syncthreads();
     if (st_on) {
-      double2* gp = sv + base + lo_off;
-#pragma unroll 8
-      for (uint32_t it = 0; it < iters; it++) gp[hi_off[it]] = tile[s_tid_st ^ swz_it_st[it]];
+      if (tid < np_st) bulk_store(sv + base + g_st0, tile + s_st0, st_bytes);
+      for (uint32_t pc = tid + kPT; pc < np_st; pc += kPT) {
+        u64 go = 0;
+        uint32_t so = 0;
+        for (int j = 0; j + (int)pb_st < b; j++)
+          if ((pc >> j) & 1u) { go |= 1ull << d.tb[pb_st + j]; so += d.cj[d.src_of[pb_st + j]]; }
+        bulk_store(sv + base + go, tile + so, st_bytes);
+      }
+      bulk_commit();
     }
-    if (permuted) __syncthreads();
   }
+  bulk_wait_read();
 }
 
 // ---- dense k-qubit gate, 3 <= k <= 12: out-of-place inside the tile (two smem buffers) ----
@@ -452,9 +530,11 @@ struct HostOp {
   int moff;
 };
 
+// bank class of a tile-local bit: it shifts the bank group by 2^(j mod 3) (see the slot layout)
+static inline int bank_class(int bit) { return bit % 3; }
 static inline bool independent3(int a, int b, int c) {
-  // three vectors of GF(2)^3 are independent iff none is zero, all differ, and c != a ^ b
-  return a && b && c && a != b && a != c && b != c && c != (a ^ b);
+  // three bits spread over all 8 bank groups iff their classes are pairwise different
+  return a != b && a != c && b != c;
 }
 
 static inline int popc(uint32_t x) { return __builtin_popcount(x); }
@@ -516,7 +596,7 @@ static int ensure_attrs() {
   if (dev < 0 || dev >= 64) return fail(QSV_ERANGE, "device ordinal out of range");
   if (!g_attr_set[dev]) {
     QSV_CUDA(cudaFuncSetAttribute(tile_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)((sizeof(double2) << QSV_MAX_TILE_QUBITS) + 48 * 1024)));
+                                  (int)((sizeof(double2) << QSV_MAX_TILE_QUBITS) + 64 * 1024)));
     QSV_CUDA(cudaFuncSetAttribute(tile_pass_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     QSV_CUDA(cudaFuncSetAttribute(dense_k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(2 * (sizeof(double2) << 12) + 4096 * sizeof(uint32_t))));
@@ -546,12 +626,69 @@ static int launch_pass(double* sv, int n, const int32_t* tile_qubits, int n_tile
   std::sort(sorted, sorted + b);
   for (int j = 0; j + 1 < b; j++)
     if (sorted[j] == sorted[j + 1]) return fail(QSV_EINVAL, "qsv_apply_pass: duplicate tile qubit");
+  for (int j = 0; j < b; j++) d.tbs[j] = (uint8_t)sorted[j];
+
+  // ---- tile-local positions: 0..2 = the three lowest tile qubits (they form the contiguous 128-byte
+  // pieces when they are physical qubits 0,1,2); the others are placed so that the two qubits of every
+  // dense gate get different bank classes (position mod 3) ----
+  int pos_phys[16];
+  {
+    const int n_fixed = std::min(b, 3);
+    int cls_of[64];
+    for (int q = 0; q < 64; q++) cls_of[q] = -1;
+    for (int j = 0; j < n_fixed; j++) {
+      pos_phys[j] = sorted[j];
+      cls_of[sorted[j]] = bank_class(j);
+    }
+    uint64_t adj[64] = {0};
+    int deg[64] = {0};
+    for (int i = 0; i < n_gates; i++) {
+      if (gates[i].kind != QSV_GATE_DENSE2) continue;
+      const int a = gates[i].q0, c = gates[i].q1;
+      if (a < 0 || a >= n || c < 0 || c >= n || a == c) continue;  // reported below
+      if (!((adj[a] >> c) & 1ull)) { adj[a] |= 1ull << c; adj[c] |= 1ull << a; deg[a]++; deg[c]++; }
+    }
+    bool pos_used[16] = {false};
+    bool placed[16] = {false};
+    for (int round = n_fixed; round < b; round++) {
+      // next qubit: the unplaced one with the most already-placed neighbours, then highest degree
+      int best_i = -1, best_key = -1;
+      for (int i = n_fixed; i < b; i++) {
+        if (placed[i]) continue;
+        const int q = sorted[i];
+        int placed_nb = 0;
+        for (int k = 0; k < b; k++)
+          if (((adj[q] >> sorted[k]) & 1ull) && cls_of[sorted[k]] >= 0) placed_nb++;
+        const int key = placed_nb * 64 + deg[q];
+        if (key > best_key) { best_key = key; best_i = i; }
+      }
+      const int q = sorted[best_i];
+      int best_pos = -1, best_conf = 1 << 30;
+      for (int ps = n_fixed; ps < b; ps++) {
+        if (pos_used[ps]) continue;
+        int conf = 0;
+        for (int k = 0; k < b; k++)
+          if (((adj[q] >> sorted[k]) & 1ull) && cls_of[sorted[k]] == bank_class(ps)) conf++;
+        if (conf < best_conf) { best_conf = conf; best_pos = ps; }
+      }
+      placed[best_i] = true;
+      pos_used[best_pos] = true;
+      pos_phys[best_pos] = q;
+      cls_of[q] = bank_class(best_pos);
+    }
+  }
   int local_of[64];
   for (int q = 0; q < 64; q++) local_of[q] = -1;
   for (int j = 0; j < b; j++) {
-    d.tb[j] = (uint8_t)sorted[j];
-    local_of[sorted[j]] = j;
+    d.tb[j] = (uint8_t)pos_phys[j];
+    local_of[pos_phys[j]] = j;
+    d.cj[j] = (uint16_t)((1u << j) + pad_of_bit(j));
   }
+  // bulk-copy piece size: the leading tile positions that are physical qubits 0,1,2 (contiguous in HBM)
+  int pb = 0;
+  while (pb < 3 && pb < b && pos_phys[pb] == pb) pb++;
+  d.pb_ld = (uint32_t)pb;
+  d.pb_st = (uint32_t)pb;
   // write-back permutation: content of tile_qubits[i] goes to dest_qubits[i]
   for (int j = 0; j < 16; j++) d.src_of[j] = (uint8_t)j;
   if (dest_qubits) {
@@ -563,8 +700,10 @@ static int launch_pass(double* sv, int n, const int32_t* tile_qubits, int n_tile
       seen[local_of[dq]] = true;
       d.src_of[local_of[dq]] = (uint8_t)local_of[tile_qubits[i]];
     }
-    for (int j = 0; j < b; j++)
-      if (d.src_of[j] != j) d.pad2[1] = 1;
+    // a write-back piece must be contiguous in shared memory too: only unpermuted leading positions
+    int ps = 0;
+    while (ps < pb && d.src_of[ps] == ps) ps++;
+    d.pb_st = (uint32_t)ps;
   }
 
   // ---- gates -> host ops (tile-local bits, matrices) ----
@@ -629,6 +768,8 @@ static int launch_pass(double* sv, int n, const int32_t* tile_qubits, int n_tile
       const uint32_t inner = inner_masks[stage_of[k]];
       int partner = -1;
       for (int j = 0; j < b && partner < 0; j++)
+        if (((inner >> j) & 1u) && j != op.t0 && bank_class(j) != bank_class(op.t0)) partner = j;
+      for (int j = 0; j < b && partner < 0; j++)
         if (((inner >> j) & 1u) && j != op.t0) partner = j;
       double m2[8];
       memcpy(m2, mats + op.moff, sizeof(m2));
@@ -645,56 +786,8 @@ static int launch_pass(double* sv, int n, const int32_t* tile_qubits, int n_tile
   }
   memcpy(d.mats, mats, sizeof(double) * moff);
 
-  // ---- bank vectors: the two bits of every dense gate should differ ----
-  for (int j = 0; j < 16; j++) d.vec[j] = (uint8_t)(1u << (j % 3));
-  {
-    auto conflicts = [&]() {
-      int cnt = 0;
-      for (int k = 0; k < n_gates; k++)
-        if (sops[k].kind == QSV_GATE_DENSE2 && d.vec[sops[k].t0] == d.vec[sops[k].t1]) cnt++;
-      // write-back reads: the 8 lanes of a quarter warp read the bits that land on positions 0..2
-      if (b >= 3 && !independent3(d.vec[d.src_of[0]] & 7, d.vec[d.src_of[1]] & 7, d.vec[d.src_of[2]] & 7)) cnt += 2;
-      return cnt;
-    };
-    int best = conflicts();
-    // first make the write-back lane bits independent
-    for (int j = 0; j < 3 && j < b && best > 0; j++) {
-      const int bit = d.src_of[j];
-      if (bit < 3) continue;
-      uint8_t best_v = d.vec[bit];
-      for (uint8_t v = 1; v < 8; v++) {
-        d.vec[bit] = v;
-        const int cnt = conflicts();
-        if (cnt < best) {
-          best = cnt;
-          best_v = v;
-        }
-      }
-      d.vec[bit] = best_v;
-    }
-    for (int round = 0; round < 4 && best > 0; round++) {
-      for (int k = 0; k < n_gates && best > 0; k++) {
-        if (sops[k].kind != QSV_GATE_DENSE2 || d.vec[sops[k].t0] != d.vec[sops[k].t1]) continue;
-        const int cand[2] = {sops[k].t1, sops[k].t0};
-        for (int ci = 0; ci < 2 && d.vec[sops[k].t0] == d.vec[sops[k].t1]; ci++) {
-          const int bit = cand[ci];
-          if (bit < 3) continue;
-          uint8_t best_v = d.vec[bit];
-          for (uint8_t v = 1; v < 8; v++) {
-            d.vec[bit] = v;
-            const int cnt = conflicts();
-            if (cnt < best) {
-              best = cnt;
-              best_v = v;
-            }
-          }
-          d.vec[bit] = best_v;
-        }
-      }
-    }
-  }
-  auto bvec = [&](int bit) { return (int)(d.vec[bit] & 7); };
-  auto sw1 = [&](int bit) { return (uint16_t)swz(d.vec, b, 1u << bit); };
+  auto bvec = [&](int bit) { return bank_class(bit); };
+  auto sw1 = [&](int bit) { return d.cj[bit]; };
 
   // ---- per-stage element order and per-op group order ----
   for (int s = 0; s < n_stages; s++) {
@@ -766,10 +859,12 @@ static int launch_pass(double* sv, int n, const int32_t* tile_qubits, int n_tile
   }
 
   if (int rc = ensure_attrs()) return rc;
-  const size_t smem = (sizeof(double2) << b) + (size_t)n_gates * (64 * sizeof(double) + sizeof(OpRec) + 32 * 4) +
+  size_t tile_slots = (size_t)1 << b;
+  for (int j = 3; j < b; j++) tile_slots += pad_of_bit(j);
+  const size_t smem = tile_slots * sizeof(double2) + (size_t)n_gates * (64 * sizeof(double) + sizeof(OpRec) + 32 * 4) +
                       (size_t)n_stages * ((kWarps + 32 + 8) * 4);
   d.n_tiles = 1u << (n - b);
-  if (const char* e = getenv("QSV_DEBUG_FLAGS")) d.pad2[0] = (uint32_t)atoi(e);
+  if (const char* e = getenv("QSV_DEBUG_FLAGS")) d.flags = (uint32_t)atoi(e);
   // one warp per 2^8 amplitudes: 512 threads for b = 12, 256 for b = 11, ...; at least one warp
   const int threads = std::max(32, std::min(kMaxPT, 1 << std::max(0, b - 3)));
   int per_sm = 1;

@@ -172,6 +172,31 @@ class DeviceState:
                                           ctypes.byref(out), self.stream), "qsv_norm2")
         return float(out.value)
 
+    def expval_pauli(self, pauli):
+        """<psi|P|psi> for a Pauli label such as "XIZY" (leftmost character = highest qubit, as in
+        qiskit.quantum_info.Pauli labels).  Mirrors Statevector._expectation_value_pauli
+        (quantum_info/states/statevector.py:377-408): masks + phase on the host, the 2^n loop on the GPU."""
+        label = pauli.upper()
+        if len(label) != self.n or any(c not in "IXYZ" for c in label):
+            raise ValueError("Pauli label must have %d characters from IXYZ" % self.n)
+        z_mask = x_mask = 0
+        n_y = 0
+        for q, c in enumerate(reversed(label)):
+            if c in "ZY":
+                z_mask |= 1 << q
+            if c in "XY":
+                x_mask |= 1 << q
+            n_y += c == "Y"
+        if z_mask == 0 and x_mask == 0:
+            return float(np.sqrt(self.norm2()))  # the reference returns the norm here (statevector.py:397-398)
+        phase = (-1j) ** n_y  # statevector.py:403-404
+        out = ctypes.c_double(0.0)
+        with self._ctx():
+            _lib.check(self.lib.qsv_expval_pauli(self.ptr, self.n, z_mask, x_mask, float(phase.real),
+                                                 float(phase.imag), ctypes.c_void_p(self._reduce_ws.data_ptr()),
+                                                 ctypes.byref(out), self.stream), "qsv_expval_pauli")
+        return float(out.value)
+
     def collapse(self, qubit, outcome, prob, is_reset=False):
         with self._ctx():
             _lib.check(self.lib.qsv_collapse(self.ptr, self.n, int(qubit), int(outcome), float(prob),

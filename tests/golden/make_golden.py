@@ -410,6 +410,34 @@ def cases_from_generators():
         save("random_%d_unitary" % n, "unitary_simulator", q)
 
 
+def expval_cases():
+    """Pauli expectation values from the reference's compiled Cython code (oracle/build_ref.py)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import build_ref
+
+    if build_ref.build() is None:
+        print("exp_value.pyx not found; skipping expval goldens")
+        return
+    from qiskit.quantum_info import Pauli, Statevector
+    import qiskit.quantum_info.states.statevector as svmod
+
+    assert "oracle/_ref" in svmod.expval_pauli_no_x.__module__ or hasattr(svmod.expval_pauli_no_x, "__call__")
+    rng = np.random.RandomState(2024)
+    cases = []
+    for n in (1, 2, 5, 9, 12):
+        vec = rng.standard_normal(2 ** n) + 1j * rng.standard_normal(2 ** n)
+        vec /= np.linalg.norm(vec)
+        labels = ["I" * n, "Z" * n, "X" * n, "Y" * n]
+        for _ in range(12):
+            labels.append("".join(rng.choice(list("IXYZ"), n)))
+        sv = Statevector(vec)
+        vals = [complex(sv.expectation_value(Pauli(lab))) for lab in labels]
+        cases.append({"n": n, "state": vec, "labels": labels, "values": np.array(vals)})
+    golden_io.dump_case("expval_pauli", {"backend": "expval", "cases": cases,
+                                         "qobj": {"config": {"n_qubits": 12}}})
+    print("wrote expval_pauli")
+
+
 def large_cases():
     save("qft_16_product", "statevector_simulator", gen.qft(16, state_seed=3))
     save("qv_16_counts", "qasm_simulator", gen.quantum_volume(16, shots=8192, seed_simulator=42))
@@ -429,11 +457,16 @@ if __name__ == "__main__":
     ap.add_argument("--large", action="store_true")
     ap.add_argument("--huge", action="store_true")
     ap.add_argument("--only-large", action="store_true")
+    ap.add_argument("--only-expval", action="store_true")
     args = ap.parse_args()
+    if args.only_expval:
+        expval_cases()
+        sys.exit(0)
     if not args.only_large:
         check_generators_against_reference()
         cases_from_reference_tests()
         cases_from_generators()
+        expval_cases()
     if args.large or args.only_large:
         large_cases()
     if args.huge:

@@ -273,3 +273,23 @@ def test_bad_arguments_fail_loudly():
         st.apply_pass([0, 1, 1], [])
     with pytest.raises(_lib.QsvLibraryError):
         st.apply_pass(list(range(6)) + [7], [])
+
+
+def test_expval_pauli_matches_reference_golden():
+    """qsv_expval_pauli vs the values the reference's Cython exp_value.pyx produced."""
+    import golden_io
+
+    fix = golden_io.load_case("expval_pauli")
+    for case in fix["cases"]:
+        st = make_state(case["n"], case["state"])
+        for label, want in zip(case["labels"], case["values"]):
+            got = st.expval_pauli(label)
+            assert abs(got - want.real) < 1e-12 and abs(want.imag) < 1e-12, (case["n"], label, got, want)
+    # a larger state against the oracle
+    n = 20
+    vec = rand_state(n, 5)
+    st = make_state(n, vec)
+    rng = np.random.RandomState(3)
+    for _ in range(6):
+        label = "".join(rng.choice(list("IXYZ"), n))
+        assert abs(st.expval_pauli(label) - orc.expval_pauli(vec, label)) < 1e-12

@@ -87,3 +87,13 @@ def test_oracle_matches_live_reference():
     got = oracle_factory("qasm_simulator").run(copy.deepcopy(qobj))
     assert ref.results[0].data.to_dict()["memory"] == got["results"][0]["data"]["memory"]
     assert dict(ref.results[0].data.to_dict()["counts"]) == got["results"][0]["data"]["counts"]
+
+
+def test_expval_oracle_matches_compiled_reference():
+    """oracle.expval_pauli vs the reference's own Cython code (exp_value.pyx compiled by
+    oracle/build_ref.py, values recorded in tests/golden/expval_pauli.json)."""
+    fix = golden_io.load_case("expval_pauli")
+    for case in fix["cases"]:
+        for label, want in zip(case["labels"], case["values"]):
+            got = orc.expval_pauli(case["state"], label)
+            assert abs(got - want) < 1e-12, (case["n"], label, got, want)
