@@ -82,8 +82,19 @@ struct PassDesc {
 // 8-byte halves (LDS.64) conflict-free.  The host orders the tile qubits so that the two bits of every
 // dense gate fall in different classes.  Every index map of the kernel is a sum of per-bit increments.
 __host__ __device__ __forceinline__ uint32_t pad_of_bit(int j) {
-  const uint32_t pads[13] = {0, 0, 0, 1, 2, 4, 9, 18, 36, 73, 146, 292, 585};
-  return pads[j];
+  switch (j) {
+    case 3: return 1;
+    case 4: return 2;
+    case 5: return 4;
+    case 6: return 9;
+    case 7: return 18;
+    case 8: return 36;
+    case 9: return 73;
+    case 10: return 146;
+    case 11: return 292;
+    case 12: return 585;
+    default: return 0;
+  }
 }
 
 // ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) and their mbarrier ----
@@ -351,33 +362,28 @@ tile_pass_kernel(double2* __restrict__ sv, const __grid_constant__ PassDesc d) {
             int o_last = o;
             while (o_last + 1 < o_end && (oprec[o_last + 1].kind == QSV_GATE_DIAG1 || oprec[o_last + 1].kind == QSV_GATE_DIAG2))
               o_last++;
-            // the lane's (up to 8) elements stay in registers while the run's factors stream by
-            double2 a[8];
-            uint32_t evs[8];
-#pragma unroll
-            for (int it = 0; it < 8; it++) {
-              evs[it] = lv + st_it[sidx][it];
-              if ((lane | ((uint32_t)it << 5)) < n_el) a[it] = tile[evs[it] >> 16];
-            }
-            for (int q = o; q <= o_last; q++) {
-              const OpRec rq = oprec[q];
-              const double* m = d.mats + rq.moff;
-              const double2 m0 = make_double2(m[0], m[1]), m1 = make_double2(m[2], m[3]);
-              if (rq.kind == QSV_GATE_DIAG1) {
-#pragma unroll
-                for (int it = 0; it < 8; it++) a[it] = cmul(((evs[it] >> rq.t0) & 1u) ? m1 : m0, a[it]);
-              } else {
-                const double2 m2 = make_double2(m[4], m[5]), m3 = make_double2(m[6], m[7]);
-#pragma unroll
-                for (int it = 0; it < 8; it++) {
-                  const uint32_t b0 = (evs[it] >> rq.t0) & 1u, b1 = (evs[it] >> rq.t1) & 1u;
-                  a[it] = cmul(b1 ? (b0 ? m3 : m2) : (b0 ? m1 : m0), a[it]);
+            for (uint32_t it = 0; it < 8u; it++) {
+              if ((lane | (it << 5)) >= n_el) break;
+              const uint32_t ev = lv + st_it[sidx][it];
+              const uint32_t li = ev & 0xffffu, sl = ev >> 16;
+              double2 a = tile[sl];
+              for (int q = o; q <= o_last; q++) {
+                const OpRec rq = oprec[q];
+                const double* m = d.mats + rq.moff;
+                const uint32_t b0 = (li >> rq.t0) & 1u;
+                double2 f;
+                if (rq.kind == QSV_GATE_DIAG1) {
+                  f = b0 ? make_double2(m[2], m[3]) : make_double2(m[0], m[1]);
+                } else {
+                  const uint32_t b1 = (li >> rq.t1) & 1u;
+                  const double2 f0 = b0 ? make_double2(m[2], m[3]) : make_double2(m[0], m[1]);
+                  const double2 f1 = b0 ? make_double2(m[6], m[7]) : make_double2(m[4], m[5]);
+                  f = b1 ? f1 : f0;
                 }
+                a = cmul(f, a);
               }
+              tile[sl] = a;
             }
-#pragma unroll
-            for (int it = 0; it < 8; it++)
-              if ((lane | ((uint32_t)it << 5)) < n_el) tile[evs[it] >> 16] = a[it];
             o = o_last;
           } else {
             const double* m = d.mats + rec.moff;
