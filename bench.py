@@ -43,6 +43,8 @@ QV_SEED = 1234
 SIM_SEED = 42
 REF_QUBITS = 24          # reference cap (qasm_simulator.py:64)
 REF_GATES_PER_STEP = 6   # bounded sample per reference step (~0.4 s per gate at n=24)
+FP64_DMMA_PEAK_TFLOPS = 37.0      # measured: tools/fp64_peak.cu on B200 (DMMA.8x8x4), profiles/r1_fp64_peak_dfma_vs_dmma.txt
+TRAFFIC_BYTES_PER_AMP = 31.79     # measured DRAM bytes per amplitude per pass (ncu, n=28)
 
 
 def measured_peaks():
@@ -327,9 +329,17 @@ def main():
         },
         "roofline": {
             "bound": "hbm", "kernel": "tile_pass_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+            "frac": achieved / peak, "traffic": TRAFFIC_BYTES_PER_AMP * 2 ** n, "peak_source": peak_src,
+            "traffic_source": "ncu --set full at n=28: dram__bytes_read 4.296 GB + write 4.237 GB per launch = "
+                              "31.8 B/amplitude (profiles/r1_tile_pass_kernel_ncu_full_summary.txt), scaled to 2^n",
             "algorithmic_bytes_per_launch": bytes_per_gate_pass, "launch_ms": per_launch_ms,
             "launches_per_step": len(passes), "pass_section_ms": pass_ms,
+            # the fused pass is FP64-bound, not HBM-bound: the same launches against the measured DMMA peak
+            "fp64": {"achieved_tflops": n_gates * 32.0 * 2 ** n / (pass_ms * 1e-3) / 1e12,
+                     "peak_tflops": FP64_DMMA_PEAK_TFLOPS,
+                     "frac": n_gates * 32.0 * 2 ** n / (pass_ms * 1e-3) / 1e12 / FP64_DMMA_PEAK_TFLOPS,
+                     "peak_source": "measured on B200 with tools/fp64_peak.cu (profiles/r1_fp64_peak_dfma_vs_dmma.txt)",
+                     "flops_per_gate": "32 * 2^n (16 complex multiply-adds per group of 4 amplitudes)"},
         },
         "cpu_baseline": cpu,
         "e2e": e2e,

@@ -284,8 +284,11 @@ tile_pass_kernel(double2* __restrict__ sv, const __grid_constant__ PassDesc d) {
           if ((pc >> j) & 1u) { go |= 1ull << d.tb[pb_ld + j]; so += d.cj[pb_ld + j]; }
         bulk_load(tile + so, sv + base + go, ld_bytes, &ld_bar);
       }
-      mbar_wait(&ld_bar, parity);
+      // one warp polls the mbarrier (acquiring the TMA writes); everybody else parks on the hardware
+      // barrier instead of burning issue slots that the other CTAs of this SM need for their gates
+      if (wid == 0) mbar_wait(&ld_bar, parity);
       parity ^= 1u;
+      __syncthreads();
     }
 
     int o = 0;
