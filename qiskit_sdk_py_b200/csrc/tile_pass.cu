@@ -162,8 +162,7 @@ struct __align__(16) OpRec {
 // run their gates, so the memory phases of one overlap the FP64 / shared-memory phases of the others.
 // A CTA owns a contiguous range of tiles.  The tile moves between HBM and shared memory with TMA bulk
 // copies of 128-byte pieces (one per thread), which bypass the LSU/L1TEX pipe that the gates saturate.
-__global__ void __launch_bounds__(kMaxPT, 2)
-tile_pass_kernel(double2* __restrict__ sv, const __grid_constant__ PassDesc d) {
+__device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const PassDesc& d) {
   // dynamic shared memory: the (padded) tile, then the per-pass tables (sized by the pass, so that short
   // passes leave room for more resident CTAs)
   extern __shared__ double2 tile[];
@@ -439,6 +438,14 @@ tile_pass_kernel(double2* __restrict__ sv, const __grid_constant__ PassDesc d) {
   bulk_wait_read();
 }
 
+// One body, three register budgets: more resident CTAs per SM (5 x 256 threads for the default 11-qubit
+// tile) keep more tiles in flight, which is what hides the HBM round trip of each CTA.
+template <int kBlock, int kMinBlocks>
+__global__ void __launch_bounds__(kBlock, kMinBlocks)
+tile_pass_kernel(double2* __restrict__ sv, const __grid_constant__ PassDesc d) {
+  tile_pass_body(sv, d);
+}
+
 // ---- dense k-qubit gate, 3 <= k <= 12: out-of-place inside the tile (two smem buffers) ----
 struct DenseKDesc {
   int32_t n, b, k, pad;
@@ -604,9 +611,13 @@ static int ensure_attrs() {
   QSV_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64) return fail(QSV_ERANGE, "device ordinal out of range");
   if (!g_attr_set[dev]) {
-    QSV_CUDA(cudaFuncSetAttribute(tile_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)((sizeof(double2) << QSV_MAX_TILE_QUBITS) + 64 * 1024)));
-    QSV_CUDA(cudaFuncSetAttribute(tile_pass_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    const int max_dyn = (int)((sizeof(double2) << QSV_MAX_TILE_QUBITS) + 64 * 1024);
+    QSV_CUDA(cudaFuncSetAttribute(tile_pass_kernel<512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+    QSV_CUDA(cudaFuncSetAttribute(tile_pass_kernel<256, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+    QSV_CUDA(cudaFuncSetAttribute(tile_pass_kernel<128, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+    QSV_CUDA(cudaFuncSetAttribute(tile_pass_kernel<512, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    QSV_CUDA(cudaFuncSetAttribute(tile_pass_kernel<256, 5>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    QSV_CUDA(cudaFuncSetAttribute(tile_pass_kernel<128, 10>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     QSV_CUDA(cudaFuncSetAttribute(dense_k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(2 * (sizeof(double2) << 12) + 4096 * sizeof(uint32_t))));
     g_attr_set[dev] = true;
@@ -877,10 +888,21 @@ static int launch_pass(double* sv, int n, const int32_t* tile_qubits, int n_tile
   // one warp per 2^8 amplitudes: 512 threads for b = 12, 256 for b = 11, ...; at least one warp
   const int threads = std::max(32, std::min(kMaxPT, 1 << std::max(0, b - 3)));
   int per_sm = 1;
-  QSV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tile_pass_kernel, threads, smem));
+  if (threads >= 512) {
+    QSV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tile_pass_kernel<512, 2>, threads, smem));
+  } else if (threads >= 256) {
+    QSV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tile_pass_kernel<256, 5>, threads, smem));
+  } else {
+    QSV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tile_pass_kernel<128, 10>, threads, smem));
+  }
   if (per_sm < 1) return fail(QSV_ERANGE, "qsv_apply_pass: pass does not fit in shared memory");
   const unsigned grid = std::min<unsigned>(d.n_tiles, (unsigned)per_sm * (unsigned)sm_count());
-  tile_pass_kernel<<<grid, threads, smem, stream>>>(reinterpret_cast<double2*>(sv), d);
+  if (threads >= 512)
+    tile_pass_kernel<512, 2><<<grid, threads, smem, stream>>>(reinterpret_cast<double2*>(sv), d);
+  else if (threads >= 256)
+    tile_pass_kernel<256, 5><<<grid, threads, smem, stream>>>(reinterpret_cast<double2*>(sv), d);
+  else
+    tile_pass_kernel<128, 10><<<grid, threads, smem, stream>>>(reinterpret_cast<double2*>(sv), d);
   QSV_LAUNCHED();
   return 0;
 }
