@@ -188,6 +188,115 @@ cdf_sequential_kernel(const void* __restrict__ src, u64 bins, double* __restrict
   }
 }
 
+// ---- exact (numpy cumsum) order, in parallel ---------------------------------------------------------
+// numpy's cumsum is one running float64 sum, s <- fl(s + p_i).  While s stays inside one binade
+// [2^k, 2^(k+1)) its ulp u = 2^(k-52) is fixed and every partial sum is a multiple of u, so
+//     fl(s + p) = s + u * rint(p / u)      (unless p/u is exactly half-way: ties depend on s)
+// i.e. the sequential sum is an INTEGER sum of q_i = rint(p_i / u), which is associative and can be
+// reduced in parallel without changing a single bit.  Per 1024-bin chunk:
+//   ZERO  all p_i == 0                                   -> running sum unchanged
+//   INT   the (approximate) running sum provably stays in one binade over the chunk and no p_i / u is a
+//         tie                                             -> add the chunk's integer increment
+//   SLOW  anything else (binade crossings: ~60 chunks)    -> sequential float64 adds, as numpy does
+// chunk_classify_kernel computes mode / binade / integer increment of every chunk in parallel;
+// chunk_chain_kernel then walks the chunks once (a few dozen cycles per chunk).
+constexpr int kModeZero = 0, kModeInt = 1, kModeSlow = 2;
+
+template <bool kAmps>
+__global__ void __launch_bounds__(kThreads)
+chunk_classify_kernel(const void* __restrict__ src, u64 bins, const double* __restrict__ aprefix,
+                      int* __restrict__ meta, long long* __restrict__ inc) {
+  __shared__ long long s_sum[kThreads / 32];
+  __shared__ int s_flag[kThreads / 32];
+  const u64 c = blockIdx.x;
+  const double a_prev = c > 0 ? aprefix[c - 1] : 0.0, a_cur = aprefix[c];
+  const double lo = a_prev * (1.0 - 9.313225746154785e-10), hi = a_cur * (1.0 + 9.313225746154785e-10);  // 2^-30 margins
+  int k = 0;
+  bool int_ok = lo > 0.0;
+  if (int_ok) {
+    k = ilogb(lo);
+    int_ok = hi < ldexp(1.0, k + 1) && k > -900;
+  }
+  long long acc = 0;
+  int flag = 0;  // bit 0: some p != 0, bit 1: a tie
+  for (int i = threadIdx.x; i < kChunk; i += kThreads) {
+    const u64 idx = c * kChunk + i;
+    if (idx >= bins) break;
+    const double pv = load_p<kAmps>(src, idx);
+    if (pv != 0.0) flag |= 1;
+    if (int_ok) {
+      const double x = ldexp(pv, 52 - k);
+      if (x - floor(x) == 0.5) flag |= 2;
+      acc += (long long)rint(x);
+    }
+  }
+  // block reduction of (acc, flag)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    flag |= __shfl_xor_sync(0xffffffffu, flag, o);
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) {
+    s_sum[wid] = acc;
+    s_flag[wid] = flag;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long tot = 0;
+    int fl = 0;
+    for (int w = 0; w < kThreads / 32; w++) {
+      tot += s_sum[w];
+      fl |= s_flag[w];
+    }
+    int mode = kModeSlow;
+    if (!(fl & 1)) mode = kModeZero;
+    else if (int_ok && !(fl & 2)) mode = kModeInt;
+    meta[c] = mode | ((k + 2048) << 2);
+    inc[c] = tot;
+  }
+}
+
+template <bool kAmps>
+__global__ void __launch_bounds__(32)
+chunk_chain_kernel(const void* __restrict__ src, u64 bins, u64 nchunks, const int* __restrict__ meta,
+                   const long long* __restrict__ inc, double* __restrict__ chunk_end, int* __restrict__ err) {
+  const int lane = threadIdx.x;
+  double run = 0.0;  // identical in every lane
+  for (u64 c0 = 0; c0 < nchunks; c0 += 32) {
+    const u64 mine = c0 + lane;
+    const int my_meta = mine < nchunks ? meta[mine] : 0;
+    const long long my_inc = mine < nchunks ? inc[mine] : 0;
+    double my_end = 0.0;
+    const int cnt = nchunks - c0 < 32 ? (int)(nchunks - c0) : 32;
+    for (int j = 0; j < cnt; j++) {
+      const int m = __shfl_sync(0xffffffffu, my_meta, j);
+      const long long q = __shfl_sync(0xffffffffu, my_inc, j);
+      const int mode = m & 3, k = (m >> 2) - 2048;
+      if (mode == kModeInt) {
+        const double scaled = ldexp(run, 52 - k);
+        const long long s0 = (long long)scaled;
+        const long long s1 = s0 + q;
+        if (!(s0 >= (1ll << 52) && s1 < (1ll << 53) && (double)s0 == scaled)) *err = 1;  // guarantee violated
+        run = ldexp((double)s1, k - 52);
+      } else if (mode == kModeSlow) {
+        const u64 begin = (c0 + j) * kChunk;
+        double vals[kChunk / 32];
+#pragma unroll
+        for (int t = 0; t < kChunk / 32; t++) {
+          const u64 idx = begin + (u64)t * 32 + lane;
+          vals[t] = idx < bins ? load_p<kAmps>(src, idx) : 0.0;
+        }
+#pragma unroll
+        for (int t = 0; t < kChunk / 32; t++)
+          for (int l = 0; l < 32; l++) run += __shfl_sync(0xffffffffu, vals[t], l);
+      }
+      if (lane == j) my_end = run;
+    }
+    if (mine < nchunks) chunk_end[mine] = my_end;
+  }
+}
+
 // Blocked order: chunk sums (sequential inside a chunk, one thread per chunk slice is too slow, so a
 // fixed-shape tree per chunk), then an inclusive scan over the chunk sums.
 template <bool kAmps>
@@ -270,6 +379,9 @@ sample_kernel(const void* __restrict__ src, u64 bins, const double* __restrict__
 
 struct SampleWs {
   double* chunk_end;   // nchunks
+  double* aprefix;     // nchunks (exact mode: approximate inclusive prefix of the chunk sums)
+  long long* inc;      // nchunks (exact mode: integer increment of each chunk)
+  int* meta;           // nchunks + 1 (exact mode: mode | binade; last entry = error flag)
   double* seg1;        // ceil(nchunks/1024)
   double* uniforms;    // shots
   long long* out;      // shots
@@ -285,6 +397,12 @@ static size_t sample_ws_layout(int log2_bins, int shots, void* ws, SampleWs* out
   char* base = reinterpret_cast<char*>(ws);
   if (out) out->chunk_end = reinterpret_cast<double*>(base + off);
   off += align_up(nchunks * sizeof(double));
+  if (out) out->aprefix = reinterpret_cast<double*>(base + off);
+  off += align_up(nchunks * sizeof(double));
+  if (out) out->inc = reinterpret_cast<long long*>(base + off);
+  off += align_up(nchunks * sizeof(long long));
+  if (out) out->meta = reinterpret_cast<int*>(base + off);
+  off += align_up((nchunks + 1) * sizeof(int));
   if (out) out->seg1 = reinterpret_cast<double*>(base + off);
   off += align_up(nseg * sizeof(double));
   if (out) out->uniforms = reinterpret_cast<double*>(base + off);
@@ -304,8 +422,30 @@ static int sample_impl(const void* src, int log2_bins, const double* host_unifor
   sample_ws_layout(log2_bins, shots, ws, &w);
   QSV_CUDA(cudaMemcpyAsync(w.uniforms, host_uniforms, (size_t)shots * sizeof(double), cudaMemcpyHostToDevice, s));
   if (exact) {
-    cdf_sequential_kernel<kAmps><<<1, 1024, 0, s>>>(src, bins, w.chunk_end);
+    // approximate prefix of the chunk sums (only used to classify chunks), then the exact chain
+    const u64 nseg = (nchunks + 1023) / 1024;
+    chunk_sum_kernel<kAmps><<<(unsigned)nchunks, kThreads, 0, s>>>(src, bins, w.aprefix);
     QSV_LAUNCHED();
+    seg_scan_kernel<<<(unsigned)((nseg + 127) / 128), 128, 0, s>>>(w.aprefix, nchunks, w.seg1);
+    QSV_LAUNCHED();
+    if (nseg > 1) {
+      serial_scan_kernel<<<1, 32, 0, s>>>(w.seg1, nseg);
+      QSV_LAUNCHED();
+      seg_add_kernel<<<(unsigned)((nchunks + 255) / 256), 256, 0, s>>>(w.aprefix, nchunks, w.seg1);
+      QSV_LAUNCHED();
+    }
+    QSV_CUDA(cudaMemsetAsync(w.meta + nchunks, 0, sizeof(int), s));
+    chunk_classify_kernel<kAmps><<<(unsigned)nchunks, kThreads, 0, s>>>(src, bins, w.aprefix, w.meta, w.inc);
+    QSV_LAUNCHED();
+    chunk_chain_kernel<kAmps><<<1, 32, 0, s>>>(src, bins, nchunks, w.meta, w.inc, w.chunk_end, w.meta + nchunks);
+    QSV_LAUNCHED();
+    int err = 0;
+    QSV_CUDA(cudaMemcpyAsync(&err, w.meta + nchunks, sizeof(int), cudaMemcpyDeviceToHost, s));
+    QSV_CUDA(cudaStreamSynchronize(s));
+    if (err) {  // cannot happen by construction; keep the plain sequential kernel as the safety net
+      cdf_sequential_kernel<kAmps><<<1, 1024, 0, s>>>(src, bins, w.chunk_end);
+      QSV_LAUNCHED();
+    }
   } else {
     chunk_sum_kernel<kAmps><<<(unsigned)nchunks, kThreads, 0, s>>>(src, bins, w.chunk_end);
     QSV_LAUNCHED();

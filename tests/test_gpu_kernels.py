@@ -293,3 +293,55 @@ def test_expval_pauli_matches_reference_golden():
     for _ in range(6):
         label = "".join(rng.choice(list("IXYZ"), n))
         assert abs(st.expval_pauli(label) - orc.expval_pauli(vec, label)) < 1e-12
+
+
+def _sample_probs(probs, uniforms, exact=True):
+    """Call qsv_sample on an explicit probability vector; returns (indices, total, chunk_end array)."""
+    import ctypes
+
+    import torch
+
+    lib = _lib.load()
+    log2_bins = int(np.log2(probs.size))
+    dev = torch.as_tensor(probs, dtype=torch.float64, device="cuda")
+    ws_bytes = lib.qsv_sample_workspace_bytes(log2_bins, uniforms.size)
+    ws = torch.zeros(ws_bytes // 8 + 8, dtype=torch.float64, device="cuda")
+    out = np.empty(uniforms.size, dtype=np.int64)
+    total = ctypes.c_double(0.0)
+    u = np.ascontiguousarray(uniforms, dtype=np.float64)
+    rc = lib.qsv_sample(ctypes.c_void_p(dev.data_ptr()), 0, log2_bins, ctypes.c_void_p(u.ctypes.data), u.size,
+                        ctypes.c_void_p(out.ctypes.data), (1 if exact else 0) | 2, ctypes.c_void_p(ws.data_ptr()),
+                        ctypes.byref(total), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _lib.check(rc, "qsv_sample")
+    nchunks = max(1, probs.size // 1024)
+    return out, total.value, ws[:nchunks].cpu().numpy()
+
+
+@pytest.mark.parametrize("kind", ["random", "wide_range", "sparse", "uniform", "ties", "tiny_tail", "leading_zeros"])
+def test_exact_cdf_is_bitwise_numpy_cumsum(kind):
+    """The parallel exact-order scan (integer sums inside a binade) must reproduce numpy's sequential
+    float64 cumsum bit for bit at every chunk boundary, and searchsorted's indices exactly."""
+    rng = np.random.RandomState(hash(kind) % 1000)
+    nbins = 1 << 18
+    if kind == "random":
+        p = rng.random_sample(nbins)
+    elif kind == "wide_range":
+        p = np.exp(rng.uniform(-60, 0, nbins))
+    elif kind == "sparse":
+        p = np.where(rng.random_sample(nbins) < 0.01, rng.random_sample(nbins), 0.0)
+    elif kind == "uniform":
+        p = np.full(nbins, 1.0)
+    elif kind == "ties":
+        p = np.ldexp(1.0, rng.randint(-70, 0, nbins))  # powers of two: exact half-way cases occur
+    elif kind == "tiny_tail":
+        p = np.concatenate([rng.random_sample(nbins // 2), 1e-25 * rng.random_sample(nbins // 2)])
+    else:
+        p = np.concatenate([np.zeros(nbins // 2 + 777), rng.random_sample(nbins // 2 - 777)])
+    p = p / p.sum()
+    cdf = p.cumsum()
+    u = np.random.RandomState(5).random_sample(3000)
+    got, total, chunk_end = _sample_probs(p, u, exact=True)
+    assert total == cdf[-1]
+    assert np.array_equal(chunk_end, cdf[1023::1024]), "chunk-end running sums differ from numpy's cumsum"
+    expected = (cdf / cdf[-1]).searchsorted(u, side="right")
+    assert np.array_equal(got, expected)

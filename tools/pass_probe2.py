@@ -18,14 +18,14 @@ def timeit(tile, ops, reps=5):
     e0.record()
     for _ in range(reps): st.apply_pass(tile, ops)
     e1.record(); torch.cuda.synchronize(); return e0.elapsed_time(e1) / reps
-pairs = [(3, 4), (5, 6), (7, 8), (9, 10), (11, 0), (1, 2), (3, 5), (4, 6)]
-tile = list(range(12))
+tile = list(range(4)) + list(range(n - 7, n))
+pairs = [(0, 4), (5, 6), (7, 8), (9, 10), (1, 5), (2, 7), (3, 9), (4, 10), (6, 8), (0, 9)]
 out = []
-for k in (0, 4, 8):
-    ops = [GateOp(_lib.GATE_DENSE2, list(p), ru(2)) for p in pairs[:k]]
+for k in (0, 2, 4, 8):
+    ops = [GateOp(_lib.GATE_DENSE2, [tile[p[0]], tile[p[1]]], ru(2)) for p in pairs[:k]]
     out.append("%d gates %.3f ms" % (k, timeit(tile, ops)))
 print(os.environ.get("QSV_DEBUG_FLAGS", "0"), " | ".join(out))
 '''
-for flags in ("0", "1", "2", "3", "4"):
+for flags in ("0", "1", "2", "3"):
     env = dict(os.environ, QSV_DEBUG_FLAGS=flags)
     subprocess.run([sys.executable, "-c", code, n], env=env, check=True)
