@@ -257,43 +257,138 @@ chunk_classify_kernel(const void* __restrict__ src, u64 bins, const double* __re
   }
 }
 
+// Groups of 32 chunks ("super-chunks") whose chunks are all INT in the same binade (or ZERO) are summarised
+// in parallel -- total increment and per-chunk inclusive prefix -- so that the sequential chain below takes
+// one integer add per 32768 bins; only mixed super-chunks (binade crossings) are walked chunk by chunk.
+__global__ void __launch_bounds__(kThreads)
+super_classify_kernel(u64 nchunks, const int* __restrict__ meta, const long long* __restrict__ inc,
+                      int* __restrict__ smeta, long long* __restrict__ sinc, long long* __restrict__ pref) {
+  const u64 sidx = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const u64 nsuper = (nchunks + 31) >> 5;
+  if (sidx >= nsuper) return;
+  const u64 c = sidx * 32 + lane;
+  const int m = c < nchunks ? meta[c] : kModeZero;
+  long long q = (c < nchunks && (m & 3) == kModeInt) ? inc[c] : 0;
+  const int mode = m & 3, k = (m >> 2) - 2048;
+  const unsigned int_mask = __ballot_sync(0xffffffffu, mode == kModeInt);
+  const unsigned slow_mask = __ballot_sync(0xffffffffu, mode == kModeSlow);
+  int k_first = 0;
+  bool uniform = slow_mask == 0;
+  if (int_mask) {
+    k_first = __shfl_sync(0xffffffffu, k, __ffs(int_mask) - 1);
+    uniform = uniform && __all_sync(0xffffffffu, mode != kModeInt || k == k_first);
+  }
+  // inclusive warp scan of the increments
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const long long t = __shfl_up_sync(0xffffffffu, q, o);
+    if (lane >= o) q += t;
+  }
+  if (c < nchunks) pref[c] = q;
+  if (lane == 31) {
+    int sm = kModeSlow;  // mixed
+    if (uniform) sm = int_mask ? kModeInt : kModeZero;
+    smeta[sidx] = sm | ((k_first + 2048) << 2);
+    sinc[sidx] = q;
+  }
+}
+
 template <bool kAmps>
 __global__ void __launch_bounds__(32)
 chunk_chain_kernel(const void* __restrict__ src, u64 bins, u64 nchunks, const int* __restrict__ meta,
-                   const long long* __restrict__ inc, double* __restrict__ chunk_end, int* __restrict__ err) {
+                   const long long* __restrict__ inc, const int* __restrict__ smeta,
+                   const long long* __restrict__ sinc, double* __restrict__ chunk_end,
+                   long long* __restrict__ sstart, int* __restrict__ err) {
   const int lane = threadIdx.x;
+  const u64 nsuper = (nchunks + 31) >> 5;
   double run = 0.0;  // identical in every lane
-  for (u64 c0 = 0; c0 < nchunks; c0 += 32) {
-    const u64 mine = c0 + lane;
-    const int my_meta = mine < nchunks ? meta[mine] : 0;
-    const long long my_inc = mine < nchunks ? inc[mine] : 0;
-    double my_end = 0.0;
-    const int cnt = nchunks - c0 < 32 ? (int)(nchunks - c0) : 32;
-    for (int j = 0; j < cnt; j++) {
-      const int m = __shfl_sync(0xffffffffu, my_meta, j);
-      const long long q = __shfl_sync(0xffffffffu, my_inc, j);
-      const int mode = m & 3, k = (m >> 2) - 2048;
-      if (mode == kModeInt) {
-        const double scaled = ldexp(run, 52 - k);
-        const long long s0 = (long long)scaled;
-        const long long s1 = s0 + q;
-        if (!(s0 >= (1ll << 52) && s1 < (1ll << 53) && (double)s0 == scaled)) *err = 1;  // guarantee violated
-        run = ldexp((double)s1, k - 52);
-      } else if (mode == kModeSlow) {
-        const u64 begin = (c0 + j) * kChunk;
-        double vals[kChunk / 32];
-#pragma unroll
-        for (int t = 0; t < kChunk / 32; t++) {
-          const u64 idx = begin + (u64)t * 32 + lane;
-          vals[t] = idx < bins ? load_p<kAmps>(src, idx) : 0.0;
-        }
-#pragma unroll
-        for (int t = 0; t < kChunk / 32; t++)
-          for (int l = 0; l < 32; l++) run += __shfl_sync(0xffffffffu, vals[t], l);
-      }
-      if (lane == j) my_end = run;
+  // inside a run of INT (super-)chunks of one binade the running sum is carried as an integer (units of
+  // the ulp): the dependent chain is then a single integer add per step
+  long long s_int = 0;
+  int cur_k = 1 << 30;
+  double dn = 0.0;
+  auto enter_int = [&](int k) {
+    if (k != cur_k) {
+      // exact scaling by powers of two (k > -900, so both exponents are in range)
+      const double up = __longlong_as_double((long long)(1023 + 52 - k) << 52);
+      dn = __longlong_as_double((long long)(1023 - 52 + k) << 52);
+      const double scaled = run * up;
+      s_int = (long long)scaled;
+      if (!(s_int >= (1ll << 52) && (double)s_int == scaled)) *err = 1;  // guarantee violated
+      cur_k = k;
     }
-    if (mine < nchunks) chunk_end[mine] = my_end;
+  };
+  for (u64 s0 = 0; s0 < nsuper; s0 += 32) {
+    const u64 smine = s0 + lane;
+    const int my_smeta = smine < nsuper ? smeta[smine] : 0;
+    const long long my_sinc = smine < nsuper ? sinc[smine] : 0;
+    long long my_start = 0;
+    const int scnt = nsuper - s0 < 32 ? (int)(nsuper - s0) : 32;
+    for (int sj = 0; sj < scnt; sj++) {
+      const int sm = __shfl_sync(0xffffffffu, my_smeta, sj);
+      const long long sq = __shfl_sync(0xffffffffu, my_sinc, sj);
+      const int smode = sm & 3, sk = (sm >> 2) - 2048;
+      if (smode == kModeInt) {
+        enter_int(sk);
+        if (lane == sj) my_start = s_int;  // running sum (in ulps of binade sk) before this super-chunk
+        s_int += sq;
+        if (s_int >= (1ll << 53)) *err = 1;
+        run = (double)s_int * dn;
+      } else if (smode == kModeZero) {
+        if (lane == sj) my_start = __double_as_longlong(run);  // every chunk end of it equals `run`
+      } else {
+        // mixed super-chunk: walk its chunks
+        const u64 c0 = (s0 + sj) * 32;
+        const u64 mine = c0 + lane;
+        const int my_meta = mine < nchunks ? meta[mine] : 0;
+        const long long my_inc = mine < nchunks ? inc[mine] : 0;
+        double my_end = 0.0;
+        const int cnt = nchunks - c0 < 32 ? (int)(nchunks - c0) : 32;
+        for (int j = 0; j < cnt; j++) {
+          const int m = __shfl_sync(0xffffffffu, my_meta, j);
+          const long long q = __shfl_sync(0xffffffffu, my_inc, j);
+          const int mode = m & 3, k = (m >> 2) - 2048;
+          if (mode == kModeInt) {
+            enter_int(k);
+            s_int += q;
+            if (s_int >= (1ll << 53)) *err = 1;
+            run = (double)s_int * dn;
+          } else if (mode == kModeSlow) {
+            const u64 begin = (c0 + j) * kChunk;
+            double vals[kChunk / 32];
+#pragma unroll
+            for (int t = 0; t < kChunk / 32; t++) {
+              const u64 idx = begin + (u64)t * 32 + lane;
+              vals[t] = idx < bins ? load_p<kAmps>(src, idx) : 0.0;
+            }
+#pragma unroll
+            for (int t = 0; t < kChunk / 32; t++)
+              for (int l = 0; l < 32; l++) run += __shfl_sync(0xffffffffu, vals[t], l);
+            cur_k = 1 << 30;  // leave integer mode: the next INT chunk re-derives it from `run`
+          }
+          if (lane == j) my_end = run;
+        }
+        if (mine < nchunks) chunk_end[mine] = my_end;
+      }
+    }
+    if (smine < nsuper) sstart[smine] = my_start;
+  }
+}
+
+// chunk ends of the uniform super-chunks, in parallel
+__global__ void __launch_bounds__(kThreads)
+chunk_fill_kernel(u64 nchunks, const int* __restrict__ smeta, const long long* __restrict__ sstart,
+                  const long long* __restrict__ pref, double* __restrict__ chunk_end) {
+  const u64 c = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nchunks) return;
+  const int sm = smeta[c >> 5];
+  const int smode = sm & 3, k = (sm >> 2) - 2048;
+  if (smode == kModeInt) {
+    const double dn = __longlong_as_double((long long)(1023 - 52 + k) << 52);
+    chunk_end[c] = (double)(sstart[c >> 5] + pref[c]) * dn;
+  } else if (smode == kModeZero) {
+    chunk_end[c] = __longlong_as_double(sstart[c >> 5]);
   }
 }
 
@@ -382,6 +477,10 @@ struct SampleWs {
   double* aprefix;     // nchunks (exact mode: approximate inclusive prefix of the chunk sums)
   long long* inc;      // nchunks (exact mode: integer increment of each chunk)
   int* meta;           // nchunks + 1 (exact mode: mode | binade; last entry = error flag)
+  long long* pref;     // nchunks (inclusive prefix of inc inside each super-chunk of 32 chunks)
+  int* smeta;          // nsuper
+  long long* sinc;     // nsuper
+  long long* sstart;   // nsuper
   double* seg1;        // ceil(nchunks/1024)
   double* uniforms;    // shots
   long long* out;      // shots
@@ -403,6 +502,15 @@ static size_t sample_ws_layout(int log2_bins, int shots, void* ws, SampleWs* out
   off += align_up(nchunks * sizeof(long long));
   if (out) out->meta = reinterpret_cast<int*>(base + off);
   off += align_up((nchunks + 1) * sizeof(int));
+  const u64 nsuper = (nchunks + 31) / 32;
+  if (out) out->pref = reinterpret_cast<long long*>(base + off);
+  off += align_up(nchunks * sizeof(long long));
+  if (out) out->smeta = reinterpret_cast<int*>(base + off);
+  off += align_up(nsuper * sizeof(int));
+  if (out) out->sinc = reinterpret_cast<long long*>(base + off);
+  off += align_up(nsuper * sizeof(long long));
+  if (out) out->sstart = reinterpret_cast<long long*>(base + off);
+  off += align_up(nsuper * sizeof(long long));
   if (out) out->seg1 = reinterpret_cast<double*>(base + off);
   off += align_up(nseg * sizeof(double));
   if (out) out->uniforms = reinterpret_cast<double*>(base + off);
@@ -437,7 +545,15 @@ static int sample_impl(const void* src, int log2_bins, const double* host_unifor
     QSV_CUDA(cudaMemsetAsync(w.meta + nchunks, 0, sizeof(int), s));
     chunk_classify_kernel<kAmps><<<(unsigned)nchunks, kThreads, 0, s>>>(src, bins, w.aprefix, w.meta, w.inc);
     QSV_LAUNCHED();
-    chunk_chain_kernel<kAmps><<<1, 32, 0, s>>>(src, bins, nchunks, w.meta, w.inc, w.chunk_end, w.meta + nchunks);
+    const u64 nsuper = (nchunks + 31) / 32;
+    super_classify_kernel<<<(unsigned)((nsuper * 32 + kThreads - 1) / kThreads), kThreads, 0, s>>>(
+        nchunks, w.meta, w.inc, w.smeta, w.sinc, w.pref);
+    QSV_LAUNCHED();
+    chunk_chain_kernel<kAmps><<<1, 32, 0, s>>>(src, bins, nchunks, w.meta, w.inc, w.smeta, w.sinc, w.chunk_end,
+                                               w.sstart, w.meta + nchunks);
+    QSV_LAUNCHED();
+    chunk_fill_kernel<<<(unsigned)((nchunks + kThreads - 1) / kThreads), kThreads, 0, s>>>(nchunks, w.smeta, w.sstart,
+                                                                                           w.pref, w.chunk_end);
     QSV_LAUNCHED();
     int err = 0;
     QSV_CUDA(cudaMemcpyAsync(&err, w.meta + nchunks, sizeof(int), cudaMemcpyDeviceToHost, s));
