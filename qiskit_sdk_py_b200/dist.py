@@ -67,12 +67,13 @@ class ShardedState:
         return (self.rank >> (phys - self.n_local)) & 1
 
     def _staging(self, amps):
+        """Two send and two receive buffers of ``amps`` amplitudes (the exchange is double-buffered)."""
         torch = self._torch
         dev = self.shard.comm_device()
-        if self._send is None or self._send.numel() < 2 * amps:
-            self._send = torch.empty(2 * amps, dtype=torch.float64, device=dev)
-            self._recv = torch.empty(2 * amps, dtype=torch.float64, device=dev)
-        return self._send[: 2 * amps], self._recv[: 2 * amps]
+        if self._send is None or self._send[0].numel() < 2 * amps:
+            self._send = [torch.empty(2 * amps, dtype=torch.float64, device=dev) for _ in range(2)]
+            self._recv = [torch.empty(2 * amps, dtype=torch.float64, device=dev) for _ in range(2)]
+        return self._send, self._recv
 
     # -- initialisation ----------------------------------------------------------------
     def init_basis0(self, phase=1.0 + 0.0j):
@@ -92,16 +93,30 @@ class ShardedState:
         half = 1 << (self.n_local - 1)
         chunk = min(self.chunk_amps, half)
         send, recv = self._staging(chunk)
-        for begin in range(0, half, chunk):
-            cnt = min(chunk, half - begin)
-            self.shard.pack_half(phys_local, 1 - beta, send, begin, cnt)
-            ops = [dist.P2POp(dist.isend, send[: 2 * cnt], peer, self.group),
-                   dist.P2POp(dist.irecv, recv[: 2 * cnt], peer, self.group)]
+        spans = [(begin, min(chunk, half - begin)) for begin in range(0, half, chunk)]
+
+        def exchange(i):
+            cnt = spans[i][1]
+            ops = [dist.P2POp(dist.isend, send[i % 2][: 2 * cnt], peer, self.group),
+                   dist.P2POp(dist.irecv, recv[i % 2][: 2 * cnt], peer, self.group)]
             if self.rank > peer:
                 ops.reverse()
-            for req in dist.batch_isend_irecv(ops):
+            return dist.batch_isend_irecv(ops)
+
+        # software pipeline: the NCCL exchange of chunk i+1 runs while chunk i is unpacked and chunk i+2
+        # is packed (the collective only waits for work enqueued before it was issued)
+        self.shard.pack_half(phys_local, 1 - beta, send[0], spans[0][0], spans[0][1])
+        reqs = exchange(0)
+        if len(spans) > 1:
+            self.shard.pack_half(phys_local, 1 - beta, send[1], spans[1][0], spans[1][1])
+        for i, (begin, cnt) in enumerate(spans):
+            for req in reqs:
                 req.wait()
-            self.shard.unpack_half(phys_local, 1 - beta, recv, begin, cnt)
+            if i + 1 < len(spans):
+                reqs = exchange(i + 1)
+            self.shard.unpack_half(phys_local, 1 - beta, recv[i % 2], begin, cnt)
+            if i + 2 < len(spans):
+                self.shard.pack_half(phys_local, 1 - beta, send[i % 2], spans[i + 2][0], spans[i + 2][1])
         qa, qb = self._logical_at(phys_global), self._logical_at(phys_local)
         self.pos[qa], self.pos[qb] = phys_local, phys_global
         self.swaps += 1
