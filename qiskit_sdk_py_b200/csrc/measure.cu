@@ -137,6 +137,25 @@ marginal_kernel(const double2* __restrict__ sv, const __grid_constant__ MargDesc
   if (threadIdx.x == 0) partial[(bin << d.log2_parts) + part] = acc;
 }
 
+// Few unmeasured qubits (n - m <= 10): one thread per bin adds its 2^(n-m) amplitudes in a fixed order.
+__global__ void __launch_bounds__(kThreads)
+marginal_small_kernel(const double2* __restrict__ sv, const __grid_constant__ MargDesc d, u64 bins,
+                      double* __restrict__ probs) {
+  const u64 bin = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (bin >= bins) return;
+  const int nu = d.n - d.m;
+  u64 base = 0;
+  for (int j = 0; j < d.m; j++) base |= ((bin >> j) & 1ull) << d.mq[j];
+  double acc = 0.0;
+  for (u64 u = 0; u < (1ull << nu); u++) {
+    u64 off = 0;
+    for (int j = 0; j < nu; j++) off |= ((u >> j) & 1ull) << d.uq[j];
+    const double2 a = sv[base | off];
+    acc += fma(a.x, a.x, a.y * a.y);
+  }
+  probs[bin] = acc;
+}
+
 __global__ void __launch_bounds__(kThreads)
 marginal_finish_kernel(const double* __restrict__ partial, u64 bins, int log2_parts, double* __restrict__ probs) {
   const u64 bin = (u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -688,6 +707,12 @@ int qsv_marginal(const double* sv, int n, const int32_t* measured_sorted, int m,
     if (!meas[q]) d.uq[nu++] = (uint8_t)q;
   d.log2_parts = marginal_log2_parts(n, m);
   const u64 bins = 1ull << m;
+  if (n - m <= 10 && bins >= 4096) {
+    marginal_small_kernel<<<(unsigned)((bins + kThreads - 1) / kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const double2*>(sv), d, bins, dev_probs);
+    QSV_LAUNCHED();
+    return 0;
+  }
   if (bins > (1ull << 31)) return fail(QSV_ERANGE, "qsv_marginal: too many bins");
   const unsigned gy = (unsigned)std::min<u64>(bins, 32768), gz = (unsigned)(bins / gy);
   dim3 grid(1u << d.log2_parts, gy, gz);

@@ -65,3 +65,82 @@ def test_no_fallback_when_library_missing(monkeypatch):
     monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libqsv.so")
     with pytest.raises(_lib.QsvLibraryError):
         gpu_factory("qasm_simulator").run(circuits.bell())
+
+
+def _oracle_factory(backend):
+    from oracle import basicaer_oracle as orc
+
+    if backend == "qasm_simulator":
+        return orc.OracleQasmSimulator()
+    if backend == "statevector_simulator":
+        return orc.OracleQasmSimulator(show_final_state=True)
+    return orc.OracleUnitarySimulator()
+
+
+def _same_as_oracle(backend, qobj, **options):
+    got = gpu_factory(backend).run(copy.deepcopy(qobj), **options)
+    ref = _oracle_factory(backend).run(copy.deepcopy(qobj), **options)
+    for g, r in zip(got["results"], ref["results"]):
+        assert g["shots"] == r["shots"]
+        if "seed_simulator" in qobj["config"]:
+            assert g["seed_simulator"] == r["seed_simulator"]
+        for key in ("counts", "memory"):
+            assert (key in g["data"]) == (key in r["data"])
+            if key in r["data"]:
+                assert g["data"][key] == r["data"][key]
+                if key == "counts":
+                    assert list(g["data"][key]) == list(r["data"][key])
+        for key in ("statevector", "unitary"):
+            assert (key in g["data"]) == (key in r["data"])
+            if key in r["data"]:
+                assert np.max(np.abs(np.asarray(g["data"][key]) - r["data"][key])) <= helpers.AMP_TOL
+    return got
+
+
+def test_edge_max_shots_and_memory():
+    """max_shots = 65536 (qasm_simulator.py:71) with memory=True."""
+    q = circuits.bell(shots=65536, seed_simulator=9)
+    q["config"]["memory"] = True
+    got = _same_as_oracle("qasm_simulator", q)
+    assert len(got["results"][0]["data"]["memory"]) == 65536
+
+
+def test_edge_wide_classical_register():
+    """More than 62 memory slots: classical memory exceeds int64, Python-int path."""
+    ins = [circuits.u2(0.0, np.pi, 0), circuits.cx(0, 1), circuits.u3(1.0, 0.2, 0.3, 2),
+           circuits.measure(0, 69), circuits.measure(1, 3), circuits.measure(2, 64), circuits.measure(0, 0)]
+    exp = circuits.make_experiment("wide", 3, ins, memory_slots=70)
+    _same_as_oracle("qasm_simulator", circuits.make_qobj(exp, shots=300, seed_simulator=4, memory=True))
+
+
+def test_edge_empty_and_single_qubit_circuits():
+    _same_as_oracle("statevector_simulator", circuits.make_qobj(circuits.make_experiment("empty", 3, []), shots=1))
+    _same_as_oracle("qasm_simulator", circuits.make_qobj(
+        circuits.make_experiment("only_measure", 2, circuits.measure_all(2), memory_slots=2), shots=20, seed_simulator=1))
+    ins = [circuits.u3(0.7, 0.1, 0.2, 0), {"name": "sx", "qubits": [0]}, circuits.u1(0.3, 0), circuits.measure(0, 0)]
+    _same_as_oracle("qasm_simulator", circuits.make_qobj(
+        circuits.make_experiment("one", 1, ins, memory_slots=1), shots=500, seed_simulator=3, memory=True))
+    _same_as_oracle("statevector_simulator", circuits.make_qobj(circuits.make_experiment("one_sv", 1, ins[:3]), shots=1))
+    _same_as_oracle("unitary_simulator", circuits.make_qobj(circuits.make_experiment("one_u", 1, ins[:3]), shots=1))
+
+
+@pytest.mark.parametrize("n", [7, 9])
+def test_unitary_simulator_larger(n):
+    ins = circuits.random_basis_instructions(n, 6, 100 + n)
+    _same_as_oracle("unitary_simulator", circuits.make_qobj(circuits.make_experiment("u%d" % n, n, ins), shots=1))
+
+
+def test_midcircuit_measure_reset_conditional_large_shots():
+    """Non-sampled path (per-shot simulation with the prefix snapshot): RNG order must match the reference."""
+    ins = [circuits.u2(0.0, np.pi, 0), circuits.cx(0, 1), circuits.u3(0.9, 0.1, 0.4, 2), circuits.cx(2, 3),
+           {"name": "measure", "qubits": [0], "memory": [0], "register": [0]},
+           {"name": "bfunc", "mask": "0x1", "relation": "==", "val": "0x1", "register": 4},
+           {"name": "x", "qubits": [3], "conditional": 4},
+           {"name": "reset", "qubits": [1]},
+           circuits.u2(0.3, 0.2, 1), circuits.cx(1, 4),
+           {"name": "measure", "qubits": [3], "memory": [1], "register": [1]},
+           {"name": "measure", "qubits": [4], "memory": [2], "register": [2]},
+           {"name": "measure", "qubits": [1], "memory": [3], "register": [3]}]
+    exp = circuits.make_experiment("mid", 5, ins, memory_slots=4)
+    _same_as_oracle("qasm_simulator", circuits.make_qobj(exp, shots=400, seed_simulator=77, memory=True))
+    _same_as_oracle("statevector_simulator", circuits.make_qobj(exp, shots=1, seed_simulator=78))

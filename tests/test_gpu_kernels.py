@@ -222,7 +222,7 @@ def test_prob_collapse(n):
 
 
 @pytest.mark.parametrize("n,measured", [(3, [0, 1, 2]), (6, [1, 4]), (10, [0]), (10, [9]), (12, [0, 3, 5, 11]),
-                                        (14, list(range(14))), (14, list(range(1, 14))), (18, [2, 17]),
+                                        (14, list(range(14))), (14, list(range(1, 14))), (18, [2, 17]), (16, [q for q in range(16) if q not in (3, 9)]),
                                         (20, list(range(20)))])
 def test_marginal_and_exact_sampling(n, measured):
     """_add_sample_measure (qasm_simulator.py:184-213): same indices as numpy's choice()."""
