@@ -163,6 +163,13 @@ int qsv_pack_half(const double* sv, int n_local, int local_qubit, int bit_value,
 int qsv_unpack_half(double* sv, int n_local, int local_qubit, int bit_value, const double* dev_buf,
                     size_t chunk_begin, size_t chunk_amps, void* stream);
 
+/* General form for swapping k global qubits with k local ones in a single all-to-all: the sub-block of
+ * 2^(n_local-k) amplitudes whose local bits local_qubits[i] equal bit i of `pattern`. */
+int qsv_pack_bits(const double* sv, int n_local, const int32_t* local_qubits, int k, uint32_t pattern,
+                  double* dev_buf, size_t chunk_begin, size_t chunk_amps, void* stream);
+int qsv_unpack_bits(double* sv, int n_local, const int32_t* local_qubits, int k, uint32_t pattern,
+                    const double* dev_buf, size_t chunk_begin, size_t chunk_amps, void* stream);
+
 /* Sum of |psi|^2 over the local shard (for distributed normalisation / sampling). */
 int qsv_norm2(const double* sv, int n_qubits, void* ws, double* host_out, void* stream);
 

@@ -78,6 +78,10 @@ SIGNATURES = {
     "qsv_unpack_half": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_size_t, _c_size_t, _c_void_p]),
     "qsv_expval_pauli": (_c_int, [_c_void_p, _c_int, ctypes.c_uint64, ctypes.c_uint64, _c_double, _c_double,
                                   _c_void_p, _p_double, _c_void_p]),
+    "qsv_pack_bits": (_c_int, [_c_void_p, _c_int, _p_int32, _c_int, ctypes.c_uint32, _c_void_p, _c_size_t, _c_size_t,
+                               _c_void_p]),
+    "qsv_unpack_bits": (_c_int, [_c_void_p, _c_int, _p_int32, _c_int, ctypes.c_uint32, _c_void_p, _c_size_t,
+                                 _c_size_t, _c_void_p]),
     "qsv_norm2": (_c_int, [_c_void_p, _c_int, _c_void_p, _p_double, _c_void_p]),
 }
 

@@ -31,6 +31,53 @@ unpack_half_kernel(double2* __restrict__ sv, int L, u64 bitv, const double2* __r
   }
 }
 
+// General form: the sub-block whose local bits `bits[0..k)` (ascending) equal the pattern `vals`.
+struct SubDesc {
+  int32_t k;
+  int32_t bits[8];   // ascending local bit positions
+  uint64_t value;    // the pattern already deposited at those positions
+};
+
+__device__ __forceinline__ u64 sub_index(const SubDesc& d, u64 h) {
+  for (int i = 0; i < d.k; i++) {
+    const int p = d.bits[i];
+    h = ((h >> p) << (p + 1)) | (h & ((1ull << p) - 1ull));
+  }
+  return h | d.value;
+}
+
+__global__ void __launch_bounds__(kThreads)
+pack_bits_kernel(const double2* __restrict__ sv, const __grid_constant__ SubDesc d, double2* __restrict__ buf,
+                 u64 begin, u64 count) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j < count; j += stride) buf[j] = sv[sub_index(d, begin + j)];
+}
+
+__global__ void __launch_bounds__(kThreads)
+unpack_bits_kernel(double2* __restrict__ sv, const __grid_constant__ SubDesc d, const double2* __restrict__ buf,
+                   u64 begin, u64 count) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j < count; j += stride) sv[sub_index(d, begin + j)] = buf[j];
+}
+
+static int make_sub(int n_local, const int32_t* local_qubits, int k, uint32_t pattern, SubDesc* d) {
+  if (k < 1 || k > 8 || k >= n_local || !local_qubits) return -1;
+  int order[8];
+  for (int i = 0; i < k; i++) order[i] = i;
+  for (int i = 0; i < k; i++)
+    for (int j = i + 1; j < k; j++)
+      if (local_qubits[order[j]] < local_qubits[order[i]]) { int t = order[i]; order[i] = order[j]; order[j] = t; }
+  d->k = k;
+  d->value = 0;
+  for (int i = 0; i < k; i++) {
+    const int q = local_qubits[order[i]];
+    if (q < 0 || q >= n_local || (i > 0 && q == d->bits[i - 1])) return -1;
+    d->bits[i] = q;
+    d->value |= (uint64_t)((pattern >> order[i]) & 1u) << q;
+  }
+  return 0;
+}
+
 static int grid_for(u64 n) {
   u64 blocks = (n + kThreads - 1) / kThreads;
   const u64 cap = (u64)kNumSMs * 16;
@@ -63,6 +110,32 @@ int qsv_unpack_half(double* sv, int n_local, int L, int bitv, const double* dev_
   if (count == 0) return 0;
   unpack_half_kernel<<<grid_for(count), kThreads, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<double2*>(sv), L, (u64)bitv, reinterpret_cast<const double2*>(dev_buf), begin, count);
+  QSV_LAUNCHED();
+  return 0;
+}
+
+int qsv_pack_bits(const double* sv, int n_local, const int32_t* local_qubits, int k, uint32_t pattern, double* dev_buf,
+                  size_t begin, size_t count, void* stream) {
+  SubDesc d;
+  if (!sv || !dev_buf || n_local < 2 || make_sub(n_local, local_qubits, k, pattern, &d) ||
+      begin + count > ((size_t)1 << (n_local - k)))
+    return fail(QSV_EINVAL, "qsv_pack_bits: bad arguments");
+  if (count == 0) return 0;
+  pack_bits_kernel<<<grid_for(count), kThreads, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const double2*>(sv), d, reinterpret_cast<double2*>(dev_buf), begin, count);
+  QSV_LAUNCHED();
+  return 0;
+}
+
+int qsv_unpack_bits(double* sv, int n_local, const int32_t* local_qubits, int k, uint32_t pattern, const double* dev_buf,
+                    size_t begin, size_t count, void* stream) {
+  SubDesc d;
+  if (!sv || !dev_buf || n_local < 2 || make_sub(n_local, local_qubits, k, pattern, &d) ||
+      begin + count > ((size_t)1 << (n_local - k)))
+    return fail(QSV_EINVAL, "qsv_unpack_bits: bad arguments");
+  if (count == 0) return 0;
+  unpack_bits_kernel<<<grid_for(count), kThreads, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<double2*>(sv), d, reinterpret_cast<const double2*>(dev_buf), begin, count);
   QSV_LAUNCHED();
   return 0;
 }

@@ -57,6 +57,7 @@ class ShardedState:
         self._send = None
         self._recv = None
         self.swaps = 0
+        self.fused_exchanges = 0
         self.swap_bytes = 0
 
     # -- helpers -----------------------------------------------------------------------
@@ -121,6 +122,75 @@ class ShardedState:
         self.pos[qa], self.pos[qb] = phys_local, phys_global
         self.swaps += 1
         self.swap_bytes += 16 * half
+
+    def swap_many(self, pairs):
+        """Swap k global bits with k local bits in ONE all-to-all among the 2^k ranks that differ only in
+        those global bits: ``pairs`` = [(phys_global, phys_local), ...].  Each rank keeps 1/2^k of its shard
+        and exchanges the other sub-blocks, (1 - 2^-k) of the shard in total -- against k/2 of the shard for
+        k successive pairwise swaps."""
+        if len(pairs) == 1:
+            return self.swap_global_local(*pairs[0])
+        dist = self._dist
+        k = len(pairs)
+        gbits = [pg - self.n_local for pg, _ in pairs]
+        lbits = [pl for _, pl in pairs]
+        beta = 0
+        for i, j in enumerate(gbits):
+            beta |= ((self.rank >> j) & 1) << i
+        peers = {}
+        for lam in range(1 << k):
+            if lam == beta:
+                continue
+            r = self.rank
+            for i, j in enumerate(gbits):
+                r = (r & ~(1 << j)) | (((lam >> i) & 1) << j)
+            peers[lam] = r
+        sub = 1 << (self.n_local - k)
+        chunk = max(1, min(self.chunk_amps // max(1, (1 << k) - 1), sub))
+        spans = [(begin, min(chunk, sub - begin)) for begin in range(0, sub, chunk)]
+        send, recv = self._staging(chunk * ((1 << k) - 1))
+        lams = sorted(peers)
+
+        def view(bufs, i, slot, cnt):
+            return bufs[i % 2][2 * slot * chunk: 2 * slot * chunk + 2 * cnt]
+
+        def pack(i):
+            begin, cnt = spans[i]
+            for slot, lam in enumerate(lams):
+                self.shard.pack_bits(lbits, lam, view(send, i, slot, cnt), begin, cnt)
+
+        def exchange(i):
+            cnt = spans[i][1]
+            ops = []
+            for slot, lam in enumerate(lams):
+                ops.append(dist.P2POp(dist.isend, view(send, i, slot, cnt), peers[lam], self.group))
+                ops.append(dist.P2POp(dist.irecv, view(recv, i, slot, cnt), peers[lam], self.group))
+            return dist.batch_isend_irecv(ops)
+
+        def unpack(i):
+            begin, cnt = spans[i]
+            for slot, lam in enumerate(lams):
+                # what arrives from the rank whose global bits are lam lands where my bits lam were
+                self.shard.unpack_bits(lbits, lam, view(recv, i, slot, cnt), begin, cnt)
+
+        pack(0)
+        reqs = exchange(0)
+        if len(spans) > 1:
+            pack(1)
+        for i in range(len(spans)):
+            for req in reqs:
+                req.wait()
+            if i + 1 < len(spans):
+                reqs = exchange(i + 1)
+            unpack(i)
+            if i + 2 < len(spans):
+                pack(i + 2)
+        for pg, pl in pairs:
+            qa, qb = self._logical_at(pg), self._logical_at(pl)
+            self.pos[qa], self.pos[qb] = pl, pg
+        self.swaps += k
+        self.fused_exchanges += 1
+        self.swap_bytes += 16 * sub * ((1 << k) - 1)
 
     # -- gates -------------------------------------------------------------------------
     def _localise(self, op):
@@ -201,10 +271,12 @@ class ShardedState:
                     need.append(q)
         need.sort(key=lambda q: first_use[q])
         never = len(deferred) + 1
+        pairs = []
+        taken = set()
         for q in need[: self.g]:
             if self.pos[q] < self.n_local:
                 continue
-            # victim: local logical qubit used furthest in the future (and later than q itself)
+            # victim: local logical qubit used furthest in the future (and not a partner of q's next gate)
             partners = set()
             for op in deferred:
                 if q in op.qubits:
@@ -212,15 +284,17 @@ class ShardedState:
                     break
             best, best_use = None, -1
             for lq in range(self.n):
-                if self.pos[lq] >= self.n_local or lq in need or lq in partners:
+                if self.pos[lq] >= self.n_local or lq in need or lq in partners or lq in taken:
                     continue
                 use = first_use.get(lq, never)
                 if use > best_use:
                     best, best_use = lq, use
             if best is None:
                 raise RuntimeError("no local qubit available to swap out")
-            self.swap_global_local(self.pos[q], self.pos[best])
-            first_use[best] = -1  # do not pick the same victim twice in this round
+            taken.add(best)
+            pairs.append((self.pos[q], self.pos[best]))
+        if pairs:
+            self.swap_many(pairs)
 
     def ensure_local(self, qubit):
         """Make logical ``qubit`` a local bit (used before measure / reset on it)."""

@@ -275,6 +275,19 @@ class DeviceState:
                                                 ctypes.c_void_p(buf.data_ptr()), int(begin), int(count),
                                                 self.stream), "qsv_unpack_half")
 
+    def pack_bits(self, local_qubits, pattern, buf, begin, count):
+        """buf <- amplitudes [begin, begin+count) of the sub-block with local_qubits[i] == bit i of pattern."""
+        with self._ctx():
+            _lib.check(self.lib.qsv_pack_bits(self.ptr, self.n, _int32_array(local_qubits), len(local_qubits),
+                                              int(pattern), ctypes.c_void_p(buf.data_ptr()), int(begin), int(count),
+                                              self.stream), "qsv_pack_bits")
+
+    def unpack_bits(self, local_qubits, pattern, buf, begin, count):
+        with self._ctx():
+            _lib.check(self.lib.qsv_unpack_bits(self.ptr, self.n, _int32_array(local_qubits), len(local_qubits),
+                                                int(pattern), ctypes.c_void_p(buf.data_ptr()), int(begin), int(count),
+                                                self.stream), "qsv_unpack_bits")
+
     def snapshot(self):
         return self.state.clone()
 

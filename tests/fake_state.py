@@ -105,6 +105,26 @@ class FakeState:
         idx = self._half_index(local_qubit, bit_value, begin, count)
         self.vec[idx] = buf[: 2 * count].numpy().copy().view(np.complex128)
 
+    def _sub_index(self, local_qubits, pattern, begin, count):
+        h = np.arange(begin, begin + count, dtype=np.int64)
+        order = sorted(range(len(local_qubits)), key=lambda i: local_qubits[i])
+        value = 0
+        for i in order:
+            q = local_qubits[i]
+            h = ((h >> q) << (q + 1)) | (h & ((1 << q) - 1))
+            value |= ((pattern >> i) & 1) << q
+        return h | value
+
+    def pack_bits(self, local_qubits, pattern, buf, begin, count):
+        import torch
+
+        idx = self._sub_index(local_qubits, pattern, begin, count)
+        buf[: 2 * count] = torch.from_numpy(np.ascontiguousarray(self.vec[idx]).view(np.float64).copy())
+
+    def unpack_bits(self, local_qubits, pattern, buf, begin, count):
+        idx = self._sub_index(local_qubits, pattern, begin, count)
+        self.vec[idx] = buf[: 2 * count].numpy().copy().view(np.complex128)
+
     def sample(self, measured_sorted, uniforms, exact_order=True, check_norm=True):
         n = self.n
         axis = list(range(n))

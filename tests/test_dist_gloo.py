@@ -50,7 +50,7 @@ def _worker(rank, world, port, n, seed, out_dir):
         else:
             mat = o.matrix
         ref = orc.apply_unitary(ref.reshape([2] * n), mat, list(o.qubits)).reshape(-1)
-    checks = {"swaps": st.swaps}
+    checks = {"swaps": st.swaps, "fused": st.fused_exchanges}
     # distributed probabilities on a permuted layout
     p = np.abs(ref) ** 2
     idx = np.arange(2 ** n)
@@ -77,7 +77,7 @@ def _worker(rank, world, port, n, seed, out_dir):
     assert err < 1e-12, err
     checks["err"] = err
     if rank == 0:
-        np.save(os.path.join(out_dir, "ok_%d_%d.npy" % (world, n)), np.array([checks["swaps"], err]))
+        np.save(os.path.join(out_dir, "ok_%d_%d.npy" % (world, n)), np.array([checks["swaps"], err, checks["fused"]]))
     dist.destroy_process_group()
 
 
@@ -88,3 +88,5 @@ def test_sharded_state_matches_oracle(tmp_path, world, n):
     res = np.load(os.path.join(str(tmp_path), "ok_%d_%d.npy" % (world, n)))
     assert res[0] > 0, "the test circuit should have needed qubit swaps"
     assert res[1] < 1e-12
+    if world == 4:
+        assert res[2] > 0, "world 4 should have used the fused multi-qubit exchange"
