@@ -60,7 +60,15 @@ def _install_stubs():
     if not hasattr(np, "product"):  # removed in numpy 2; used by quantum_info (operators/random.py:53)
         np.product = np.prod
     if "retworkx" not in sys.modules:
-        rx = _stub_module("retworkx")
+        # pure-Python stand-in for the part of retworkx DAGCircuit uses (retworkx_shim.py), so that the
+        # reference's transpile()/execute() can run here
+        import importlib.util
+
+        spec = importlib.util.spec_from_file_location(
+            "retworkx", os.path.join(os.path.dirname(os.path.abspath(__file__)), "retworkx_shim.py"))
+        rx = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(rx)
+        sys.modules["retworkx"] = rx
         _stub_module("retworkx.visualization")
         rx.visualization = sys.modules["retworkx.visualization"]
     if "ply" not in sys.modules:
