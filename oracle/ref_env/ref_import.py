@@ -5,7 +5,7 @@ golden fixtures) and by the CPU-side adapter tests that are skipped when /root/r
 absent (it is absent on the GPU box).  Nothing in the product package imports this file.
 
 The reference needs a few third-party modules that are not installed here and cannot be
-installed (no network): retworkx, ply, fastjsonschema, python-constraint, plus three Cython
+installed (no network): retworkx (-> retworkx_shim.py), ply (-> qasm2_reader.py), fastjsonschema, python-constraint, plus three Cython
 extensions that are not built in the read-only tree.  None of them is on the BasicAer
 arithmetic path (qiskit/providers/basicaer/qasm_simulator.py:145-161 is numpy only), so
 they are replaced by inert stand-ins registered in ``sys.modules`` *before* ``import qiskit``.
@@ -124,4 +124,18 @@ def import_reference():
         sys.path.insert(0, REFERENCE_ROOT)
     # namespace-ish parent for the un-__init__'d cython dir
     qiskit = importlib.import_module("qiskit")
+    if getattr(sys.modules.get("ply"), "__file__", None) is None:
+        _install_qasm_reader(qiskit)
     return qiskit
+
+
+def _install_qasm_reader(qiskit):
+    """Without ply the reference cannot parse OpenQASM; route the two loaders to qasm2_reader.py."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location(
+        "_qsv_qasm2_reader", os.path.join(os.path.dirname(os.path.abspath(__file__)), "qasm2_reader.py"))
+    reader = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(reader)
+    qiskit.QuantumCircuit.from_qasm_file = staticmethod(lambda path: reader.circuit_from_qasm_file(qiskit, path))
+    qiskit.QuantumCircuit.from_qasm_str = staticmethod(lambda text: reader.circuit_from_qasm_str(qiskit, text))

@@ -438,6 +438,88 @@ def expval_cases():
     print("wrote expval_pauli")
 
 
+def transpiled_cases():
+    """Circuits that go through the reference's own transpile() + assemble() (level 0/1 are deterministic;
+    the DAG is backed by oracle/ref_env/retworkx_shim.py), i.e. the Qobj streams execute() really produces."""
+    from qiskit import transpile
+    from qiskit.circuit.library import QFT, GroverOperator, QuantumVolume
+
+    sim = BasicAer.get_backend("qasm_simulator")
+
+    def lib_gates(n):
+        qc = QuantumCircuit(n, n)
+        for q in range(n):
+            qc.h(q)
+        qc.ccx(0, 1, 2)
+        qc.swap(1, 3)
+        qc.cswap(0, 2, 4)
+        qc.crz(0.7, 3, 4)
+        qc.ch(2, 0)
+        qc.cp(0.4, 1, 2)
+        qc.cy(4, 1)
+        qc.cz(0, 3)
+        qc.rxx(0.3, 1, 4)
+        qc.rzz(0.9, 2, 3)
+        qc.mcx([0, 1, 2], 3)
+        qc.t(0)
+        qc.sdg(1)
+        qc.sx(2)
+        qc.ry(0.2, 3)
+        qc.global_phase = 0.5
+        return qc
+
+    for level in (0, 1):
+        qc = lib_gates(5)
+        save("transpiled_lib_gates_l%d_state" % level, "statevector_simulator",
+             assembled(transpile(qc, sim, optimization_level=level), shots=1))
+        qc.measure(range(5), range(5))
+        save("transpiled_lib_gates_l%d_counts" % level, "qasm_simulator",
+             assembled(transpile(qc, sim, optimization_level=level), shots=4000, seed_simulator=7))
+    # library QFT (with the final swaps) on a product state
+    qc = QuantumCircuit(9)
+    for q in range(9):
+        qc.ry(0.3 + 0.2 * q, q)
+    qc = qc.compose(QFT(9))
+    save("transpiled_qft_lib_9_state", "statevector_simulator", assembled(transpile(qc, sim, optimization_level=1), shots=1))
+    # library quantum volume: SU(4) blocks stay ``unitary`` instructions
+    qv = QuantumVolume(10, 10, seed=17)
+    qv.measure_all()
+    save("transpiled_qv_lib_10_counts", "qasm_simulator",
+         assembled(transpile(qv, sim, optimization_level=1), shots=4096, seed_simulator=42))
+    # Grover iteration (multi-controlled gates unrolled to the basis)
+    oracle_c = QuantumCircuit(5)
+    oracle_c.x([1, 3])
+    oracle_c.h(4)
+    oracle_c.mcx([0, 1, 2, 3], 4)
+    oracle_c.h(4)
+    oracle_c.x([1, 3])
+    grover = QuantumCircuit(5, 5)
+    grover.h(range(5))
+    op = GroverOperator(oracle_c)
+    for _ in range(3):
+        grover = grover.compose(op)
+    grover.measure(range(5), range(5))
+    save("transpiled_grover_5_counts", "qasm_simulator",
+         assembled(transpile(grover, sim, optimization_level=1), shots=2000, seed_simulator=5))
+    # initialize + reset + conditional through the transpiler
+    rng = np.random.RandomState(3)
+    vec = rng.randn(8) + 1j * rng.randn(8)
+    vec /= np.linalg.norm(vec)
+    qr = QuantumRegister(4, "qr")
+    cr = ClassicalRegister(4, "cr")
+    qc = QuantumCircuit(qr, cr)
+    qc.h(3)
+    qc.initialize(vec, [0, 1, 2])
+    qc.cx(3, 0)
+    qc.measure(0, 0)
+    qc.reset(1)
+    qc.h(1)
+    qc.x(2).c_if(cr, 1)
+    qc.measure(range(4), range(4))
+    save("transpiled_init_reset_cond_counts", "qasm_simulator",
+         assembled(transpile(qc, sim, optimization_level=1), shots=3000, seed_simulator=21, memory=True))
+
+
 def large_cases():
     save("qft_16_product", "statevector_simulator", gen.qft(16, state_seed=3))
     save("qv_16_counts", "qasm_simulator", gen.quantum_volume(16, shots=8192, seed_simulator=42))
@@ -458,15 +540,20 @@ if __name__ == "__main__":
     ap.add_argument("--huge", action="store_true")
     ap.add_argument("--only-large", action="store_true")
     ap.add_argument("--only-expval", action="store_true")
+    ap.add_argument("--only-transpiled", action="store_true")
     args = ap.parse_args()
     if args.only_expval:
         expval_cases()
+        sys.exit(0)
+    if args.only_transpiled:
+        transpiled_cases()
         sys.exit(0)
     if not args.only_large:
         check_generators_against_reference()
         cases_from_reference_tests()
         cases_from_generators()
         expval_cases()
+        transpiled_cases()
     if args.large or args.only_large:
         large_cases()
     if args.huge:
