@@ -59,18 +59,20 @@ def _install_stubs():
 
     if not hasattr(np, "product"):  # removed in numpy 2; used by quantum_info (operators/random.py:53)
         np.product = np.prod
+    if not hasattr(np, "unicode_"):  # removed in numpy 2; used by result/counts handling (opflow state functions)
+        np.unicode_ = np.str_
     if "retworkx" not in sys.modules:
         # pure-Python stand-in for the part of retworkx DAGCircuit uses (retworkx_shim.py), so that the
         # reference's transpile()/execute() can run here
-        import importlib.util
-
-        spec = importlib.util.spec_from_file_location(
-            "retworkx", os.path.join(os.path.dirname(os.path.abspath(__file__)), "retworkx_shim.py"))
-        rx = importlib.util.module_from_spec(spec)
-        spec.loader.exec_module(rx)
+        rx = _load_sibling("retworkx", "retworkx_shim.py")
         sys.modules["retworkx"] = rx
         _stub_module("retworkx.visualization")
         rx.visualization = sys.modules["retworkx.visualization"]
+    if "ddt" not in sys.modules:
+        try:
+            importlib.import_module("ddt")
+        except ImportError:
+            sys.modules["ddt"] = _load_sibling("ddt", "ddt_shim.py")
     if "ply" not in sys.modules:
         ply = _stub_module("ply")
         ply.lex = _stub_module("ply.lex")
@@ -95,6 +97,15 @@ def _install_stubs():
     ):
         if name not in sys.modules:
             _stub_module(name)
+
+
+def _load_sibling(name, filename):
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location(name, os.path.join(os.path.dirname(os.path.abspath(__file__)), filename))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
 
 
 def _load_compiled_exp_value():
@@ -131,11 +142,6 @@ def import_reference():
 
 def _install_qasm_reader(qiskit):
     """Without ply the reference cannot parse OpenQASM; route the two loaders to qasm2_reader.py."""
-    import importlib.util
-
-    spec = importlib.util.spec_from_file_location(
-        "_qsv_qasm2_reader", os.path.join(os.path.dirname(os.path.abspath(__file__)), "qasm2_reader.py"))
-    reader = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(reader)
+    reader = _load_sibling("_qsv_qasm2_reader", "qasm2_reader.py")
     qiskit.QuantumCircuit.from_qasm_file = staticmethod(lambda path: reader.circuit_from_qasm_file(qiskit, path))
     qiskit.QuantumCircuit.from_qasm_str = staticmethod(lambda text: reader.circuit_from_qasm_str(qiskit, text))

@@ -275,11 +275,32 @@ PyDAG = PyDiGraph
 
 
 class PyGraph(PyDiGraph):
-    """Undirected variant (coupling maps); only constructed, never traversed, on the paths used here."""
+    """Undirected variant: an edge is stored once and seen from both ends (opflow/converters/abelian_grouper.py:108)."""
 
-    def add_edge(self, u, v, obj):
-        eid = super().add_edge(u, v, obj)
-        return eid
+    def neighbors(self, idx):
+        seen, out = set(), []
+        for eid in self._out.get(idx, []) + self._in.get(idx, []):
+            u, v, _ = self._edges[eid]
+            other = v if u == idx else u
+            if other not in seen:
+                seen.add(other)
+                out.append(other)
+        return out
+
+    def degree(self, idx):
+        return len(self._out.get(idx, [])) + len(self._in.get(idx, []))
+
+
+def graph_greedy_color(graph):
+    """Greedy colouring, largest degree first (abelian_grouper.py:112); returns {node index: colour}."""
+    colors = {}
+    for node in sorted(graph._nodes, key=lambda n: (-graph.degree(n), n)):
+        used = {colors[m] for m in graph.neighbors(node) if m in colors}
+        color = 0
+        while color in used:
+            color += 1
+        colors[node] = color
+    return colors
 
 
 # -- algorithms ------------------------------------------------------------------------------------
