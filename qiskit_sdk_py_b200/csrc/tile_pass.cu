@@ -36,7 +36,9 @@ thread_local char g_err[512] = "";
 unsigned long long g_launches = 0;
 
 constexpr int kMaxOps = QSV_MAX_PASS_GATES;
-constexpr int kMaxMat = 1536;  // doubles of matrix payload per pass (48 dense 2-qubit gates)
+constexpr int kMaxIn = 1536;   // doubles of matrix payload per pass as passed in (48 dense 2-qubit gates)
+constexpr int kMaxMat = 3072;  // ... after pair fusion (24 fused 3-qubit blocks of 8x8 complex)
+constexpr int kGateDense3 = 6; // internal kind: two 2-qubit gates sharing a qubit, fused by launch_pass
 constexpr int kMaxPT = 512;    // threads of the pass kernel: 2^(b-3), at most 512 (one warp per 2^8 amplitudes)
 constexpr int kWarps = kMaxPT / 32;
 constexpr int kInner = 8;      // inner bits of a stage: 2^8 amplitudes per warp
@@ -45,7 +47,8 @@ constexpr int kMaxStages = kMaxOps;
 struct __align__(4) PassOp {
   uint8_t kind, t0, t1, ngl;  // t0/t1: tile-local gate bits; ngl = log2(#groups in a warp's sub-cube)
   uint16_t moff;              // offset (doubles) of the matrix in PassDesc::mats
-  uint16_t z0, z1;            // slot increments of the gate bits: cj[t0], cj[t1]
+  uint16_t foff;              // offset (units of 64 doubles) of the B fragments in shared memory
+  uint16_t z0, z1, z2;        // slot increments of the gate bits: cj[t0], cj[t1] (, cj[t2] for fused blocks)
   uint16_t col[6];            // slot increments of the free inner bits: col[0..2] vary inside a warp step
 };
 
@@ -59,6 +62,7 @@ struct __align__(4) PassStage {
 
 struct PassDesc {
   int32_t n, b, nops, nstages;
+  int32_t nfrag;        // B-fragment units (64 doubles) of all ops: 1 per 2-qubit gate, 4 per fused block
   uint32_t n_tiles;
   uint32_t flags;       // QSV_DEBUG_FLAGS (profiling experiments)
   uint32_t pb_ld;       // log2(amplitudes per bulk-load piece): contiguous low tile bits, at most 3 (128 B)
@@ -172,8 +176,8 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
   const uint32_t tile_amps = 1u << b;
   uint32_t tile_slots = tile_amps;
   for (int j = 3; j < b; j++) tile_slots += pad_of_bit(j);
-  double (*frag)[64] = reinterpret_cast<double (*)[64]>(tile + tile_slots);    // [nops][64] B fragments
-  OpRec* oprec = reinterpret_cast<OpRec*>(frag + nops_all);                     // [nops]
+  double* frag = reinterpret_cast<double*>(tile + tile_slots);                  // [nfrag][64] B fragments
+  OpRec* oprec = reinterpret_cast<OpRec*>(frag + (size_t)d.nfrag * 64);         // [nops]
   uint32_t (*opl)[32] = reinterpret_cast<uint32_t (*)[32]>(oprec + nops_all);   // [nops][32] lane slots
   uint32_t (*st_warp)[kWarps] = reinterpret_cast<uint32_t (*)[kWarps]>(opl + nops_all);  // [nstages][16]
   uint32_t (*st_lane)[32] = reinterpret_cast<uint32_t (*)[32]>(st_warp + nst_all);       // [nstages][32]
@@ -201,7 +205,7 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
       double v;
       if ((nrow & 1) == 0) v = (kcol & 1) == 0 ? m[0] : -m[1];
       else v = (kcol & 1) == 0 ? m[1] : m[0];
-      frag[o][e] = v;
+      frag[op.foff * 64 + e] = v;
     }
     if (e < 32) {
       const uint32_t g = e >> 2, c = e & 3u;
@@ -218,8 +222,25 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
       r.z0 = op.z0; r.z1 = op.z1; r.c3 = op.col[3]; r.c4 = op.col[4]; r.c5 = op.col[5];
       r.kind = op.kind; r.ngl = op.ngl; r.t0 = op.t0; r.t1 = op.t1;
       r.moff = op.moff;
+      if (op.kind == kGateDense3) { r.c5 = op.z2; r.moff = op.foff; }  // a fused block has at most 5 free bits
+      if (op.kind == QSV_GATE_DENSE2) r.moff = op.foff;
       oprec[o] = r;
     }
+  }
+  // B fragments of fused 3-qubit blocks: the 8x8 complex block is the 16x16 real matrix [[Re,-Im],[Im,Re]];
+  // fragment (h, s) -- output half h, k-slice s -- holds Mreal[n = 8 h + (l >> 2)][k = 4 s + (l & 3)] in lane l
+  for (int idx = tid; idx < nops * 256; idx += kPT) {
+    const int o = idx >> 8, e = idx & 255;
+    const PassOp& op = d.ops[o];
+    if (op.kind != kGateDense3) continue;
+    const int h = e >> 7, sl = (e >> 5) & 3, l = e & 31;
+    const int nrow = 8 * h + (l >> 2), kcol = 4 * sl + (l & 3);
+    const int r = nrow >> 1, c = kcol >> 1;
+    const double* m = d.mats + op.moff + 2 * (8 * r + c);
+    double v;
+    if ((nrow & 1) == 0) v = (kcol & 1) == 0 ? m[0] : -m[1];
+    else v = (kcol & 1) == 0 ? m[1] : m[0];
+    frag[op.foff * 64 + e] = v;
   }
   for (int idx = tid; idx < nstages * 64; idx += kPT) {
     const int sidx = idx >> 6, e = idx & 63;
@@ -307,7 +328,8 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
 
         if (rec.kind == QSV_GATE_DENSE2) {
           // ---- FP64 tensor path: 8 groups per warp step, up to 8 steps per sub-cube ----
-          const double b0 = frag[o][lane], b1 = frag[o][32 + lane];
+          const double* fr = frag + (uint32_t)rec.moff * 64u;
+          const double b0 = fr[lane], b1 = fr[32 + lane];
           const uint32_t v = opl[o][lane];
           const uint32_t a_ld = (s_w + (v & 0xffffu)) << 4;  // byte offsets of 16-byte slots
           const uint32_t a_st = (s_w + (v >> 16)) << 4;
@@ -352,6 +374,71 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
               dmma884(d0, d1, x0, b0);
               dmma884(d0, d1, x1, b1);
               if (valid) *reinterpret_cast<double2*>(reinterpret_cast<char*>(tile) + (a_st + xo)) = make_double2(d0, d1);
+            }
+          }
+        } else if (rec.kind == kGateDense3) {
+          // ---- fused pair of 2-qubit gates sharing a qubit: one 8x8 complex block per 8 amplitudes, i.e. one
+          // shared-memory round trip for two gates at the same FP64 work (8 DMMA per 64 amplitudes) ----
+          const double* fr = frag + (uint32_t)rec.moff * 64u;
+          double bq[8];
+#pragma unroll
+          for (int q = 0; q < 8; q++) bq[q] = fr[q * 32 + lane];
+          const uint32_t v = opl[o][lane];
+          const uint32_t a_ld = (s_w + (v & 0xffffu)) << 4;
+          const uint32_t a_st = (s_w + (v >> 16)) << 4;
+          const uint32_t z1b = (uint32_t)rec.z1 << 4, z2b = (uint32_t)rec.c5 << 4;
+          const uint32_t c3 = (uint32_t)rec.c3 << 4, c4 = (uint32_t)rec.c4 << 4;
+          if (rec.ngl == 5u) {
+#pragma unroll
+            for (int hb = 0; hb < 2; hb++) {
+              const uint32_t xh = hb ? c4 : 0u;
+              const uint32_t xo[2] = {xh, xh + c3};
+              double x[2][4];
+#pragma unroll
+              for (int it = 0; it < 2; it++) {
+                const uint32_t a = a_ld + xo[it];
+                x[it][0] = *reinterpret_cast<const double*>(tb8 + a);
+                x[it][1] = *reinterpret_cast<const double*>(tb8 + (a + z1b));
+                x[it][2] = *reinterpret_cast<const double*>(tb8 + (a + z2b));
+                x[it][3] = *reinterpret_cast<const double*>(tb8 + (a + z1b + z2b));
+              }
+#pragma unroll
+              for (int it = 0; it < 2; it++) {
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                  double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+                  for (int sl = 0; sl < 4; sl++) dmma884(d0, d1, x[it][sl], bq[4 * h + sl]);
+                  *reinterpret_cast<double2*>(reinterpret_cast<char*>(tile) + (a_st + xo[it] + (h ? z2b : 0u))) =
+                      make_double2(d0, d1);
+                }
+              }
+            }
+          } else {
+            const uint32_t ng = 1u << rec.ngl;
+            const uint32_t n_it = ng > 8u ? (ng >> 3) : 1u;
+            for (uint32_t it = 0; it < n_it; it++) {
+              uint32_t xo = 0;
+              if (it & 1u) xo += c3;
+              if (it & 2u) xo += c4;
+              const bool valid = (g | (it << 3)) < ng;
+              double x[4] = {0.0, 0.0, 0.0, 0.0};
+              if (valid) {
+                const uint32_t a = a_ld + xo;
+                x[0] = *reinterpret_cast<const double*>(tb8 + a);
+                x[1] = *reinterpret_cast<const double*>(tb8 + (a + z1b));
+                x[2] = *reinterpret_cast<const double*>(tb8 + (a + z2b));
+                x[3] = *reinterpret_cast<const double*>(tb8 + (a + z1b + z2b));
+              }
+#pragma unroll
+              for (int h = 0; h < 2; h++) {
+                double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+                for (int sl = 0; sl < 4; sl++) dmma884(d0, d1, x[sl], bq[4 * h + sl]);
+                if (valid)
+                  *reinterpret_cast<double2*>(reinterpret_cast<char*>(tile) + (a_st + xo + (h ? z2b : 0u))) =
+                      make_double2(d0, d1);
+              }
             }
           }
         } else {
@@ -438,7 +525,7 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
   bulk_wait_read();
 }
 
-// One body, three register budgets: more resident CTAs per SM (5 x 256 threads for the default 11-qubit
+// One body, three launch shapes: several resident CTAs per SM (4 x 256 threads for the default 11-qubit
 // tile) keep more tiles in flight, which is what hides the HBM round trip of each CTA.
 template <int kBlock, int kMinBlocks>
 __global__ void __launch_bounds__(kBlock, kMinBlocks)
@@ -544,7 +631,49 @@ struct HostOp {
   uint32_t touch;  // every tile bit the gate reads (ordering)
   uint32_t need;   // tile bits that must be inner bits of the gate's stage
   int moff;
+  int t2;          // third bit of a fused block
+  int foff;        // B-fragment offset (units of 64 doubles)
 };
+
+// ---- pair fusion (host): 2-qubit dense gates that share a qubit and are adjacent on it become one
+// 3-qubit block.  The block costs the same FP64 work as its two gates (8 complex MACs per amplitude) but
+// only one shared-memory round trip, which is what bounds the single-gate path.  Gates that act inside the
+// bits of the current block are multiplied in for free. ----
+static inline int popc_u(uint32_t x) { return __builtin_popcount(x); }
+
+// `g4` (4x4 complex, row-major, index bit 0 = position pa, bit 1 = position pb) embedded into `nb` index bits
+static void embed_gate(const double* g4, int nb, int pa, int pb, double* out) {
+  const int dim = 1 << nb;
+  const int keep = (dim - 1) & ~((1 << pa) | (1 << pb));
+  for (int r = 0; r < dim; r++)
+    for (int c = 0; c < dim; c++) {
+      double re = 0.0, im = 0.0;
+      if ((r & keep) == (c & keep)) {
+        const int rg = ((r >> pa) & 1) | (((r >> pb) & 1) << 1);
+        const int cg = ((c >> pa) & 1) | (((c >> pb) & 1) << 1);
+        re = g4[2 * (4 * rg + cg)];
+        im = g4[2 * (4 * rg + cg) + 1];
+      }
+      out[2 * (dim * r + c)] = re;
+      out[2 * (dim * r + c) + 1] = im;
+    }
+}
+
+// out = a * b (complex dim x dim, row-major); out must not alias a or b
+static void cmat_mul(const double* a, const double* b, int dim, double* out) {
+  for (int r = 0; r < dim; r++)
+    for (int c = 0; c < dim; c++) {
+      double re = 0.0, im = 0.0;
+      for (int k = 0; k < dim; k++) {
+        const double ar = a[2 * (dim * r + k)], ai = a[2 * (dim * r + k) + 1];
+        const double br = b[2 * (dim * k + c)], bi = b[2 * (dim * k + c) + 1];
+        re += ar * br - ai * bi;
+        im += ar * bi + ai * br;
+      }
+      out[2 * (dim * r + c)] = re;
+      out[2 * (dim * r + c) + 1] = im;
+    }
+}
 
 // bank class of a tile-local bit: it shifts the bank group by 2^(j mod 3) (see the slot layout)
 static inline int bank_class(int bit) { return bit % 3; }
@@ -613,11 +742,11 @@ static int ensure_attrs() {
   if (!g_attr_set[dev]) {
     const int max_dyn = (int)((sizeof(double2) << QSV_MAX_TILE_QUBITS) + 64 * 1024);
     QSV_CUDA(cudaFuncSetAttribute(tile_pass_kernel<512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
-    QSV_CUDA(cudaFuncSetAttribute(tile_pass_kernel<256, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
-    QSV_CUDA(cudaFuncSetAttribute(tile_pass_kernel<128, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+    QSV_CUDA(cudaFuncSetAttribute(tile_pass_kernel<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+    QSV_CUDA(cudaFuncSetAttribute(tile_pass_kernel<128, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
     QSV_CUDA(cudaFuncSetAttribute(tile_pass_kernel<512, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    QSV_CUDA(cudaFuncSetAttribute(tile_pass_kernel<256, 5>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    QSV_CUDA(cudaFuncSetAttribute(tile_pass_kernel<128, 10>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    QSV_CUDA(cudaFuncSetAttribute(tile_pass_kernel<256, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    QSV_CUDA(cudaFuncSetAttribute(tile_pass_kernel<128, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     QSV_CUDA(cudaFuncSetAttribute(dense_k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(2 * (sizeof(double2) << 12) + 4096 * sizeof(uint32_t))));
     g_attr_set[dev] = true;
@@ -727,12 +856,14 @@ static int launch_pass(double* sv, int n, const int32_t* tile_qubits, int n_tile
   }
 
   // ---- gates -> host ops (tile-local bits, matrices) ----
-  HostOp hops[kMaxOps];
-  double mats[kMaxMat];
+  HostOp hops_in[kMaxOps];
+  double mats_in[kMaxIn];
   int moff = 0;
   for (int i = 0; i < n_gates; i++) {
     const qsv_gate_t& gsrc = gates[i];
-    HostOp& op = hops[i];
+    HostOp& op = hops_in[i];
+    op.t2 = -1;
+    op.foff = 0;
     int nq, ndbl;
     switch (gsrc.kind) {
       case QSV_GATE_DENSE1: nq = 1; ndbl = b >= 2 ? 32 : 8; break;
@@ -746,7 +877,7 @@ static int launch_pass(double* sv, int n, const int32_t* tile_qubits, int n_tile
       return fail(QSV_EINVAL, "qsv_apply_pass: gate qubit q0 is not a tile qubit");
     if (nq == 2 && (gsrc.q1 < 0 || gsrc.q1 >= n || local_of[gsrc.q1] < 0 || gsrc.q1 == gsrc.q0))
       return fail(QSV_EINVAL, "qsv_apply_pass: gate qubit q1 is not a tile qubit / equals q0");
-    if (moff + ndbl > kMaxMat) return fail(QSV_ERANGE, "qsv_apply_pass: matrix payload too large");
+    if (moff + ndbl > kMaxIn) return fail(QSV_ERANGE, "qsv_apply_pass: matrix payload too large");
     op.kind = gsrc.kind;
     op.t0 = local_of[gsrc.q0];
     op.t1 = nq == 2 ? local_of[gsrc.q1] : -1;
@@ -760,12 +891,110 @@ static int launch_pass(double* sv, int n, const int32_t* tile_qubits, int n_tile
       default: op.need = 0; break;                      // diagonal gates need no particular partition
     }
     if (gsrc.kind == QSV_GATE_DENSE1 && b >= 2) {
-      memset(mats + moff, 0, sizeof(double) * 32);  // widened once the partner bit is known
-      memcpy(mats + moff, gsrc.m, sizeof(double) * 8);
+      memset(mats_in + moff, 0, sizeof(double) * 32);  // widened once the partner bit is known
+      memcpy(mats_in + moff, gsrc.m, sizeof(double) * 8);
     } else {
-      memcpy(mats + moff, gsrc.m, sizeof(double) * ndbl);
+      memcpy(mats_in + moff, gsrc.m, sizeof(double) * ndbl);
     }
     moff += ndbl;
+  }
+  if (const char* e = getenv("QSV_DEBUG_FLAGS")) d.flags = (uint32_t)atoi(e);
+
+  // ---- pair fusion: hops_in (program order) -> hops (fused, still a valid order) ----
+  HostOp hops[kMaxOps];
+  double mats[kMaxMat];
+  const int n_in = n_gates;
+  {
+    const bool fuse_on = !(d.flags & 8u) && b >= 3;
+    bool used[kMaxOps] = {false};
+    int n_out = 0, mo = 0;
+    for (int i = 0; i < n_in; i++) {
+      if (used[i]) continue;
+      used[i] = true;
+      const HostOp& src = hops_in[i];
+      HostOp& out = hops[n_out++];
+      out = src;
+      out.moff = mo;
+      int ndbl_i;
+      switch (src.kind) {
+        case QSV_GATE_DENSE1: ndbl_i = b >= 2 ? 32 : 8; break;
+        case QSV_GATE_DENSE2: ndbl_i = 32; break;
+        case QSV_GATE_DIAG1: ndbl_i = 4; break;
+        case QSV_GATE_DIAG2: ndbl_i = 8; break;
+        default: ndbl_i = 0; break;
+      }
+      if (src.kind != QSV_GATE_DENSE2 || !fuse_on) {
+        memcpy(mats + mo, mats_in + src.moff, sizeof(double) * ndbl_i);
+        mo += ndbl_i;
+        continue;
+      }
+      // current block: index bit k of `cur` <-> tile bit ub[k]
+      int ub[3] = {src.t0, src.t1, -1}, nb = 2;
+      uint32_t cur_touch = src.touch;
+      double cur[128], emb[128], tmp[128];
+      memcpy(cur, mats_in + src.moff, sizeof(double) * 32);
+      uint32_t touched = 0;
+      for (int j = i + 1; j < n_in; j++) {
+        if (used[j]) continue;
+        const HostOp& oj = hops_in[j];
+        if (oj.kind == QSV_GATE_DENSE2 && !(oj.touch & touched) && (oj.touch & cur_touch) &&
+            popc_u(oj.touch | cur_touch) <= 3) {
+          if (popc_u(oj.touch | cur_touch) == 3 && nb == 2) {  // grow to three bits
+            for (int q = 0; q < 32; q++) tmp[q] = cur[q];
+            embed_gate(tmp, 3, 0, 1, cur);
+            ub[2] = (oj.touch & ~cur_touch) == (1u << oj.t0) ? oj.t0 : oj.t1;
+            nb = 3;
+            cur_touch |= oj.touch;
+          }
+          int pa = -1, pb2 = -1;
+          for (int k = 0; k < nb; k++) {
+            if (ub[k] == oj.t0) pa = k;
+            if (ub[k] == oj.t1) pb2 = k;
+          }
+          embed_gate(mats_in + oj.moff, nb, pa, pb2, emb);
+          cmat_mul(emb, cur, 1 << nb, tmp);
+          memcpy(cur, tmp, sizeof(double) * 2 * (1 << nb) * (1 << nb));
+          used[j] = true;
+          continue;
+        }
+        touched |= oj.touch;
+        if ((touched & cur_touch) == cur_touch) break;  // every bit of the block is fenced off
+      }
+      if (nb == 2) {
+        memcpy(mats + mo, cur, sizeof(double) * 32);
+        mo += 32;
+        continue;
+      }
+      // roles of the three bits: (t0, t1) should differ in bank class (see the slot layout)
+      int role[3] = {0, 1, 2};
+      bool found = false;
+      for (int a = 0; a < 3 && !found; a++)
+        for (int c = 0; c < 3 && !found; c++)
+          if (a != c && bank_class(ub[a]) != bank_class(ub[c])) {
+            role[0] = a; role[1] = c; role[2] = 3 - a - c;
+            found = true;
+          }
+      double* m8 = mats + mo;
+      for (int r = 0; r < 8; r++)
+        for (int c = 0; c < 8; c++) {
+          int ro = 0, co = 0;  // index in the ub order
+          for (int k = 0; k < 3; k++) {
+            ro |= ((r >> k) & 1) << role[k];
+            co |= ((c >> k) & 1) << role[k];
+          }
+          m8[2 * (8 * r + c)] = cur[2 * (8 * ro + co)];
+          m8[2 * (8 * r + c) + 1] = cur[2 * (8 * ro + co) + 1];
+        }
+      out.kind = kGateDense3;
+      out.t0 = ub[role[0]];
+      out.t1 = ub[role[1]];
+      out.t2 = ub[role[2]];
+      out.touch = cur_touch;
+      out.need = cur_touch;
+      mo += 128;
+    }
+    n_gates = n_out;
+    moff = mo;
   }
 
   // ---- stages ----
@@ -805,6 +1034,13 @@ static int launch_pass(double* sv, int n, const int32_t* tile_qubits, int n_tile
     }
   }
   memcpy(d.mats, mats, sizeof(double) * moff);
+  int nfrag = 0;
+  for (int k = 0; k < n_gates; k++) {
+    sops[k].foff = nfrag;
+    if (sops[k].kind == QSV_GATE_DENSE2) nfrag += 1;
+    if (sops[k].kind == kGateDense3) nfrag += 4;
+  }
+  d.nfrag = nfrag;
 
   auto bvec = [&](int bit) { return bank_class(bit); };
   auto sw1 = [&](int bit) { return d.cj[bit]; };
@@ -851,14 +1087,16 @@ static int launch_pass(double* sv, int n, const int32_t* tile_qubits, int n_tile
       op.t0 = (uint8_t)h.t0;
       op.t1 = (uint8_t)(h.t1 < 0 ? 0 : h.t1);
       op.moff = (uint16_t)h.moff;
+      op.foff = (uint16_t)h.foff;
       op.z0 = sw1(h.t0);
       op.z1 = h.t1 < 0 ? 0 : sw1(h.t1);
-      if (h.kind != QSV_GATE_DENSE2) continue;
+      op.z2 = h.t2 < 0 ? 0 : sw1(h.t2);
+      if (h.kind != QSV_GATE_DENSE2 && h.kind != kGateDense3) continue;
       // free inner bits of the gate: f0 with {f0,t0,t1} independent (STS.128: 2 groups x 4 amplitudes per
       // quarter warp), f1 with {f0,f1,t0} independent (LDS.64: 4 groups x 2 amplitudes per half warp)
       int fb[16], nf = 0;
       for (int i = 0; i < ni; i++)
-        if (ib[i] != h.t0 && ib[i] != h.t1) fb[nf++] = ib[i];
+        if (ib[i] != h.t0 && ib[i] != h.t1 && ib[i] != h.t2) fb[nf++] = ib[i];
       const int v0 = bvec(h.t0), v1 = bvec(h.t1);
       int f0 = -1, f1 = -1;
       for (int i = 0; i < nf && f0 < 0; i++)
@@ -881,28 +1119,27 @@ static int launch_pass(double* sv, int n, const int32_t* tile_qubits, int n_tile
   if (int rc = ensure_attrs()) return rc;
   size_t tile_slots = (size_t)1 << b;
   for (int j = 3; j < b; j++) tile_slots += pad_of_bit(j);
-  const size_t smem = tile_slots * sizeof(double2) + (size_t)n_gates * (64 * sizeof(double) + sizeof(OpRec) + 32 * 4) +
-                      (size_t)n_stages * ((kWarps + 32 + 8) * 4);
+  const size_t smem = tile_slots * sizeof(double2) + (size_t)nfrag * 64 * sizeof(double) +
+                      (size_t)n_gates * (sizeof(OpRec) + 32 * 4) + (size_t)n_stages * ((kWarps + 32 + 8) * 4);
   d.n_tiles = 1u << (n - b);
-  if (const char* e = getenv("QSV_DEBUG_FLAGS")) d.flags = (uint32_t)atoi(e);
   // one warp per 2^8 amplitudes: 512 threads for b = 12, 256 for b = 11, ...; at least one warp
   const int threads = std::max(32, std::min(kMaxPT, 1 << std::max(0, b - 3)));
   int per_sm = 1;
   if (threads >= 512) {
     QSV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tile_pass_kernel<512, 2>, threads, smem));
   } else if (threads >= 256) {
-    QSV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tile_pass_kernel<256, 5>, threads, smem));
+    QSV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tile_pass_kernel<256, 4>, threads, smem));
   } else {
-    QSV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tile_pass_kernel<128, 10>, threads, smem));
+    QSV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tile_pass_kernel<128, 8>, threads, smem));
   }
   if (per_sm < 1) return fail(QSV_ERANGE, "qsv_apply_pass: pass does not fit in shared memory");
   const unsigned grid = std::min<unsigned>(d.n_tiles, (unsigned)per_sm * (unsigned)sm_count());
   if (threads >= 512)
     tile_pass_kernel<512, 2><<<grid, threads, smem, stream>>>(reinterpret_cast<double2*>(sv), d);
   else if (threads >= 256)
-    tile_pass_kernel<256, 5><<<grid, threads, smem, stream>>>(reinterpret_cast<double2*>(sv), d);
+    tile_pass_kernel<256, 4><<<grid, threads, smem, stream>>>(reinterpret_cast<double2*>(sv), d);
   else
-    tile_pass_kernel<128, 10><<<grid, threads, smem, stream>>>(reinterpret_cast<double2*>(sv), d);
+    tile_pass_kernel<128, 8><<<grid, threads, smem, stream>>>(reinterpret_cast<double2*>(sv), d);
   QSV_LAUNCHED();
   return 0;
 }

@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Breakdown experiment: run the probe under QSV_DEBUG_FLAGS (1 no stores, 2 no loads, 4 no gates)."""
+"""Breakdown experiment: run the probe under QSV_DEBUG_FLAGS (1 no stores, 2 no loads, 4 no gates, 8 no pair
+fusion).  Usage: pass_probe2.py [n_qubits] [comma-separated flag values]."""
 import os, subprocess, sys
 n = sys.argv[1] if len(sys.argv) > 1 else "30"
 code = r'''
@@ -26,6 +27,6 @@ for k in (0, 2, 4, 8):
     out.append("%d gates %.3f ms" % (k, timeit(tile, ops)))
 print(os.environ.get("QSV_DEBUG_FLAGS", "0"), " | ".join(out))
 '''
-for flags in ("0", "1", "2", "3"):
+for flags in (sys.argv[2].split(",") if len(sys.argv) > 2 else ("0", "1", "2", "3")):
     env = dict(os.environ, QSV_DEBUG_FLAGS=flags)
     subprocess.run([sys.executable, "-c", code, n], env=env, check=True)
