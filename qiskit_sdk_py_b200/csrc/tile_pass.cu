@@ -65,9 +65,9 @@ struct PassDesc {
   int32_t nfrag;        // B-fragment units (64 doubles) of all ops: 1 per 2-qubit gate, 4 per fused block
   uint32_t n_tiles;
   uint32_t flags;       // QSV_DEBUG_FLAGS (profiling experiments)
-  uint32_t pb_ld;       // log2(amplitudes per bulk-load piece): contiguous low tile bits, at most 3 (128 B)
+  uint32_t pb_ld;       // log2(amplitudes per bulk-load piece): contiguous low tile bits, at most 4 (256 B)
   uint32_t pb_st;       // same for the write-back (smaller if the write-back permutes low bits)
-  uint8_t tb[16];       // physical bit of tile-local position j (positions 0..2 = the three lowest tile qubits)
+  uint8_t tb[16];       // physical bit of tile-local position j (positions 0..3 = the four lowest tile qubits)
   uint8_t tbs[16];      // the tile's physical bits in ascending order (tile base computation)
   uint16_t cj[16];      // shared-memory slot increment of tile-local bit j (see slot layout below)
   uint8_t src_of[16];   // write-back permutation: tile-local position j receives the content of bit src_of[j]
@@ -77,26 +77,28 @@ struct PassDesc {
 };
 
 // Shared-memory slot layout (16-byte slots; bank group = slot & 7).  Amplitude li of the tile lives at
-//     slot(li) = sum_j bit_j(li) * cj[j],   cj[j] = 2^j for j < 3,   cj[j] = 2^j + pad_j for j >= 3,
-// i.e. the 128-byte pieces (8 amplitudes, low three bits) stay contiguous -- they are moved by single
-// TMA bulk copies -- and padding slots are inserted between pieces.  pad_j is super-increasing
-// (1,2,4,9,18,36,73,146,292: pieces never overlap) with pad_j mod 8 = 2^(j mod 3), so bit j shifts the
-// bank group by 2^(j mod 3): any three index bits of pairwise different class j mod 3 spread over all 8
-// bank groups, which makes the accesses of a quarter warp (LDS/STS.128) or of a half warp reading
-// 8-byte halves (LDS.64) conflict-free.  The host orders the tile qubits so that the two bits of every
-// dense gate fall in different classes.  Every index map of the kernel is a sum of per-bit increments.
+//     slot(li) = sum_j bit_j(li) * cj[j],   cj[j] = 2^j for j < 4,   cj[j] = 2^j + pad_j for j >= 4,
+// i.e. the 256-byte pieces (16 amplitudes, low four bits) stay contiguous -- they are moved by single
+// TMA bulk copies, and the TMA request rate is what limits the copy phases, so pieces are as large as the
+// contiguous runs of the tile in HBM -- and padding slots are inserted between pieces.  pad_j is
+// super-increasing (1,2,4,9,18,36,73,146,292: pieces never overlap) with pad_j mod 8 = 2^((j-1) mod 3), so
+// bit j >= 4 shifts the bank group by 2^((j-1) mod 3) and bits 0,1,2 by 1,2,4: any three index bits of
+// pairwise different class spread over all 8 bank groups, which makes the accesses of a quarter warp
+// (LDS/STS.128) or of a half warp reading 8-byte halves (LDS.64) conflict-free.  Bit 3 has no class (it
+// moves by a whole 128-byte row): the host never lets it vary inside a wavefront of the dense paths when it
+// can avoid it, and orders the tile qubits so that the two bits of every dense gate fall in different
+// classes.  Every index map of the kernel is a sum of per-bit increments.
 __host__ __device__ __forceinline__ uint32_t pad_of_bit(int j) {
   switch (j) {
-    case 3: return 1;
-    case 4: return 2;
-    case 5: return 4;
-    case 6: return 9;
-    case 7: return 18;
-    case 8: return 36;
-    case 9: return 73;
-    case 10: return 146;
-    case 11: return 292;
-    case 12: return 585;
+    case 4: return 1;
+    case 5: return 2;
+    case 6: return 4;
+    case 7: return 9;
+    case 8: return 18;
+    case 9: return 36;
+    case 10: return 73;
+    case 11: return 146;
+    case 12: return 292;
     default: return 0;
   }
 }
@@ -165,7 +167,7 @@ struct __align__(16) OpRec {
 // while one CTA waits for HBM (TMA bulk load of its next tile, bulk write-back of the last) the others
 // run their gates, so the memory phases of one overlap the FP64 / shared-memory phases of the others.
 // A CTA owns a contiguous range of tiles.  The tile moves between HBM and shared memory with TMA bulk
-// copies of 128-byte pieces (one per thread), which bypass the LSU/L1TEX pipe that the gates saturate.
+// copies of 256-byte pieces (one per two threads), which bypass the LSU/L1TEX pipe that the gates saturate.
 __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const PassDesc& d) {
   // dynamic shared memory: the (padded) tile, then the per-pass tables (sized by the pass, so that short
   // passes leave room for more resident CTAs)
@@ -175,7 +177,7 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
   const int b = d.b;
   const uint32_t tile_amps = 1u << b;
   uint32_t tile_slots = tile_amps;
-  for (int j = 3; j < b; j++) tile_slots += pad_of_bit(j);
+  for (int j = 4; j < b; j++) tile_slots += pad_of_bit(j);
   double* frag = reinterpret_cast<double*>(tile + tile_slots);                  // [nfrag][64] B fragments
   OpRec* oprec = reinterpret_cast<OpRec*>(frag + (size_t)d.nfrag * 64);         // [nops]
   uint32_t (*opl)[32] = reinterpret_cast<uint32_t (*)[32]>(oprec + nops_all);   // [nops][32] lane slots
@@ -265,15 +267,22 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
   const uint32_t pb_ld = d.pb_ld, pb_st = d.pb_st;
   const uint32_t np_ld = tile_amps >> pb_ld, np_st = tile_amps >> pb_st;
   const uint32_t ld_bytes = 16u << pb_ld, st_bytes = 16u << pb_st;
-  uint32_t my_ld_bytes = 0;
-  for (uint32_t pc = tid; pc < np_ld; pc += kPT) my_ld_bytes += ld_bytes;
-  // the common case (128-byte pieces, one per thread) keeps its two offsets in registers
+  // With fewer pieces than threads (256-byte pieces: every second thread) the issuing threads are spread
+  // evenly over the warps, because a warp issues its bulk copies one lane at a time.
+  const uint32_t sh_ld = np_ld < kPT ? (uint32_t)__ffs((int)(kPT / np_ld)) - 1u : 0u;
+  const uint32_t sh_st = np_st < kPT ? (uint32_t)__ffs((int)(kPT / np_st)) - 1u : 0u;
+  const uint32_t pc_ld0 = tid >> sh_ld, pc_st0 = tid >> sh_st;
+  const bool own_ld = (tid & ((1u << sh_ld) - 1u)) == 0u && pc_ld0 < np_ld;
+  const bool own_st = (tid & ((1u << sh_st) - 1u)) == 0u && pc_st0 < np_st;
+  uint32_t my_ld_bytes = own_ld ? ld_bytes : 0u;
+  for (uint32_t pc = tid + kPT; pc < np_ld; pc += kPT) my_ld_bytes += ld_bytes;
+  // the common case (at most one piece per thread) keeps its two offsets in registers
   u64 g_ld0 = 0, g_st0 = 0;
   uint32_t s_ld0 = 0, s_st0 = 0;
   for (int j = 0; j + (int)pb_ld < b; j++)
-    if ((tid >> j) & 1u) { g_ld0 |= 1ull << d.tb[pb_ld + j]; s_ld0 += d.cj[pb_ld + j]; }
+    if ((pc_ld0 >> j) & 1u) { g_ld0 |= 1ull << d.tb[pb_ld + j]; s_ld0 += d.cj[pb_ld + j]; }
   for (int j = 0; j + (int)pb_st < b; j++)
-    if ((tid >> j) & 1u) { g_st0 |= 1ull << d.tb[pb_st + j]; s_st0 += d.cj[d.src_of[pb_st + j]]; }
+    if ((pc_st0 >> j) & 1u) { g_st0 |= 1ull << d.tb[pb_st + j]; s_st0 += d.cj[d.src_of[pb_st + j]]; }
   const bool ld_on = !(dbg & 2u), st_on = !(dbg & 1u);
   const uint32_t lane = tid & 31u, wid = tid >> 5;
   const uint32_t g = lane >> 2;
@@ -296,7 +305,7 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
     }
     if (ld_on) {
       mbar_arrive_expect_tx(&ld_bar, my_ld_bytes);
-      if (tid < np_ld) bulk_load(tile + s_ld0, sv + base + g_ld0, ld_bytes, &ld_bar);
+      if (own_ld) bulk_load(tile + s_ld0, sv + base + g_ld0, ld_bytes, &ld_bar);
       for (uint32_t pc = tid + kPT; pc < np_ld; pc += kPT) {  // small pieces only (tile without the low qubits)
         u64 go = 0;
         uint32_t so = 0;
@@ -511,7 +520,7 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
     fence_proxy_async();  // the gates' generic-proxy stores must be visible to the async proxy
     __syncthreads();
     if (st_on) {
-      if (tid < np_st) bulk_store(sv + base + g_st0, tile + s_st0, st_bytes);
+      if (own_st) bulk_store(sv + base + g_st0, tile + s_st0, st_bytes);
       for (uint32_t pc = tid + kPT; pc < np_st; pc += kPT) {
         u64 go = 0;
         uint32_t so = 0;
@@ -676,10 +685,23 @@ static void cmat_mul(const double* a, const double* b, int dim, double* out) {
 }
 
 // bank class of a tile-local bit: it shifts the bank group by 2^(j mod 3) (see the slot layout)
-static inline int bank_class(int bit) { return bit % 3; }
+static inline int bank_class(int bit) { return bit < 3 ? bit : bit == 3 ? -1 : (bit - 1) % 3; }
+static inline bool differ(int a, int b) { return a >= 0 && b >= 0 && a != b; }
 static inline bool independent3(int a, int b, int c) {
-  // three bits spread over all 8 bank groups iff their classes are pairwise different
-  return a != b && a != c && b != c;
+  // three bits spread over all 8 bank groups iff their classes are pairwise different (bit 3 has none)
+  return differ(a, b) && differ(a, c) && differ(b, c);
+}
+
+// swap the two index bits of a 4x4 complex matrix (roles of a 2-qubit gate's qubits exchanged)
+static void swap_gate_bits(double* m) {
+  double t[32];
+  memcpy(t, m, sizeof(t));
+  static const int sw[4] = {0, 2, 1, 3};
+  for (int r = 0; r < 4; r++)
+    for (int c = 0; c < 4; c++) {
+      m[2 * (4 * r + c)] = t[2 * (4 * sw[r] + sw[c])];
+      m[2 * (4 * r + c) + 1] = t[2 * (4 * sw[r] + sw[c]) + 1];
+    }
 }
 
 static inline int popc(uint32_t x) { return __builtin_popcount(x); }
@@ -777,12 +799,12 @@ static int launch_pass(double* sv, int n, const int32_t* tile_qubits, int n_tile
     if (sorted[j] == sorted[j + 1]) return fail(QSV_EINVAL, "qsv_apply_pass: duplicate tile qubit");
   for (int j = 0; j < b; j++) d.tbs[j] = (uint8_t)sorted[j];
 
-  // ---- tile-local positions: 0..2 = the three lowest tile qubits (they form the contiguous 128-byte
-  // pieces when they are physical qubits 0,1,2); the others are placed so that the two qubits of every
-  // dense gate get different bank classes (position mod 3) ----
+  // ---- tile-local positions: 0..3 = the four lowest tile qubits (they form the contiguous 256-byte
+  // pieces when they are physical qubits 0..3); the others are placed so that the two qubits of every
+  // dense gate get different bank classes ----
   int pos_phys[16];
   {
-    const int n_fixed = std::min(b, 3);
+    const int n_fixed = std::min(b, 4);
     int cls_of[64];
     for (int q = 0; q < 64; q++) cls_of[q] = -1;
     for (int j = 0; j < n_fixed; j++) {
@@ -833,9 +855,9 @@ static int launch_pass(double* sv, int n, const int32_t* tile_qubits, int n_tile
     local_of[pos_phys[j]] = j;
     d.cj[j] = (uint16_t)((1u << j) + pad_of_bit(j));
   }
-  // bulk-copy piece size: the leading tile positions that are physical qubits 0,1,2 (contiguous in HBM)
+  // bulk-copy piece size: the leading tile positions that are physical qubits 0..3 (contiguous in HBM)
   int pb = 0;
-  while (pb < 3 && pb < b && pos_phys[pb] == pb) pb++;
+  while (pb < 4 && pb < b && pos_phys[pb] == pb) pb++;
   d.pb_ld = (uint32_t)pb;
   d.pb_st = (uint32_t)pb;
   // write-back permutation: content of tile_qubits[i] goes to dest_qubits[i]
@@ -970,7 +992,7 @@ static int launch_pass(double* sv, int n, const int32_t* tile_qubits, int n_tile
       bool found = false;
       for (int a = 0; a < 3 && !found; a++)
         for (int c = 0; c < 3 && !found; c++)
-          if (a != c && bank_class(ub[a]) != bank_class(ub[c])) {
+          if (a != c && differ(bank_class(ub[a]), bank_class(ub[c]))) {
             role[0] = a; role[1] = c; role[2] = 3 - a - c;
             found = true;
           }
@@ -1017,7 +1039,9 @@ static int launch_pass(double* sv, int n, const int32_t* tile_qubits, int n_tile
       const uint32_t inner = inner_masks[stage_of[k]];
       int partner = -1;
       for (int j = 0; j < b && partner < 0; j++)
-        if (((inner >> j) & 1u) && j != op.t0 && bank_class(j) != bank_class(op.t0)) partner = j;
+        if (((inner >> j) & 1u) && j != op.t0 && differ(bank_class(j), bank_class(op.t0))) partner = j;
+      for (int j = 0; j < b && partner < 0; j++)
+        if (((inner >> j) & 1u) && j != op.t0 && bank_class(j) >= 0) partner = j;
       for (int j = 0; j < b && partner < 0; j++)
         if (((inner >> j) & 1u) && j != op.t0) partner = j;
       double m2[8];
@@ -1031,6 +1055,11 @@ static int launch_pass(double* sv, int n, const int32_t* tile_qubits, int n_tile
         }
       op.kind = QSV_GATE_DENSE2;
       op.t1 = partner;
+    }
+    // the lane-varying gate bit (t0) should have a bank class: bit 3 takes the other role
+    if (op.kind == QSV_GATE_DENSE2 && bank_class(op.t0) < 0 && bank_class(op.t1) >= 0) {
+      swap_gate_bits(mats + op.moff);
+      std::swap(op.t0, op.t1);
     }
   }
   memcpy(d.mats, mats, sizeof(double) * moff);
@@ -1102,7 +1131,9 @@ static int launch_pass(double* sv, int n, const int32_t* tile_qubits, int n_tile
       for (int i = 0; i < nf && f0 < 0; i++)
         if (independent3(bvec(fb[i]), v0, v1)) f0 = fb[i];
       for (int i = 0; i < nf && f0 < 0; i++)
-        if (bvec(fb[i]) != v0) f0 = fb[i];
+        if (differ(bvec(fb[i]), v0)) f0 = fb[i];
+      for (int i = 0; i < nf && f0 < 0; i++)
+        if (bvec(fb[i]) >= 0) f0 = fb[i];
       if (f0 >= 0)
         for (int i = 0; i < nf && f1 < 0; i++)
           if (fb[i] != f0 && independent3(bvec(f0), bvec(fb[i]), v0)) f1 = fb[i];
@@ -1118,7 +1149,7 @@ static int launch_pass(double* sv, int n, const int32_t* tile_qubits, int n_tile
 
   if (int rc = ensure_attrs()) return rc;
   size_t tile_slots = (size_t)1 << b;
-  for (int j = 3; j < b; j++) tile_slots += pad_of_bit(j);
+  for (int j = 4; j < b; j++) tile_slots += pad_of_bit(j);
   const size_t smem = tile_slots * sizeof(double2) + (size_t)nfrag * 64 * sizeof(double) +
                       (size_t)n_gates * (sizeof(OpRec) + 32 * 4) + (size_t)n_stages * ((kWarps + 32 + 8) * 4);
   d.n_tiles = 1u << (n - b);
