@@ -82,7 +82,7 @@ int qsv_scale(double* sv, int n_qubits, double re, double im, void* stream);
 /* One cache-blocked pass: every CTA stages the 2^n_tile amplitudes spanned by `tile_qubits` in shared
  * memory (one HBM read), applies `gates` in order there, and writes the tile back (one HBM write).
  * All gate qubits must be in tile_qubits; n_tile <= min(n_qubits, QSV_MAX_TILE_QUBITS).  For full
- * memory coalescing tile_qubits should contain qubits 0,1,2 (128-byte runs).  Replaces a RUN of
+ * memory coalescing tile_qubits should contain qubits 0..3 (256-byte runs = one TMA bulk copy each).  Replaces a RUN of
  * consecutive _add_unitary calls (qasm_simulator.py:145-161, loop :526-559), each of which is one
  * np.einsum pass over the whole vector in the reference. */
 int qsv_apply_pass(double* sv, int n_qubits, const int32_t* tile_qubits, int n_tile,
@@ -95,6 +95,16 @@ int qsv_apply_pass(double* sv, int n_qubits, const int32_t* tile_qubits, int n_t
  * read-out.  (New: the reference never moves qubits; its einsum addresses them in place.) */
 int qsv_apply_pass_remap(double* sv, int n_qubits, const int32_t* tile_qubits, int n_tile,
                          const qsv_gate_t* gates, int n_gates, const int32_t* dest_qubits, void* stream);
+
+/* Host-only introspection of the lowering qsv_apply_pass[_remap] would do for these arguments (no GPU is
+ * touched, nothing is launched): info[0] = kernel ops after gate fusion (2-qubit gates that share a qubit
+ * are merged into 3-qubit blocks), info[1] = stages (block-wide barriers + 1), info[2] = fused 3-qubit
+ * blocks, info[3] = dynamic shared memory (bytes), info[4] = threads per CTA, info[5] / info[6] = log2 of
+ * the amplitudes per TMA bulk-copy piece of the load / the write-back, info[7] = gates passed in.
+ * Same argument validation and error codes as qsv_apply_pass_remap.  (New: planning aid and CPU-side test
+ * hook; no reference counterpart.) */
+int qsv_pass_info(int n_qubits, const int32_t* tile_qubits, int n_tile, const qsv_gate_t* gates,
+                  int n_gates, const int32_t* dest_qubits, int32_t* info);
 
 /* psi <- (G on qubits) psi for a dense k-qubit matrix, k >= 1.  Replaces one _add_unitary call
  * (qasm_simulator.py:145-161; `unitary` instruction :543-546).  k <= 2 goes through qsv_apply_pass;

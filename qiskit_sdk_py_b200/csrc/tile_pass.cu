@@ -284,6 +284,10 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
   for (int j = 0; j + (int)pb_st < b; j++)
     if ((pc_st0 >> j) & 1u) { g_st0 |= 1ull << d.tb[pb_st + j]; s_st0 += d.cj[d.src_of[pb_st + j]]; }
   const bool ld_on = !(dbg & 2u), st_on = !(dbg & 1u);
+  // L2 prefetch of the next tile: every thread covers its share of one load piece
+  const uint32_t pf_bytes = (ld_bytes >> sh_ld) ? (ld_bytes >> sh_ld) : ld_bytes;
+  const uint32_t pf_off = (tid & ((1u << sh_ld) - 1u)) * (ld_bytes >> sh_ld);
+  const bool pf_on = !(dbg & 32u) && pc_ld0 < np_ld && (ld_bytes >> sh_ld) != 0u;
   const uint32_t lane = tid & 31u, wid = tid >> 5;
   const uint32_t g = lane >> 2;
   const char* tb8 = reinterpret_cast<const char*>(tile) + (lane & 1u) * 8u;
@@ -318,6 +322,14 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
       if (wid == 0) mbar_wait(&ld_bar, parity);
       parity ^= 1u;
       __syncthreads();
+      // pull the next tile of this CTA into L2 while the gates run, so that its bulk load sees L2 latency
+      // instead of HBM latency (the CTA has a single tile buffer, the load cannot start earlier)
+      if (pf_on && t + 1 < t_end) {
+        const u64 nb = ((base | tile_mask) + 1) & ~tile_mask;
+        const char* pa = reinterpret_cast<const char*>(sv + nb + g_ld0) + pf_off;
+        for (uint32_t o2 = 0; o2 < pf_bytes; o2 += 128u)
+          asm volatile("prefetch.global.L2 [%0];\n" ::"l"(pa + o2));
+      }
     }
 
     int o = 0;
@@ -776,15 +788,21 @@ static int ensure_attrs() {
   return 0;
 }
 
-static int launch_pass(double* sv, int n, const int32_t* tile_qubits, int n_tile, const qsv_gate_t* gates,
-                       int n_gates, cudaStream_t stream, const int32_t* dest_qubits = nullptr) {
-  if (!sv || n < 1 || n > 40) return fail(QSV_EINVAL, "qsv_apply_pass: bad state / n_qubits");
+struct PassPlan {
+  size_t smem;
+  int threads, n_in, n_fused3;
+};
+
+// Host-only lowering of a pass (no CUDA call): validates the arguments, fuses gates, builds the stages and
+// every index table of the kernel into `d`.
+static int lower_pass(PassDesc& d, PassPlan& plan, int n, const int32_t* tile_qubits, int n_tile,
+                      const qsv_gate_t* gates, int n_gates, const int32_t* dest_qubits) {
+  if (n < 1 || n > 40) return fail(QSV_EINVAL, "qsv_apply_pass: bad state / n_qubits");
   if (n_tile < 1 || n_tile > QSV_MAX_TILE_QUBITS || n_tile > n)
     return fail(QSV_ERANGE, "qsv_apply_pass: n_tile must be in [1, min(n_qubits, 12)]");
   if (n_gates < 0 || n_gates > kMaxOps) return fail(QSV_ERANGE, "qsv_apply_pass: too many gates");
   if (n - n_tile > 31) return fail(QSV_ERANGE, "qsv_apply_pass: grid too large");
 
-  static thread_local PassDesc d;
   memset(&d, 0, sizeof(d));
   const int b = n_tile;
   d.n = n;
@@ -1147,14 +1165,29 @@ static int launch_pass(double* sv, int n, const int32_t* tile_qubits, int n_tile
     }
   }
 
-  if (int rc = ensure_attrs()) return rc;
   size_t tile_slots = (size_t)1 << b;
   for (int j = 4; j < b; j++) tile_slots += pad_of_bit(j);
   const size_t smem = tile_slots * sizeof(double2) + (size_t)nfrag * 64 * sizeof(double) +
                       (size_t)n_gates * (sizeof(OpRec) + 32 * 4) + (size_t)n_stages * ((kWarps + 32 + 8) * 4);
   d.n_tiles = 1u << (n - b);
   // one warp per 2^8 amplitudes: 512 threads for b = 12, 256 for b = 11, ...; at least one warp
-  const int threads = std::max(32, std::min(kMaxPT, 1 << std::max(0, b - 3)));
+  plan.smem = smem;
+  plan.threads = std::max(32, std::min(kMaxPT, 1 << std::max(0, b - 3)));
+  plan.n_in = n_in;
+  plan.n_fused3 = 0;
+  for (int k = 0; k < n_gates; k++) plan.n_fused3 += d.ops[k].kind == kGateDense3;
+  return 0;
+}
+
+static int launch_pass(double* sv, int n, const int32_t* tile_qubits, int n_tile, const qsv_gate_t* gates,
+                       int n_gates, cudaStream_t stream, const int32_t* dest_qubits = nullptr) {
+  if (!sv) return fail(QSV_EINVAL, "qsv_apply_pass: bad state / n_qubits");
+  static thread_local PassDesc d;
+  PassPlan plan;
+  if (int rc = lower_pass(d, plan, n, tile_qubits, n_tile, gates, n_gates, dest_qubits)) return rc;
+  if (int rc = ensure_attrs()) return rc;
+  const size_t smem = plan.smem;
+  const int threads = plan.threads;
   int per_sm = 1;
   if (threads >= 512) {
     QSV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tile_pass_kernel<512, 2>, threads, smem));
@@ -1259,6 +1292,23 @@ int qsv_apply_pass(double* sv, int n, const int32_t* tile_qubits, int n_tile, co
                    int n_gates, void* stream) {
   if (!tile_qubits || (n_gates > 0 && !gates)) return fail(QSV_EINVAL, "qsv_apply_pass: null pointer");
   return launch_pass(sv, n, tile_qubits, n_tile, gates, n_gates, (cudaStream_t)stream);
+}
+
+int qsv_pass_info(int n, const int32_t* tile_qubits, int n_tile, const qsv_gate_t* gates, int n_gates,
+                  const int32_t* dest_qubits, int32_t* info) {
+  if (!tile_qubits || !info || (n_gates > 0 && !gates)) return fail(QSV_EINVAL, "qsv_pass_info: null pointer");
+  static thread_local PassDesc d;
+  PassPlan plan;
+  if (int rc = lower_pass(d, plan, n, tile_qubits, n_tile, gates, n_gates, dest_qubits)) return rc;
+  info[0] = d.nops;
+  info[1] = d.nstages;
+  info[2] = plan.n_fused3;
+  info[3] = (int32_t)plan.smem;
+  info[4] = plan.threads;
+  info[5] = (int32_t)d.pb_ld;
+  info[6] = (int32_t)d.pb_st;
+  info[7] = plan.n_in;
+  return 0;
 }
 
 int qsv_apply_pass_remap(double* sv, int n, const int32_t* tile_qubits, int n_tile, const qsv_gate_t* gates,

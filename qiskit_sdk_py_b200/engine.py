@@ -117,6 +117,20 @@ class DeviceState:
         self.passes_launched += 1
         self.gates_applied += len(ops)
 
+    @staticmethod
+    def pass_info(n_qubits, tile_qubits, ops, dest=None):
+        """Host-only: how qsv_apply_pass would lower this pass (no GPU needed).  Returns a dict with the
+        kernel ops after gate fusion, stages, fused 3-qubit blocks, shared memory, threads, copy piece sizes."""
+        lib = _lib.load()
+        gates = (_lib.QsvGate * max(1, len(ops)))()
+        for i, op in enumerate(ops):
+            _fill_gate(gates[i], op)
+        info = (ctypes.c_int32 * 8)()
+        _lib.check(lib.qsv_pass_info(n_qubits, _int32_array(tile_qubits), len(tile_qubits), gates, len(ops),
+                                     None if dest is None else _int32_array(dest), info), "qsv_pass_info")
+        keys = ("ops", "stages", "fused3", "smem_bytes", "threads", "piece_log2_load", "piece_log2_store", "gates")
+        return dict(zip(keys, list(info)))
+
     def apply_dense(self, qubits, matrix):
         """One stand-alone k-qubit gate (the `unitary` instruction with k >= 3)."""
         k = len(qubits)

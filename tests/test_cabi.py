@@ -67,3 +67,71 @@ def test_engine_does_not_import_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert "import oracle" not in src and "from oracle" not in src, fn
+
+
+def _unitary(rng, k):
+    import numpy as np
+
+    z = rng.standard_normal((2 ** k, 2 ** k)) + 1j * rng.standard_normal((2 ** k, 2 ** k))
+    q, r = np.linalg.qr(z)
+    return q * (np.diag(r) / np.abs(np.diag(r)))
+
+
+def test_pass_lowering_is_host_only_and_fuses_gate_pairs():
+    """qsv_pass_info runs the host lowering of a pass without a GPU: 2-qubit gates that share a qubit are
+    merged into 3-qubit blocks (one shared-memory round trip for two gates), gates on the same pair are
+    multiplied together, and gates fenced off by an intermediate gate stay separate."""
+    import numpy as np
+
+    from qiskit_sdk_py_b200.engine import DeviceState
+    from qiskit_sdk_py_b200.lower import GateOp
+
+    rng = np.random.RandomState(1)
+    tile = list(range(11))
+    dense = lambda a, b: GateOp(_lib.GATE_DENSE2, [a, b], _unitary(rng, 2))
+    # chain (4,5),(5,6): one block
+    info = DeviceState.pass_info(20, tile, [dense(4, 5), dense(5, 6)])
+    assert (info["gates"], info["ops"], info["fused3"]) == (2, 1, 1)
+    # same pair twice: one 2-qubit op, no block
+    info = DeviceState.pass_info(20, tile, [dense(4, 5), dense(5, 4)])
+    assert (info["ops"], info["fused3"]) == (1, 0)
+    # (4,5) (6,7) (5,6): (5,6) cannot be hoisted over (6,7) to join (4,5), but it can join (6,7)
+    info = DeviceState.pass_info(20, tile, [dense(4, 5), dense(6, 7), dense(5, 6)])
+    assert (info["ops"], info["fused3"]) == (2, 1)
+    # a third gate inside the block's bits is absorbed
+    info = DeviceState.pass_info(20, tile, [dense(4, 5), dense(5, 6), dense(4, 6)])
+    assert (info["ops"], info["fused3"]) == (1, 1)
+    # disjoint gates are never merged (that would double the FP64 work)
+    info = DeviceState.pass_info(20, tile, [dense(4, 5), dense(6, 7), dense(8, 9)])
+    assert (info["ops"], info["fused3"], info["stages"]) == (3, 0, 1)
+    # copy pieces: 256 bytes (16 amplitudes) when the tile holds qubits 0..3, smaller otherwise
+    assert info["piece_log2_load"] == 4 and info["piece_log2_store"] == 4 and info["threads"] == 256
+    assert DeviceState.pass_info(20, [0, 1, 2, 9, 10, 11, 12, 13], [])["piece_log2_load"] == 3
+    assert DeviceState.pass_info(20, [5, 6, 7, 8], [])["piece_log2_load"] == 0
+    # remapped write-back keeps only the unpermuted leading bits in one piece
+    info = DeviceState.pass_info(20, tile, [], dest=[0, 1, 3, 2] + list(range(4, 11)))
+    assert info["piece_log2_store"] == 2
+    # argument errors are the same as qsv_apply_pass's
+    with pytest.raises(_lib.QsvLibraryError, match="not a tile qubit"):
+        DeviceState.pass_info(20, tile, [dense(4, 15)])
+
+
+def test_quantum_volume_pass_statistics():
+    """QuantumVolume(33) through planner + lowering, all on the host: about three quarters of the SU(4) gates
+    end up in fused blocks and a pass needs fewer than 1.5 stages on average."""
+    from qiskit_sdk_py_b200 import circuits, lower, planner
+    from qiskit_sdk_py_b200.engine import DeviceState
+
+    n = 33
+    qobj = circuits.quantum_volume(n, measure_final=False, shots=1)
+    ops = [lower.lower_gate(i["name"], i["qubits"], i.get("params", [])) for i in qobj["experiments"][0]["instructions"]]
+    passes = planner.plan_passes(ops, n)
+    tot = {"gates": 0, "ops": 0, "fused3": 0, "stages": 0}
+    for p in passes:
+        info = DeviceState.pass_info(n, p.tile_qubits, p.ops)
+        for key in tot:
+            tot[key] += info[key]
+        assert info["smem_bytes"] < 56 * 1024  # four CTAs per SM
+    assert tot["gates"] == 528
+    assert tot["gates"] - tot["ops"] >= 0.35 * tot["gates"]
+    assert tot["stages"] <= 1.5 * len(passes)
