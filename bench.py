@@ -44,7 +44,7 @@ SIM_SEED = 42
 REF_QUBITS = 24          # reference cap (qasm_simulator.py:64)
 REF_GATES_PER_STEP = 6   # bounded sample per reference step (~0.4 s per gate at n=24)
 FP64_DMMA_PEAK_TFLOPS = 37.0      # measured: tools/fp64_peak.cu on B200 (DMMA.8x8x4), profiles/r1_fp64_peak_dfma_vs_dmma.txt
-TRAFFIC_BYTES_PER_AMP = 31.79     # measured DRAM bytes per amplitude per pass (ncu, n=28)
+TRAFFIC_BYTES_PER_AMP = 32.38     # measured DRAM bytes per amplitude per pass (ncu, n=28)
 
 
 def measured_peaks():
@@ -159,7 +159,7 @@ def reference_arm(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 def cpu_baseline_leg(seconds_budget=20.0):
@@ -212,6 +212,13 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
+
+    # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on
+    # fd 1), so fd 1 is pointed at stderr for the whole run and the JSON line goes to the saved real stdout.
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
 
     if args.impl == "reference":
         reference_arm(args)
@@ -330,8 +337,8 @@ def main():
         "roofline": {
             "bound": "hbm", "kernel": "tile_pass_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": achieved / peak, "traffic": TRAFFIC_BYTES_PER_AMP * 2 ** n, "peak_source": peak_src,
-            "traffic_source": "ncu --set full at n=28: dram__bytes_read 4.296 GB + write 4.237 GB per launch = "
-                              "31.8 B/amplitude (profiles/r1_tile_pass_kernel_ncu_full_summary.txt), scaled to 2^n",
+            "traffic_source": "ncu --set full at n=28: dram__bytes_read 4.446 GB + write 4.246 GB per launch = "
+                              "32.4 B/amplitude (profiles/r1_tile_pass_kernel_ncu_full_summary.txt), scaled to 2^n",
             "algorithmic_bytes_per_launch": bytes_per_gate_pass, "launch_ms": per_launch_ms,
             "launches_per_step": len(passes), "pass_section_ms": pass_ms,
             # the fused pass is FP64-bound, not HBM-bound: the same launches against the measured DMMA peak
@@ -347,7 +354,7 @@ def main():
         "clocks": clock_info,
         "check": {"sample_total_prob": total, "max_bin_mod4096": counts_top},
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":

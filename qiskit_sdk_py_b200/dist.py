@@ -495,5 +495,5 @@ def bench_main(args, metric, unit, measured_peaks, clock_sampler_cls):
             "clocks": clock_info,
             "check": {"sample_total_prob": total},
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     dist.destroy_process_group()

@@ -27,12 +27,13 @@ class Pass:
     at the start of the pass; ``dest`` (or None) says where each tile qubit's content lands on
     write-back (``dest[i]`` for ``tile_qubits[i]``)."""
 
-    __slots__ = ("tile_qubits", "ops", "dest")
+    __slots__ = ("tile_qubits", "ops", "dest", "op_indices")
 
-    def __init__(self, tile_qubits, ops, dest=None):
+    def __init__(self, tile_qubits, ops, dest=None, op_indices=None):
         self.tile_qubits = tuple(tile_qubits)
         self.ops = list(ops)
         self.dest = None if dest is None else tuple(dest)
+        self.op_indices = None if op_indices is None else list(op_indices)  # positions in plan_passes' input
 
     def __repr__(self):
         return "Pass(tile=%r, %d ops%s)" % (self.tile_qubits, len(self.ops), ", remap" if self.dest else "")
@@ -86,6 +87,7 @@ def plan_passes(ops, n_qubits, tile_qubits=DEFAULT_TILE_QUBITS, max_gates=_lib.M
         low_log = [inv[ph] for ph in range(n_low)]  # logical qubits sitting in the pinned low bits
         used = set(low_log)
         chosen = []
+        chosen_idx = []
         payload = 0
         while len(chosen) < max_gates:
             best, best_cost = None, 99
@@ -101,6 +103,7 @@ def plan_passes(ops, n_qubits, tile_qubits=DEFAULT_TILE_QUBITS, max_gates=_lib.M
             op = ops[best]
             frontier.discard(best)
             chosen.append(op)
+            chosen_idx.append(best)
             used.update(op.qubits)
             payload += op.payload_doubles
             n_left -= 1
@@ -134,7 +137,7 @@ def plan_passes(ops, n_qubits, tile_qubits=DEFAULT_TILE_QUBITS, max_gates=_lib.M
                 new_pos[qi], new_pos[qe] = layout[qe], layout[qi]
             if incoming:
                 dest = [new_pos[q] for q in tile_log]
-        passes.append(Pass(tile_phys, [_relabel(op, layout) for op in chosen], dest))
+        passes.append(Pass(tile_phys, [_relabel(op, layout) for op in chosen], dest, chosen_idx))
         if dest is not None:
             for q, d in zip(tile_log, dest):
                 layout[q] = d

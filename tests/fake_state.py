@@ -57,13 +57,17 @@ class FakeState:
         if not run:
             return
         for p in plan_passes(run, self.n, self.tile_qubits):
-            assert len(p.tile_qubits) == min(self.n, self.tile_qubits)
-            for op in p.ops:
-                assert set(op.qubits) <= set(p.tile_qubits)
-                self._apply(op)
-            self.passes_launched += 1
-            self.gates_applied += len(p.ops)
+            self.apply_pass(p.tile_qubits, p.ops)
             self.pass_log.append(p)
+
+    def apply_pass(self, tile_qubits, ops, dest=None):
+        assert dest is None
+        assert len(tile_qubits) == min(self.n, self.tile_qubits) and len(set(tile_qubits)) == len(tile_qubits)
+        for op in ops:
+            assert set(op.qubits) <= set(tile_qubits)
+            self._apply(op)
+        self.passes_launched += 1
+        self.gates_applied += len(ops)
 
     def prob_qubit(self, qubit):
         p = np.abs(self.vec) ** 2
