@@ -11,7 +11,7 @@ import numpy as np
 
 from . import _lib
 from .lower import GateOp
-from .planner import DEFAULT_TILE_QUBITS, plan_passes
+from .planner import DEFAULT_TILE_QUBITS, merge_ops, plan_passes
 
 _p_int32 = ctypes.POINTER(ctypes.c_int32)
 
@@ -167,7 +167,7 @@ class DeviceState:
     def _flush(self, run):
         if not run:
             return
-        for p in plan_passes(run, self.n, self.tile_qubits):
+        for p in plan_passes(merge_ops(run), self.n, self.tile_qubits):
             self.apply_pass(p.tile_qubits, p.ops)
 
     # -- measurement -----------------------------------------------------------------

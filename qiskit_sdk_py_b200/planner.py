@@ -15,8 +15,10 @@ program order, the set of gates for each pass:
 
 Pure host logic, no device access: unit-tested on CPU.
 """
+import numpy as np
+
 from . import _lib
-from .lower import GateOp
+from .lower import GateOp, matrix_op
 
 DEFAULT_TILE_QUBITS = 11
 LOW_QUBITS = 4  # 16 amplitudes = 256 B contiguous runs (measured: 128 B runs 4.06 TB/s, 256 B 5.03, contiguous 5.27)
@@ -27,16 +29,78 @@ class Pass:
     at the start of the pass; ``dest`` (or None) says where each tile qubit's content lands on
     write-back (``dest[i]`` for ``tile_qubits[i]``)."""
 
-    __slots__ = ("tile_qubits", "ops", "dest", "op_indices")
+    __slots__ = ("tile_qubits", "ops", "dest")
 
-    def __init__(self, tile_qubits, ops, dest=None, op_indices=None):
+    def __init__(self, tile_qubits, ops, dest=None):
         self.tile_qubits = tuple(tile_qubits)
         self.ops = list(ops)
         self.dest = None if dest is None else tuple(dest)
-        self.op_indices = None if op_indices is None else list(op_indices)  # positions in plan_passes' input
 
     def __repr__(self):
         return "Pass(tile=%r, %d ops%s)" % (self.tile_qubits, len(self.ops), ", remap" if self.dest else "")
+
+
+_CX = np.array([[1, 0, 0, 0], [0, 0, 0, 1], [0, 0, 1, 0], [0, 1, 0, 0]], dtype=complex)  # basicaertools.py:70-72
+
+
+def _dense(op):
+    """The op as a dense matrix in its own qubit order (qubits[0] = LSB of the index)."""
+    if op.kind in (_lib.GATE_DIAG1, _lib.GATE_DIAG2):
+        return np.diag(np.asarray(op.matrix, dtype=complex))
+    if op.kind == _lib.GATE_CX:
+        return _CX
+    return np.asarray(op.matrix, dtype=complex)
+
+
+def _embed(mat, qubits, support):
+    """``mat`` on ``qubits`` as a matrix on ``support`` (1 or 2 qubits, support[0] = LSB)."""
+    qubits, support = tuple(qubits), tuple(support)
+    if qubits == support:
+        return mat
+    if len(qubits) == 2:  # same pair, roles exchanged: swap the two index bits
+        perm = [0, 2, 1, 3]
+        return mat[np.ix_(perm, perm)]
+    eye = np.eye(2, dtype=complex)
+    return np.kron(eye, mat) if support.index(qubits[0]) == 0 else np.kron(mat, eye)
+
+
+def merge_ops(ops):
+    """Peephole fusion on the host: a gate is multiplied into the latest earlier gate when together they act
+    on at most two qubits and no gate in between touches those qubits.  A controlled-phase written in the
+    simulator basis (u1 a; cx a,b; u1 b; cx a,b; u1 b -- five passes over the tile in shared memory, and five
+    einsum passes over the whole vector in the reference, qasm_simulator.py:145-161) becomes ONE diagonal
+    2-qubit op; runs of 1-qubit gates collapse; a 1-qubit gate next to a 2-qubit gate on its qubit is free.
+    The product is re-classified (diagonal / dense), so exact zeros keep diagonal gates on the cheap path.
+    Ops that merge with nothing are passed through untouched (same objects)."""
+    out = []    # [support, matrix or None (= untouched original), original op]
+    last = {}   # qubit -> index in ``out`` of the latest op touching it
+    for op in ops:
+        qs = tuple(op.qubits)
+        if op.kind == "densek" or len(qs) > 2:
+            for q in qs:
+                last[q] = len(out)
+            out.append([qs, None, op])
+            continue
+        k = max((last.get(q, -1) for q in qs), default=-1)
+        target = out[k] if k >= 0 else None
+        if target is not None and target[2].kind != "densek" and len(target[0]) <= 2:
+            # k is the latest op on ANY qubit of the incoming gate, so nothing after position k touches the
+            # gate's qubits: it commutes back to position k, where it multiplies the target
+            union = target[0] + tuple(q for q in qs if q not in target[0])
+            if len(union) <= 2:
+                prev = target[1] if target[1] is not None else _dense(target[2])
+                mat = _embed(_dense(op), qs, union) @ _embed(prev, target[0], union)
+                target[0], target[1] = union, mat
+                for q in qs:
+                    last[q] = k
+                continue
+        for q in qs:
+            last[q] = len(out)
+        out.append([qs, None, op])
+    merged = []
+    for support, mat, op in out:
+        merged.append(op if mat is None else matrix_op(mat, support))
+    return merged
 
 
 def _relabel(op, layout):
@@ -87,7 +151,6 @@ def plan_passes(ops, n_qubits, tile_qubits=DEFAULT_TILE_QUBITS, max_gates=_lib.M
         low_log = [inv[ph] for ph in range(n_low)]  # logical qubits sitting in the pinned low bits
         used = set(low_log)
         chosen = []
-        chosen_idx = []
         payload = 0
         while len(chosen) < max_gates:
             best, best_cost = None, 99
@@ -103,7 +166,6 @@ def plan_passes(ops, n_qubits, tile_qubits=DEFAULT_TILE_QUBITS, max_gates=_lib.M
             op = ops[best]
             frontier.discard(best)
             chosen.append(op)
-            chosen_idx.append(best)
             used.update(op.qubits)
             payload += op.payload_doubles
             n_left -= 1
@@ -137,7 +199,7 @@ def plan_passes(ops, n_qubits, tile_qubits=DEFAULT_TILE_QUBITS, max_gates=_lib.M
                 new_pos[qi], new_pos[qe] = layout[qe], layout[qi]
             if incoming:
                 dest = [new_pos[q] for q in tile_log]
-        passes.append(Pass(tile_phys, [_relabel(op, layout) for op in chosen], dest, chosen_idx))
+        passes.append(Pass(tile_phys, [_relabel(op, layout) for op in chosen], dest))
         if dest is not None:
             for q, d in zip(tile_log, dest):
                 layout[q] = d

@@ -8,7 +8,7 @@ import numpy as np
 
 from oracle import basicaer_oracle as orc
 from qiskit_sdk_py_b200 import _lib
-from qiskit_sdk_py_b200.planner import plan_passes
+from qiskit_sdk_py_b200.planner import merge_ops, plan_passes
 
 
 class FakeState:
@@ -56,7 +56,7 @@ class FakeState:
     def _flush(self, run):
         if not run:
             return
-        for p in plan_passes(run, self.n, self.tile_qubits):
+        for p in plan_passes(merge_ops(run), self.n, self.tile_qubits):
             self.apply_pass(p.tile_qubits, p.ops)
             self.pass_log.append(p)
 

@@ -158,3 +158,55 @@ def test_get_simulator_aliases():
     assert simulator.get_simulator("local_qasm_simulator_py", state_factory=FakeState).name() == "qasm_simulator"
     with pytest.raises(LookupError):
         simulator.get_simulator("nope")
+
+
+def _apply_all(ops, n, vec):
+    from oracle import basicaer_oracle as orc
+
+    for op in ops:
+        if op.kind in (_lib.GATE_DIAG1, _lib.GATE_DIAG2):
+            mat = np.diag(op.matrix)
+        elif op.kind == _lib.GATE_CX:
+            mat = orc.cx_gate_matrix()
+        else:
+            mat = op.matrix
+        vec = orc.apply_unitary(vec.reshape([2] * n), mat, list(op.qubits)).reshape(-1)
+    return vec
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_merge_ops_is_exact_on_random_streams(seed):
+    """merge_ops changes the op list, never the state: random basis-gate streams mixed with SU(4) blocks."""
+    from qiskit_sdk_py_b200.planner import merge_ops
+
+    n = 6
+    ins = circuits.random_basis_instructions(n, 40, seed) + circuits.quantum_volume_instructions(n, 3, seed)
+    ins += circuits.random_basis_instructions(n, 20, seed + 50)
+    ops = [o for o in (lower.lower_gate(i["name"], i["qubits"], i.get("params")) for i in ins) if o is not None]
+    merged = merge_ops(ops)
+    assert len(merged) < len(ops)
+    rng = np.random.RandomState(seed)
+    vec = rng.standard_normal(2 ** n) + 1j * rng.standard_normal(2 ** n)
+    assert np.max(np.abs(_apply_all(merged, n, vec.copy()) - _apply_all(ops, n, vec.copy()))) < 1e-12
+    for op in merged:
+        assert len(op.qubits) <= 2 and len(set(op.qubits)) == len(op.qubits)
+
+
+def test_merge_ops_turns_controlled_phase_into_one_diagonal_op():
+    """QFT in the simulator basis: every cp = u1 cx u1 cx u1 collapses into a single diagonal op, so QFT-20
+    (1000 instructions) becomes 200 ops: 171 diagonal 2-qubit ops and 29 dense ones (each H joins the first
+    controlled phase on its qubit; the final swaps are 3 cx = one dense op)."""
+    from qiskit_sdk_py_b200.planner import merge_ops
+
+    qobj = circuits.qft(20)
+    ins = qobj["experiments"][0]["instructions"]
+    ops = [o for o in (lower.lower_gate(i["name"], i["qubits"], i.get("params")) for i in ins) if o is not None]
+    assert len(ops) == 1000
+    merged = merge_ops(ops)
+    kinds = [op.kind for op in merged]
+    assert len(merged) <= 230
+    assert kinds.count(_lib.GATE_DIAG2) >= 170
+    assert kinds.count(_lib.GATE_CX) == 0
+    # untouched ops are passed through as the same objects
+    lone = [lower.lower_gate("u3", [0], [0.1, 0.2, 0.3]), lower.lower_gate("cx", [1, 2], None)]
+    assert merge_ops(lone)[0] is lone[0] and merge_ops(lone)[1] is lone[1]

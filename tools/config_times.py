@@ -20,3 +20,6 @@ for name in ("qft_20_product", "qv_20_counts", "qv_24_counts"):
     run(name, case["backend"], case["qobj"])
 run("qv_24 statevector", "statevector_simulator", circuits.quantum_volume(24, measure_final=False, shots=1))
 run("qv_26 counts (blocked sampler)", "qasm_simulator", circuits.quantum_volume(27, shots=8192))
+# QFT at sizes beyond the reference's 24-qubit cap (statevector stays on the device: counts of a product state)
+for nq in (28, 30, 32):
+    run("qft_%d counts" % nq, "qasm_simulator", circuits.qft(nq, state_seed=3, shots=8192, measure_final=True, seed_simulator=21))
