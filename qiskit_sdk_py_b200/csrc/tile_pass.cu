@@ -60,9 +60,22 @@ struct __align__(4) PassStage {
   uint16_t ocol[4];       // cj[obit[j]]
 };
 
+constexpr int kMaxRuns = 4;      // diagonal runs of a pass that get a lookup table (4 KiB of shared memory each)
+constexpr int kRunBits = 8;      // ... over at most 8 tile bits
+
+// A run of consecutive diagonal gates of one stage, folded on the host into ONE table over the tile bits the
+// run touches: element li is multiplied by tab[x(li)], x = the run's bits of li gathered.  x is a sum of a
+// warp part, a lane part and an iteration part, like every other index of the kernel.
+struct DiagRun {
+  uint8_t first_op, n_ops, nbits, pad;
+  uint16_t moff;                      // table (2^nbits complex) in PassDesc::mats
+  uint16_t xw[kWarps], xl[32], xit[8];
+};
+
 struct PassDesc {
   int32_t n, b, nops, nstages;
   int32_t nfrag;        // B-fragment units (64 doubles) of all ops: 1 per 2-qubit gate, 4 per fused block
+  int32_t nruns;        // tabulated diagonal runs
   uint32_t n_tiles;
   uint32_t flags;       // QSV_DEBUG_FLAGS (profiling experiments)
   uint32_t pb_ld;       // log2(amplitudes per bulk-load piece): contiguous low tile bits, at most 4 (256 B)
@@ -71,6 +84,7 @@ struct PassDesc {
   uint8_t tbs[16];      // the tile's physical bits in ascending order (tile base computation)
   uint16_t cj[16];      // shared-memory slot increment of tile-local bit j (see slot layout below)
   uint8_t src_of[16];   // write-back permutation: tile-local position j receives the content of bit src_of[j]
+  DiagRun runs[kMaxRuns];
   PassStage stages[kMaxStages];
   PassOp ops[kMaxOps];
   double mats[kMaxMat];
@@ -184,6 +198,10 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
   uint32_t (*st_warp)[kWarps] = reinterpret_cast<uint32_t (*)[kWarps]>(opl + nops_all);  // [nstages][16]
   uint32_t (*st_lane)[32] = reinterpret_cast<uint32_t (*)[32]>(st_warp + nst_all);       // [nstages][32]
   uint32_t (*st_it)[8] = reinterpret_cast<uint32_t (*)[8]>(st_lane + nst_all);           // [nstages][8]
+  // tabulated diagonal runs: [nruns][256] complex (16-byte aligned), then [nruns][56] index parts
+  const uintptr_t run_base = (reinterpret_cast<uintptr_t>(st_it + nst_all) + 15u) & ~(uintptr_t)15u;
+  double2 (*runtab)[1 << kRunBits] = reinterpret_cast<double2 (*)[1 << kRunBits]>(run_base);
+  uint16_t (*runix)[56] = reinterpret_cast<uint16_t (*)[56]>(runtab + d.nruns);
 
   const uint32_t tid = threadIdx.x;
   const uint32_t dbg = d.flags;  // 1 = no write-back, 2 = no loads, 4 = no gates
@@ -225,9 +243,13 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
       r.kind = op.kind; r.ngl = op.ngl; r.t0 = op.t0; r.t1 = op.t1;
       r.moff = op.moff;
       if (op.kind == kGateDense3) { r.c5 = op.z2; r.moff = op.foff; }  // a fused block has at most 5 free bits
-      if (op.kind == QSV_GATE_DENSE2) r.moff = op.foff;
+      if (op.kind == QSV_GATE_DENSE2 || op.kind == QSV_GATE_DIAG1 || op.kind == QSV_GATE_DIAG2) r.moff = op.foff;
       oprec[o] = r;
     }
+    // diagonal gates: the 2 or 4 factors live in shared memory (a lane-dependent index into the kernel
+    // parameters would be a divergent constant load, serialised per distinct address)
+    if ((op.kind == QSV_GATE_DIAG1 || op.kind == QSV_GATE_DIAG2) && e >= 48 && e < 56)
+      frag[op.foff * 64 + (e - 48)] = (op.kind == QSV_GATE_DIAG2 || e - 48 < 4) ? d.mats[op.moff + (e - 48)] : 0.0;
   }
   // B fragments of fused 3-qubit blocks: the 8x8 complex block is the 16x16 real matrix [[Re,-Im],[Im,Re]];
   // fragment (h, s) -- output half h, k-slice s -- holds Mreal[n = 8 h + (l >> 2)][k = 4 s + (l & 3)] in lane l
@@ -261,6 +283,12 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
         if (((e - 32) >> j) & 1) { li |= 1u << st.ebit[j]; sl += st.ecol[j]; }
       st_lane[sidx][e - 32] = li | (sl << 16);
     }
+  }
+  for (int idx = tid; idx < d.nruns * (1 << kRunBits); idx += kPT) {
+    const int r = idx >> kRunBits, x = idx & ((1 << kRunBits) - 1);
+    const DiagRun& run = d.runs[r];
+    if (x < (1 << run.nbits)) runtab[r][x] = make_double2(d.mats[run.moff + 2 * x], d.mats[run.moff + 2 * x + 1]);
+    if (x < 56) runix[r][x] = x < kWarps ? run.xw[x] : x < kWarps + 32 ? run.xl[x - kWarps] : run.xit[x - kWarps - 32];
   }
   // bulk-copy pieces of this thread: piece p covers tile-local bits [0, pb); its index bits are the
   // tile-local bits pb.. ; thread t owns pieces t, t + kPT, ...
@@ -467,10 +495,22 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
           const uint32_t n_el = 1u << n_inner;
           const uint32_t lv = wv + st_lane[sidx][lane];  // li (low 16 bits) and slot (high 16): no carries between them
           const bool is_diag = rec.kind == QSV_GATE_DIAG1 || rec.kind == QSV_GATE_DIAG2;
-          if (is_diag) {
+          if (is_diag && rec.ngl) {
+            // tabulated run: one table lookup and one complex multiply per element for the whole run
+            const int r = rec.ngl - 1;
+            const double2* tab = runtab[r];
+            const uint32_t x0 = (uint32_t)runix[r][wid] + (uint32_t)runix[r][kWarps + lane];
+            for (uint32_t it = 0; it < 8u; it++) {
+              if ((lane | (it << 5)) >= n_el) break;
+              const uint32_t sl = (lv + st_it[sidx][it]) >> 16;
+              tile[sl] = cmul(tab[x0 + runix[r][kWarps + 32 + it]], tile[sl]);
+            }
+            o += d.runs[r].n_ops - 1;
+          } else if (is_diag) {
             // a run of consecutive diagonal gates of the stage is applied in one read-modify-write
             int o_last = o;
-            while (o_last + 1 < o_end && (oprec[o_last + 1].kind == QSV_GATE_DIAG1 || oprec[o_last + 1].kind == QSV_GATE_DIAG2))
+            while (o_last + 1 < o_end && !oprec[o_last + 1].ngl &&
+                   (oprec[o_last + 1].kind == QSV_GATE_DIAG1 || oprec[o_last + 1].kind == QSV_GATE_DIAG2))
               o_last++;
             for (uint32_t it = 0; it < 8u; it++) {
               if ((lane | (it << 5)) >= n_el) break;
@@ -479,18 +519,10 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
               double2 a = tile[sl];
               for (int q = o; q <= o_last; q++) {
                 const OpRec rq = oprec[q];
-                const double* m = d.mats + rq.moff;
-                const uint32_t b0 = (li >> rq.t0) & 1u;
-                double2 f;
-                if (rq.kind == QSV_GATE_DIAG1) {
-                  f = b0 ? make_double2(m[2], m[3]) : make_double2(m[0], m[1]);
-                } else {
-                  const uint32_t b1 = (li >> rq.t1) & 1u;
-                  const double2 f0 = b0 ? make_double2(m[2], m[3]) : make_double2(m[0], m[1]);
-                  const double2 f1 = b0 ? make_double2(m[6], m[7]) : make_double2(m[4], m[5]);
-                  f = b1 ? f1 : f0;
-                }
-                a = cmul(f, a);
+                const double2* fac = reinterpret_cast<const double2*>(frag + (uint32_t)rq.moff * 64u);
+                uint32_t x = (li >> rq.t0) & 1u;
+                if (rq.kind == QSV_GATE_DIAG2) x |= ((li >> rq.t1) & 1u) << 1;
+                a = cmul(fac[x], a);
               }
               tile[sl] = a;
             }
@@ -1084,7 +1116,7 @@ static int lower_pass(PassDesc& d, PassPlan& plan, int n, const int32_t* tile_qu
   int nfrag = 0;
   for (int k = 0; k < n_gates; k++) {
     sops[k].foff = nfrag;
-    if (sops[k].kind == QSV_GATE_DENSE2) nfrag += 1;
+    if (sops[k].kind == QSV_GATE_DENSE2 || sops[k].kind == QSV_GATE_DIAG1 || sops[k].kind == QSV_GATE_DIAG2) nfrag += 1;
     if (sops[k].kind == kGateDense3) nfrag += 4;
   }
   d.nfrag = nfrag;
@@ -1163,12 +1195,80 @@ static int lower_pass(PassDesc& d, PassPlan& plan, int n, const int32_t* tile_qu
       op.ngl = (uint8_t)nf;
       for (int j = 0; j < 6; j++) op.col[j] = j < nf ? sw1(fo[j]) : 0;
     }
+
+    // ---- runs of consecutive diagonal gates -> lookup tables (QFT-like circuits are mostly such runs) ----
+    const bool tab_on = !(d.flags & 64u);
+    int k = st.first_op;
+    const int k_end = st.first_op + st.n_ops;
+    while (tab_on && k < k_end) {
+      auto is_diag = [&](int idx) { return sops[idx].kind == QSV_GATE_DIAG1 || sops[idx].kind == QSV_GATE_DIAG2; };
+      if (!is_diag(k)) { k++; continue; }
+      uint32_t bits = 0;
+      int k2 = k;
+      while (k2 < k_end && is_diag(k2) && popc(bits | sops[k2].touch) <= kRunBits) bits |= sops[k2++].touch;
+      const int n_run = k2 - k, nb = popc(bits);
+      // a table costs about as much as two gates of the plain path
+      if (n_run >= 3 && d.nruns < kMaxRuns && moff + (2 << nb) <= kMaxMat) {
+        DiagRun& run = d.runs[d.nruns];
+        int ub[kRunBits], nu = 0;
+        for (int j = 0; j < b; j++)
+          if ((bits >> j) & 1u) ub[nu++] = j;
+        auto gather = [&](uint32_t li) {
+          uint32_t x = 0;
+          for (int j = 0; j < nu; j++) x |= ((li >> ub[j]) & 1u) << j;
+          return (uint16_t)x;
+        };
+        run.first_op = (uint8_t)k;
+        run.n_ops = (uint8_t)n_run;
+        run.nbits = (uint8_t)nb;
+        run.moff = (uint16_t)moff;
+        for (uint32_t x = 0; x < (1u << nb); x++) {
+          uint32_t li = 0;
+          for (int j = 0; j < nu; j++) li |= ((x >> j) & 1u) << ub[j];
+          double re = 1.0, im = 0.0;
+          for (int q = k; q < k2; q++) {  // same order as the gates would be applied
+            const HostOp& h = sops[q];
+            uint32_t fx = (li >> h.t0) & 1u;
+            if (h.kind == QSV_GATE_DIAG2) fx |= ((li >> h.t1) & 1u) << 1;
+            const double fr = d.mats[h.moff + 2 * fx], fi = d.mats[h.moff + 2 * fx + 1];
+            const double nr = fr * re - fi * im, ni = fr * im + fi * re;
+            re = nr;
+            im = ni;
+          }
+          d.mats[moff + 2 * x] = re;
+          d.mats[moff + 2 * x + 1] = im;
+        }
+        moff += 2 << nb;
+        for (int e = 0; e < kWarps; e++) {
+          uint32_t li = 0;
+          for (int j = 0; j < st.n_outer; j++)
+            if ((e >> j) & 1) li |= 1u << st.obit[j];
+          run.xw[e] = gather(li);
+        }
+        for (int e = 0; e < 32; e++) {
+          uint32_t li = 0;
+          for (int j = 0; j < 5 && j < st.n_inner; j++)
+            if ((e >> j) & 1) li |= 1u << st.ebit[j];
+          run.xl[e] = gather(li);
+        }
+        for (int e = 0; e < 8; e++) {
+          uint32_t li = 0;
+          for (int j = 0; j < 3; j++)
+            if (((e >> j) & 1) && 5 + j < st.n_inner) li |= 1u << st.ebit[5 + j];
+          run.xit[e] = gather(li);
+        }
+        d.ops[k].ngl = (uint8_t)(d.nruns + 1);
+        d.nruns++;
+      }
+      k = k2;
+    }
   }
 
   size_t tile_slots = (size_t)1 << b;
   for (int j = 4; j < b; j++) tile_slots += pad_of_bit(j);
   const size_t smem = tile_slots * sizeof(double2) + (size_t)nfrag * 64 * sizeof(double) +
-                      (size_t)n_gates * (sizeof(OpRec) + 32 * 4) + (size_t)n_stages * ((kWarps + 32 + 8) * 4);
+                      (size_t)n_gates * (sizeof(OpRec) + 32 * 4) + (size_t)n_stages * ((kWarps + 32 + 8) * 4) + 16 +
+                      (size_t)d.nruns * ((sizeof(double2) << kRunBits) + 56 * sizeof(uint16_t));
   d.n_tiles = 1u << (n - b);
   // one warp per 2^8 amplitudes: 512 threads for b = 12, 256 for b = 11, ...; at least one warp
   plan.smem = smem;

@@ -52,16 +52,24 @@ def _dense(op):
     return np.asarray(op.matrix, dtype=complex)
 
 
+_SWAP_BITS = np.array([0, 2, 1, 3])
+
+
 def _embed(mat, qubits, support):
-    """``mat`` on ``qubits`` as a matrix on ``support`` (1 or 2 qubits, support[0] = LSB)."""
-    qubits, support = tuple(qubits), tuple(support)
+    """``mat`` on ``qubits`` as a matrix on ``support`` (1 or 2 qubits, support[0] = LSB).  Written with slice
+    assignments: this runs once per merged gate on the host, np.kron would dominate small circuits."""
     if qubits == support:
         return mat
     if len(qubits) == 2:  # same pair, roles exchanged: swap the two index bits
-        perm = [0, 2, 1, 3]
-        return mat[np.ix_(perm, perm)]
-    eye = np.eye(2, dtype=complex)
-    return np.kron(eye, mat) if support.index(qubits[0]) == 0 else np.kron(mat, eye)
+        return mat[_SWAP_BITS][:, _SWAP_BITS]
+    out = np.zeros((4, 4), dtype=complex)
+    if support[0] == qubits[0]:  # acts on index bit 0: I (x) M
+        out[0:2, 0:2] = mat
+        out[2:4, 2:4] = mat
+    else:                        # acts on index bit 1: M (x) I
+        out[0::2, 0::2] = mat
+        out[1::2, 1::2] = mat
+    return out
 
 
 def merge_ops(ops):
