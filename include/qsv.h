@@ -96,6 +96,22 @@ int qsv_apply_pass(double* sv, int n_qubits, const int32_t* tile_qubits, int n_t
 int qsv_apply_pass_remap(double* sv, int n_qubits, const int32_t* tile_qubits, int n_tile,
                          const qsv_gate_t* gates, int n_gates, const int32_t* dest_qubits, void* stream);
 
+/* qsv_apply_pass_remap plus a DIAGONAL TAIL: after `gates`, and inside the same pass (no extra HBM traffic),
+ * the `n_tail` diagonal gates of `tail` (QSV_GATE_DIAG1 / QSV_GATE_DIAG2) are applied.  Their qubits need
+ * NOT be tile qubits: outside the tile a qubit is constant per tile, so per tile the whole tail collapses to
+ * one factor pair per tile qubit and the kernel applies it with one or two table look-ups per amplitude,
+ * however many gates the tail has.  A 2-qubit tail gate must have at least one qubit outside the tile (gates
+ * inside the tile belong in `gates`); n_tail <= QSV_MAX_TAIL_GATES.  `dev_scratch` = device buffer of
+ * qsv_tail_scratch_bytes() bytes (only read by this pass; reusable by the next call on the same stream).
+ * Replaces the runs of _add_unitary calls (qasm_simulator.py:145-161) that a controlled-phase ladder makes in
+ * the reference -- e.g. the 435 cp gates of a 30-qubit QFT, each five einsum passes there.  (The tail gates
+ * are applied after ALL of `gates`: the caller guarantees that this order is equivalent to program order.) */
+#define QSV_MAX_TAIL_GATES 192
+int qsv_apply_pass_tail(double* sv, int n_qubits, const int32_t* tile_qubits, int n_tile,
+                        const qsv_gate_t* gates, int n_gates, const int32_t* dest_qubits,
+                        const qsv_gate_t* tail, int n_tail, void* dev_scratch, void* stream);
+size_t qsv_tail_scratch_bytes(void);
+
 /* Host-only introspection of the lowering qsv_apply_pass[_remap] would do for these arguments (no GPU is
  * touched, nothing is launched): info[0] = kernel ops after gate fusion (2-qubit gates that share a qubit
  * are merged into 3-qubit blocks), info[1] = stages (block-wide barriers + 1), info[2] = fused 3-qubit

@@ -24,6 +24,7 @@ MAX_TILE_QUBITS = 12
 MAX_PASS_GATES = 48
 MAX_PASS_MATRIX_DOUBLES = 1536
 MAX_DENSE_K = 12
+MAX_TAIL_GATES = 192
 
 
 class QsvLibraryError(RuntimeError):
@@ -63,6 +64,9 @@ SIGNATURES = {
                                 _c_void_p]),
     "qsv_apply_pass_remap": (_c_int, [_c_void_p, _c_int, _p_int32, _c_int, ctypes.POINTER(QsvGate), _c_int,
                                       _p_int32, _c_void_p]),
+    "qsv_apply_pass_tail": (_c_int, [_c_void_p, _c_int, _p_int32, _c_int, ctypes.POINTER(QsvGate), _c_int, _p_int32,
+                                     ctypes.POINTER(QsvGate), _c_int, _c_void_p, _c_void_p]),
+    "qsv_tail_scratch_bytes": (_c_size_t, []),
     "qsv_pass_info": (_c_int, [_c_int, _p_int32, _c_int, ctypes.POINTER(QsvGate), _c_int, _p_int32, _p_int32]),
     "qsv_apply_matrix": (_c_int, [_c_void_p, _c_int, _p_int32, _c_int, _c_void_p, _c_void_p, _c_void_p]),
     "qsv_reduce_workspace_bytes": (_c_size_t, []),

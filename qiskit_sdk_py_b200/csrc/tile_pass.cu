@@ -72,6 +72,25 @@ struct DiagRun {
   uint16_t xw[kWarps], xl[32], xit[8];
 };
 
+constexpr int kMaxTail = 192;    // diagonal tail gates of a pass (gates with qubits outside the tile)
+
+// Diagonal TAIL of a pass: diagonal gates with at least one qubit outside the tile, applied after the pass's
+// other gates.  Outside the tile a qubit is constant per tile (a bit of the tile's base address), so per
+// tile every tail gate collapses to a factor pair on ONE tile bit (or to a scalar), the factors of a tile
+// bit multiply up, and the whole tail -- however many gates -- becomes one or two small tables over the tile
+// bits, rebuilt per tile, i.e. one or two complex multiplies per amplitude and NO extra pass over HBM.  (A
+// controlled-phase ladder of a QFT touches every qubit of the register: without this each rung needs its
+// two qubits resident, i.e. a pass of its own.)
+struct TailDesc {
+  int32_t n;                          // entries (0 = no tail)
+  uint8_t start[16];                  // entries [start[j], start[j+1]) multiply tile bit j; index b = scalars
+  uint8_t pk[kMaxTail];               // physical bit selecting the factor row (0xff: none)
+  uint8_t pk2[kMaxTail];              // scalars only: second physical bit (0xff: none)
+  uint8_t na, nb;                     // tile bits with factors, split in two table groups of at most 6 bits
+  uint8_t abit[6], bbit[6];
+  uint16_t xw[2][kWarps], xl[2][32], xit[2][8];  // table index parts in the last stage's element order
+};
+
 struct PassDesc {
   int32_t n, b, nops, nstages;
   int32_t nfrag;        // B-fragment units (64 doubles) of all ops: 1 per 2-qubit gate, 4 per fused block
@@ -85,10 +104,13 @@ struct PassDesc {
   uint16_t cj[16];      // shared-memory slot increment of tile-local bit j (see slot layout below)
   uint8_t src_of[16];   // write-back permutation: tile-local position j receives the content of bit src_of[j]
   DiagRun runs[kMaxRuns];
+  TailDesc tail;
   PassStage stages[kMaxStages];
   PassOp ops[kMaxOps];
   double mats[kMaxMat];
 };
+
+static_assert(sizeof(PassDesc) + 16 <= 32764, "PassDesc travels as a __grid_constant__ kernel parameter");
 
 // Shared-memory slot layout (16-byte slots; bank group = slot & 7).  Amplitude li of the tile lives at
 //     slot(li) = sum_j bit_j(li) * cj[j],   cj[j] = 2^j for j < 4,   cj[j] = 2^j + pad_j for j >= 4,
@@ -182,7 +204,8 @@ struct __align__(16) OpRec {
 // run their gates, so the memory phases of one overlap the FP64 / shared-memory phases of the others.
 // A CTA owns a contiguous range of tiles.  The tile moves between HBM and shared memory with TMA bulk
 // copies of 256-byte pieces (one per two threads), which bypass the LSU/L1TEX pipe that the gates saturate.
-__device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const PassDesc& d) {
+__device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const PassDesc& d,
+                                               const double2* __restrict__ tail_ent) {
   // dynamic shared memory: the (padded) tile, then the per-pass tables (sized by the pass, so that short
   // passes leave room for more resident CTAs)
   extern __shared__ double2 tile[];
@@ -202,6 +225,9 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
   const uintptr_t run_base = (reinterpret_cast<uintptr_t>(st_it + nst_all) + 15u) & ~(uintptr_t)15u;
   double2 (*runtab)[1 << kRunBits] = reinterpret_cast<double2 (*)[1 << kRunBits]>(run_base);
   uint16_t (*runix)[56] = reinterpret_cast<uint16_t (*)[56]>(runtab + d.nruns);
+  __shared__ double2 tail_f[16][2];          // per tile: factor pair of every tile bit; [b] = scalar
+  __shared__ double2 tail_tab[2][64];        // per tile: the two tables of the diagonal tail
+  __shared__ uint16_t tail_ix[2][56];
 
   const uint32_t tid = threadIdx.x;
   const uint32_t dbg = d.flags;  // 1 = no write-back, 2 = no loads, 4 = no gates
@@ -289,6 +315,10 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
     const DiagRun& run = d.runs[r];
     if (x < (1 << run.nbits)) runtab[r][x] = make_double2(d.mats[run.moff + 2 * x], d.mats[run.moff + 2 * x + 1]);
     if (x < 56) runix[r][x] = x < kWarps ? run.xw[x] : x < kWarps + 32 ? run.xl[x - kWarps] : run.xit[x - kWarps - 32];
+  }
+  for (int idx = tid; d.tail.n && idx < 112; idx += kPT) {
+    const int g2 = idx / 56, x = idx % 56;
+    tail_ix[g2][x] = x < kWarps ? d.tail.xw[g2][x] : x < kWarps + 32 ? d.tail.xl[g2][x - kWarps] : d.tail.xit[g2][x - kWarps - 32];
   }
   // bulk-copy pieces of this thread: piece p covers tile-local bits [0, pb); its index bits are the
   // tile-local bits pb.. ; thread t owns pieces t, t + kPT, ...
@@ -559,6 +589,67 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
       }
     }
 
+    // ---- diagonal tail (see TailDesc): per-tile factors -> two small tables -> one sweep over the tile ----
+    if (d.tail.n && !(dbg & 4u)) {
+      // (1) factor pair of every tile bit and the scalar: one warp per range, lanes over its entries
+      for (int jj = wid; jj <= b; jj += (int)(kPT >> 5)) {
+        double2 f0 = make_double2(1.0, 0.0), f1 = make_double2(1.0, 0.0);
+        const int e_begin = d.tail.start[jj], e_end = d.tail.start[jj + 1];
+        for (int e0 = e_begin; e0 < e_end; e0 += 32) {
+          const int e = e0 + (int)lane;
+          if (e < e_end) {
+            const uint32_t k1 = d.tail.pk[e], k2 = d.tail.pk2[e];
+            const uint32_t r1 = k1 == 0xffu ? 0u : (uint32_t)((base >> k1) & 1ull);
+            const uint32_t r2 = k2 == 0xffu ? 0u : (uint32_t)((base >> k2) & 1ull);
+            const double2* ent = tail_ent + (size_t)e * 4;
+            if (jj < b) {  // entry = [row][bit of the tile qubit]
+              f0 = cmul(ent[2 * r1], f0);
+              f1 = cmul(ent[2 * r1 + 1], f1);
+            } else {       // scalar entry = [row][second row]
+              f0 = cmul(ent[2 * r1 + r2], f0);
+            }
+          }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          double2 g0, g1;
+          g0.x = __shfl_xor_sync(0xffffffffu, f0.x, off); g0.y = __shfl_xor_sync(0xffffffffu, f0.y, off);
+          g1.x = __shfl_xor_sync(0xffffffffu, f1.x, off); g1.y = __shfl_xor_sync(0xffffffffu, f1.y, off);
+          f0 = cmul(g0, f0);
+          f1 = cmul(g1, f1);
+        }
+        if (lane == 0) { tail_f[jj][0] = f0; tail_f[jj][1] = f1; }
+      }
+      __syncthreads();
+      // (2) tables over the two groups of tile bits (the scalar goes into the first)
+      for (int idx = tid; idx < 128; idx += kPT) {
+        const int g2 = idx >> 6, x = idx & 63;
+        const int nbits = g2 ? d.tail.nb : d.tail.na;
+        if (x < (1 << nbits)) {
+          double2 v = g2 ? make_double2(1.0, 0.0) : tail_f[b][0];
+          for (int i = 0; i < nbits; i++) v = cmul(tail_f[g2 ? d.tail.bbit[i] : d.tail.abit[i]][(x >> i) & 1], v);
+          tail_tab[g2][x] = v;
+        }
+      }
+      __syncthreads();
+      // (3) sweep, in the element order of the last stage
+      const int sl_idx = nstages - 1;
+      if (wid < (1u << d.stages[sl_idx].n_outer)) {
+        const uint32_t n_el = 1u << d.stages[sl_idx].n_inner;
+        const uint32_t lv = st_warp[sl_idx][wid] + st_lane[sl_idx][lane];
+        const uint32_t xa0 = (uint32_t)tail_ix[0][wid] + (uint32_t)tail_ix[0][kWarps + lane];
+        const uint32_t xb0 = (uint32_t)tail_ix[1][wid] + (uint32_t)tail_ix[1][kWarps + lane];
+        const bool two = d.tail.nb != 0;
+        for (uint32_t it = 0; it < 8u; it++) {
+          if ((lane | (it << 5)) >= n_el) break;
+          const uint32_t sl = (lv + st_it[sl_idx][it]) >> 16;
+          double2 a = cmul(tail_tab[0][xa0 + tail_ix[0][kWarps + 32 + it]], tile[sl]);
+          if (two) a = cmul(tail_tab[1][xb0 + tail_ix[1][kWarps + 32 + it]], a);
+          tile[sl] = a;
+        }
+      }
+    }
+
     // ---- write-back: one HBM write of the tile (TMA bulk copies), optionally with the tile qubits
     // permuted: position j receives the content of tile bit src_of[j] (a free qubit remap) ----
     fence_proxy_async();  // the gates' generic-proxy stores must be visible to the async proxy
@@ -582,8 +673,8 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
 // tile) keep more tiles in flight, which is what hides the HBM round trip of each CTA.
 template <int kBlock, int kMinBlocks>
 __global__ void __launch_bounds__(kBlock, kMinBlocks)
-tile_pass_kernel(double2* __restrict__ sv, const __grid_constant__ PassDesc d) {
-  tile_pass_body(sv, d);
+tile_pass_kernel(double2* __restrict__ sv, const __grid_constant__ PassDesc d, const double2* __restrict__ tail_ent) {
+  tile_pass_body(sv, d, tail_ent);
 }
 
 // ---- dense k-qubit gate, 3 <= k <= 12: out-of-place inside the tile (two smem buffers) ----
@@ -828,7 +919,10 @@ struct PassPlan {
 // Host-only lowering of a pass (no CUDA call): validates the arguments, fuses gates, builds the stages and
 // every index table of the kernel into `d`.
 static int lower_pass(PassDesc& d, PassPlan& plan, int n, const int32_t* tile_qubits, int n_tile,
-                      const qsv_gate_t* gates, int n_gates, const int32_t* dest_qubits) {
+                      const qsv_gate_t* gates, int n_gates, const int32_t* dest_qubits,
+                      const qsv_gate_t* tail = nullptr, int n_tail = 0, double* tail_ent = nullptr) {
+  if (n_tail < 0 || n_tail > kMaxTail) return fail(QSV_ERANGE, "qsv_apply_pass_tail: too many tail gates");
+  if (n_tail > 0 && (!tail || !tail_ent)) return fail(QSV_EINVAL, "qsv_apply_pass_tail: null pointer");
   if (n < 1 || n > 40) return fail(QSV_EINVAL, "qsv_apply_pass: bad state / n_qubits");
   if (n_tile < 1 || n_tile > QSV_MAX_TILE_QUBITS || n_tile > n)
     return fail(QSV_ERANGE, "qsv_apply_pass: n_tile must be in [1, min(n_qubits, 12)]");
@@ -1072,7 +1166,15 @@ static int lower_pass(PassDesc& d, PassPlan& plan, int n, const int32_t* tile_qu
   // ---- stages ----
   int order[kMaxOps];
   uint32_t inner_masks[kMaxStages];
-  const int n_stages = build_stages(hops, n_gates, b, order, d.stages, inner_masks);
+  int n_stages = build_stages(hops, n_gates, b, order, d.stages, inner_masks);
+  if (n_stages == 0 && n_tail > 0) {  // the tail sweep borrows the element order of the last stage
+    PassStage& st = d.stages[0];
+    memset(&st, 0, sizeof(st));
+    st.n_inner = (uint8_t)std::min(b, kInner);
+    st.n_outer = (uint8_t)(b - st.n_inner);
+    inner_masks[0] = (1u << st.n_inner) - 1u;
+    n_stages = 1;
+  }
   d.nstages = n_stages;
   d.nops = n_gates;
 
@@ -1264,6 +1366,112 @@ static int lower_pass(PassDesc& d, PassPlan& plan, int n, const int32_t* tile_qu
     }
   }
 
+  // ---- diagonal tail: entries sorted by the tile bit they multiply (index b = scalars) ----
+  if (n_tail > 0) {
+    TailDesc& td = d.tail;
+    int range_of[kMaxTail];
+    uint8_t pk1[kMaxTail], pk2[kMaxTail];
+    double ent[kMaxTail][8];
+    int count[16] = {0};
+    for (int i = 0; i < n_tail; i++) {
+      const qsv_gate_t& g = tail[i];
+      if (g.kind != QSV_GATE_DIAG1 && g.kind != QSV_GATE_DIAG2)
+        return fail(QSV_EINVAL, "qsv_apply_pass_tail: tail gates must be diagonal (QSV_GATE_DIAG1 / QSV_GATE_DIAG2)");
+      const bool two = g.kind == QSV_GATE_DIAG2;
+      if (g.q0 < 0 || g.q0 >= n || (two && (g.q1 < 0 || g.q1 >= n || g.q1 == g.q0)))
+        return fail(QSV_EINVAL, "qsv_apply_pass_tail: tail gate qubit out of range");
+      const int l0 = local_of[g.q0], l1 = two ? local_of[g.q1] : -1;
+      if (two && l0 >= 0 && l1 >= 0)
+        return fail(QSV_EINVAL, "qsv_apply_pass_tail: a 2-qubit tail gate needs a qubit outside the tile");
+      // factor of the gate for (bit of q0, bit of q1): m[b0 + 2 b1] (complex)
+      auto fac = [&](int b0, int b1, double* out) {
+        const int idx = b0 + 2 * b1;
+        out[0] = g.m[2 * idx];
+        out[1] = g.m[2 * idx + 1];
+      };
+      pk1[i] = 0xff;
+      pk2[i] = 0xff;
+      if (!two) {
+        if (l0 >= 0) {  // in the tile: [row any][bit]
+          range_of[i] = l0;
+          for (int r = 0; r < 2; r++)
+            for (int bj = 0; bj < 2; bj++) fac(bj, 0, ent[i] + 2 * (2 * r + bj));
+        } else {        // scalar: [row = bit of q0][*]
+          range_of[i] = b;
+          pk1[i] = (uint8_t)g.q0;
+          for (int r = 0; r < 2; r++)
+            for (int r2 = 0; r2 < 2; r2++) fac(r, 0, ent[i] + 2 * (2 * r + r2));
+        }
+      } else if (l0 >= 0) {  // q0 in the tile, q1 selects the row
+        range_of[i] = l0;
+        pk1[i] = (uint8_t)g.q1;
+        for (int r = 0; r < 2; r++)
+          for (int bj = 0; bj < 2; bj++) fac(bj, r, ent[i] + 2 * (2 * r + bj));
+      } else if (l1 >= 0) {  // q1 in the tile, q0 selects the row
+        range_of[i] = l1;
+        pk1[i] = (uint8_t)g.q0;
+        for (int r = 0; r < 2; r++)
+          for (int bj = 0; bj < 2; bj++) fac(r, bj, ent[i] + 2 * (2 * r + bj));
+      } else {               // both outside: scalar [row = q0][row2 = q1]
+        range_of[i] = b;
+        pk1[i] = (uint8_t)g.q0;
+        pk2[i] = (uint8_t)g.q1;
+        for (int r = 0; r < 2; r++)
+          for (int r2 = 0; r2 < 2; r2++) fac(r, r2, ent[i] + 2 * (2 * r + r2));
+      }
+      count[range_of[i]]++;
+    }
+    int at[17];
+    at[0] = 0;
+    for (int j = 0; j <= b; j++) at[j + 1] = at[j] + count[j];
+    for (int j = 0; j <= b + 1; j++) td.start[j] = (uint8_t)at[j];
+    int fill[16];
+    for (int j = 0; j <= b; j++) fill[j] = at[j];
+    for (int i = 0; i < n_tail; i++) {  // stable: gates of one range keep their order
+      const int e = fill[range_of[i]]++;
+      td.pk[e] = pk1[i];
+      td.pk2[e] = pk2[i];
+      memcpy(tail_ent + 8 * e, ent[i], sizeof(double) * 8);
+    }
+    td.n = n_tail;
+    // table groups: the tile bits that have factors, at most 6 per table
+    int nj = 0, jb[16];
+    for (int j = 0; j < b; j++)
+      if (count[j]) jb[nj++] = j;
+    td.na = (uint8_t)std::min(nj, 6);
+    td.nb = (uint8_t)(nj - td.na);
+    for (int i = 0; i < td.na; i++) td.abit[i] = (uint8_t)jb[i];
+    for (int i = 0; i < td.nb; i++) td.bbit[i] = (uint8_t)jb[6 + i];
+    const PassStage& st = d.stages[n_stages - 1];
+    for (int g2 = 0; g2 < 2; g2++) {
+      const uint8_t* gb = g2 ? td.bbit : td.abit;
+      const int ng = g2 ? td.nb : td.na;
+      auto gather = [&](uint32_t li) {
+        uint32_t x = 0;
+        for (int i = 0; i < ng; i++) x |= ((li >> gb[i]) & 1u) << i;
+        return (uint16_t)x;
+      };
+      for (int e = 0; e < kWarps; e++) {
+        uint32_t li = 0;
+        for (int j = 0; j < st.n_outer; j++)
+          if ((e >> j) & 1) li |= 1u << st.obit[j];
+        td.xw[g2][e] = gather(li);
+      }
+      for (int e = 0; e < 32; e++) {
+        uint32_t li = 0;
+        for (int j = 0; j < 5 && j < st.n_inner; j++)
+          if ((e >> j) & 1) li |= 1u << st.ebit[j];
+        td.xl[g2][e] = gather(li);
+      }
+      for (int e = 0; e < 8; e++) {
+        uint32_t li = 0;
+        for (int j = 0; j < 3; j++)
+          if (((e >> j) & 1) && 5 + j < st.n_inner) li |= 1u << st.ebit[5 + j];
+        td.xit[g2][e] = gather(li);
+      }
+    }
+  }
+
   size_t tile_slots = (size_t)1 << b;
   for (int j = 4; j < b; j++) tile_slots += pad_of_bit(j);
   const size_t smem = tile_slots * sizeof(double2) + (size_t)nfrag * 64 * sizeof(double) +
@@ -1280,12 +1488,19 @@ static int lower_pass(PassDesc& d, PassPlan& plan, int n, const int32_t* tile_qu
 }
 
 static int launch_pass(double* sv, int n, const int32_t* tile_qubits, int n_tile, const qsv_gate_t* gates,
-                       int n_gates, cudaStream_t stream, const int32_t* dest_qubits = nullptr) {
+                       int n_gates, cudaStream_t stream, const int32_t* dest_qubits = nullptr,
+                       const qsv_gate_t* tail = nullptr, int n_tail = 0, void* dev_scratch = nullptr) {
   if (!sv) return fail(QSV_EINVAL, "qsv_apply_pass: bad state / n_qubits");
+  if (n_tail > 0 && !dev_scratch) return fail(QSV_EINVAL, "qsv_apply_pass_tail: null device scratch");
   static thread_local PassDesc d;
+  static thread_local double tail_ent[kMaxTail * 8];
   PassPlan plan;
-  if (int rc = lower_pass(d, plan, n, tile_qubits, n_tile, gates, n_gates, dest_qubits)) return rc;
+  if (int rc = lower_pass(d, plan, n, tile_qubits, n_tile, gates, n_gates, dest_qubits, tail, n_tail, tail_ent))
+    return rc;
   if (int rc = ensure_attrs()) return rc;
+  if (n_tail > 0)  // small pageable copy: staged by the driver before the call returns, ordered on the stream
+    QSV_CUDA(cudaMemcpyAsync(dev_scratch, tail_ent, sizeof(double) * 8 * (size_t)n_tail, cudaMemcpyHostToDevice, stream));
+  const double2* d_tail = reinterpret_cast<const double2*>(dev_scratch);
   const size_t smem = plan.smem;
   const int threads = plan.threads;
   int per_sm = 1;
@@ -1299,11 +1514,11 @@ static int launch_pass(double* sv, int n, const int32_t* tile_qubits, int n_tile
   if (per_sm < 1) return fail(QSV_ERANGE, "qsv_apply_pass: pass does not fit in shared memory");
   const unsigned grid = std::min<unsigned>(d.n_tiles, (unsigned)per_sm * (unsigned)sm_count());
   if (threads >= 512)
-    tile_pass_kernel<512, 2><<<grid, threads, smem, stream>>>(reinterpret_cast<double2*>(sv), d);
+    tile_pass_kernel<512, 2><<<grid, threads, smem, stream>>>(reinterpret_cast<double2*>(sv), d, d_tail);
   else if (threads >= 256)
-    tile_pass_kernel<256, 4><<<grid, threads, smem, stream>>>(reinterpret_cast<double2*>(sv), d);
+    tile_pass_kernel<256, 4><<<grid, threads, smem, stream>>>(reinterpret_cast<double2*>(sv), d, d_tail);
   else
-    tile_pass_kernel<128, 8><<<grid, threads, smem, stream>>>(reinterpret_cast<double2*>(sv), d);
+    tile_pass_kernel<128, 8><<<grid, threads, smem, stream>>>(reinterpret_cast<double2*>(sv), d, d_tail);
   QSV_LAUNCHED();
   return 0;
 }
@@ -1393,6 +1608,16 @@ int qsv_apply_pass(double* sv, int n, const int32_t* tile_qubits, int n_tile, co
   if (!tile_qubits || (n_gates > 0 && !gates)) return fail(QSV_EINVAL, "qsv_apply_pass: null pointer");
   return launch_pass(sv, n, tile_qubits, n_tile, gates, n_gates, (cudaStream_t)stream);
 }
+
+int qsv_apply_pass_tail(double* sv, int n, const int32_t* tile_qubits, int n_tile, const qsv_gate_t* gates,
+                        int n_gates, const int32_t* dest_qubits, const qsv_gate_t* tail, int n_tail,
+                        void* dev_scratch, void* stream) {
+  if (!tile_qubits || (n_gates > 0 && !gates)) return fail(QSV_EINVAL, "qsv_apply_pass_tail: null pointer");
+  return launch_pass(sv, n, tile_qubits, n_tile, gates, n_gates, (cudaStream_t)stream, dest_qubits, tail, n_tail,
+                     dev_scratch);
+}
+
+size_t qsv_tail_scratch_bytes(void) { return sizeof(double) * 8 * kMaxTail; }
 
 int qsv_pass_info(int n, const int32_t* tile_qubits, int n_tile, const qsv_gate_t* gates, int n_gates,
                   const int32_t* dest_qubits, int32_t* info) {

@@ -51,6 +51,7 @@ class DeviceState:
             self._reduce_ws = torch.empty(self.lib.qsv_reduce_workspace_bytes() // 8 + 8,
                                           dtype=torch.float64, device=self.device)
         self._mat_scratch = None
+        self._tail_scratch = None
         self._sample_ws = None
         self._marg_ws = None
         self._probs = None
@@ -99,15 +100,28 @@ class DeviceState:
             _lib.check(self.lib.qsv_scale(self.ptr, self.n, factor.real, factor.imag, self.stream), "qsv_scale")
 
     # -- gates -----------------------------------------------------------------------
-    def apply_pass(self, tile_qubits, ops, dest=None):
+    def apply_pass(self, tile_qubits, ops, dest=None, tail=None):
         """One cache-blocked pass on PHYSICAL qubits; ``dest`` (optional) permutes the tile qubits on
-        write-back (content of tile_qubits[i] lands on dest[i])."""
+        write-back (content of tile_qubits[i] lands on dest[i]); ``tail`` (optional) is a list of diagonal
+        GateOps, on any qubits, applied after ``ops`` inside the same pass (qsv_apply_pass_tail)."""
         gates = (_lib.QsvGate * max(1, len(ops)))()
         for i, op in enumerate(ops):
             _fill_gate(gates[i], op)
         tile = _int32_array(tile_qubits)
         with self._ctx():
-            if dest is None:
+            if tail:
+                tgates = (_lib.QsvGate * len(tail))()
+                for i, op in enumerate(tail):
+                    _fill_gate(tgates[i], op)
+                if self._tail_scratch is None:
+                    self._tail_scratch = self._torch.empty(int(self.lib.qsv_tail_scratch_bytes()) // 8,
+                                                           dtype=self._torch.float64, device=self.device)
+                _lib.check(self.lib.qsv_apply_pass_tail(self.ptr, self.n, tile, len(tile_qubits), gates, len(ops),
+                                                        None if dest is None else _int32_array(dest), tgates,
+                                                        len(tail), ctypes.c_void_p(self._tail_scratch.data_ptr()),
+                                                        self.stream), "qsv_apply_pass_tail")
+                self.gates_applied += len(tail)
+            elif dest is None:
                 _lib.check(self.lib.qsv_apply_pass(self.ptr, self.n, tile, len(tile_qubits), gates, len(ops),
                                                    self.stream), "qsv_apply_pass")
             else:
@@ -167,8 +181,8 @@ class DeviceState:
     def _flush(self, run):
         if not run:
             return
-        for p in plan_passes(merge_ops(run), self.n, self.tile_qubits):
-            self.apply_pass(p.tile_qubits, p.ops)
+        for p in plan_passes(merge_ops(run), self.n, self.tile_qubits, tails=True):
+            self.apply_pass(p.tile_qubits, p.ops, tail=p.tail)
 
     # -- measurement -----------------------------------------------------------------
     def prob_qubit(self, qubit):

@@ -29,15 +29,17 @@ class Pass:
     at the start of the pass; ``dest`` (or None) says where each tile qubit's content lands on
     write-back (``dest[i]`` for ``tile_qubits[i]``)."""
 
-    __slots__ = ("tile_qubits", "ops", "dest")
+    __slots__ = ("tile_qubits", "ops", "dest", "tail")
 
-    def __init__(self, tile_qubits, ops, dest=None):
+    def __init__(self, tile_qubits, ops, dest=None, tail=None):
         self.tile_qubits = tuple(tile_qubits)
         self.ops = list(ops)
         self.dest = None if dest is None else tuple(dest)
+        self.tail = list(tail) if tail else []  # diagonal ops on any qubits, applied after ``ops`` in the same pass
 
     def __repr__(self):
-        return "Pass(tile=%r, %d ops%s)" % (self.tile_qubits, len(self.ops), ", remap" if self.dest else "")
+        return "Pass(tile=%r, %d ops%s%s)" % (self.tile_qubits, len(self.ops), ", remap" if self.dest else "",
+                                              ", %d tail" % len(self.tail) if self.tail else "")
 
 
 _CX = np.array([[1, 0, 0, 0], [0, 0, 0, 1], [0, 0, 1, 0], [0, 1, 0, 0]], dtype=complex)  # basicaertools.py:70-72
@@ -116,7 +118,7 @@ def _relabel(op, layout):
 
 
 def plan_passes(ops, n_qubits, tile_qubits=DEFAULT_TILE_QUBITS, max_gates=_lib.MAX_PASS_GATES,
-                max_payload=_lib.MAX_PASS_MATRIX_DOUBLES, layout=None, remap=False):
+                max_payload=_lib.MAX_PASS_MATRIX_DOUBLES, layout=None, remap=False, tails=False):
     """Group ``ops`` (GateOps on LOGICAL qubits, <= 2 qubits each) into passes.
 
     Frontier-greedy over the gate dependency DAG: a gate is *ready* when it is the first pending gate
@@ -124,6 +126,12 @@ def plan_passes(ops, n_qubits, tile_qubits=DEFAULT_TILE_QUBITS, max_gates=_lib.M
     new tile qubits is taken next (ties: program order), until nothing fits.  Only gates on disjoint
     qubits are ever commuted.  (On QuantumVolume(33) this yields 7.3 gates per 11-qubit pass against
     5.7 for a plain program-order scan.)
+
+    With ``tails`` every pass also takes a diagonal TAIL (``Pass.tail``, qsv_apply_pass_tail): once the
+    pass's gates are chosen, every diagonal gate that is next in line on all of its qubits and has a qubit
+    outside the tile (or is a 1-qubit diagonal) rides along -- the kernel applies the whole tail with one or
+    two table look-ups per amplitude, wherever the gates' qubits are.  A controlled-phase ladder (QFT) then
+    needs a pass per ~7 Hadamards instead of a pass per handful of controlled phases.
 
     ``layout[q]`` is the physical bit of logical qubit q (identity if None); it is updated in place when
     given.  With ``remap`` the write-back of each pass moves the tile qubits that the following gates
@@ -194,6 +202,27 @@ def plan_passes(ops, n_qubits, tile_qubits=DEFAULT_TILE_QUBITS, max_gates=_lib.M
             used |= set(cand[: tile_size - len(used)])
         tile_log = sorted(used, key=lambda q: layout[q])
         tile_phys = [layout[q] for q in tile_log]
+        tail = []
+        if tails:
+            diag = (_lib.GATE_DIAG1, _lib.GATE_DIAG2)
+            grew = True
+            while grew and len(tail) < _lib.MAX_TAIL_GATES:
+                grew = False
+                for idx in sorted(frontier):
+                    op = ops[idx]
+                    if op.kind not in diag or (len(op.qubits) == 2 and all(q in used for q in op.qubits)):
+                        continue  # a 2-qubit diagonal inside the tile is an ordinary gate of a pass
+                    frontier.discard(idx)
+                    tail.append(op)
+                    n_left -= 1
+                    for q in op.qubits:
+                        queues[q].popleft()
+                    for q in op.qubits:
+                        if queues[q] and is_ready(queues[q][0]):
+                            frontier.add(queues[q][0])
+                    grew = True
+                    if len(tail) >= _lib.MAX_TAIL_GATES:
+                        break
         dest = None
         if remap and n_left:
             # the n_low tile qubits needed soonest become the residents of the low bits
@@ -207,7 +236,8 @@ def plan_passes(ops, n_qubits, tile_qubits=DEFAULT_TILE_QUBITS, max_gates=_lib.M
                 new_pos[qi], new_pos[qe] = layout[qe], layout[qi]
             if incoming:
                 dest = [new_pos[q] for q in tile_log]
-        passes.append(Pass(tile_phys, [_relabel(op, layout) for op in chosen], dest))
+        passes.append(Pass(tile_phys, [_relabel(op, layout) for op in chosen], dest,
+                           [_relabel(op, layout) for op in tail]))
         if dest is not None:
             for q, d in zip(tile_log, dest):
                 layout[q] = d

@@ -56,18 +56,24 @@ class FakeState:
     def _flush(self, run):
         if not run:
             return
-        for p in plan_passes(merge_ops(run), self.n, self.tile_qubits):
-            self.apply_pass(p.tile_qubits, p.ops)
+        for p in plan_passes(merge_ops(run), self.n, self.tile_qubits, tails=True):
+            self.apply_pass(p.tile_qubits, p.ops, tail=p.tail)
             self.pass_log.append(p)
 
-    def apply_pass(self, tile_qubits, ops, dest=None):
+    def apply_pass(self, tile_qubits, ops, dest=None, tail=None):
         assert dest is None
         assert len(tile_qubits) == min(self.n, self.tile_qubits) and len(set(tile_qubits)) == len(tile_qubits)
         for op in ops:
             assert set(op.qubits) <= set(tile_qubits)
             self._apply(op)
+        tail = tail or []
+        assert len(tail) <= _lib.MAX_TAIL_GATES
+        for op in tail:  # the contract of qsv_apply_pass_tail
+            assert op.kind in (_lib.GATE_DIAG1, _lib.GATE_DIAG2)
+            assert len(op.qubits) == 1 or not set(op.qubits) <= set(tile_qubits)
+            self._apply(op)
         self.passes_launched += 1
-        self.gates_applied += len(ops)
+        self.gates_applied += len(ops) + len(tail)
 
     def prob_qubit(self, qubit):
         p = np.abs(self.vec) ** 2

@@ -156,6 +156,88 @@ def test_remap_passes(n, tile):
     assert np.max(np.abs(st.download() - ref)) < TOL
 
 
+def _random_tail(n, tile, count, rng):
+    """Diagonal gates allowed in a pass tail: 1-qubit anywhere, 2-qubit with at least one qubit outside the tile."""
+    outside = [q for q in range(n) if q not in tile]
+    tail = []
+    for _ in range(count):
+        kind = rng.randint(4)
+        if kind == 0 or not outside:
+            tail.append(GateOp(_lib.GATE_DIAG1, [rng.randint(n)], np.exp(1j * rng.uniform(0, 6, 2))))
+            continue
+        a = outside[rng.randint(len(outside))]
+        if kind == 3 and len(outside) >= 2:
+            b = a
+            while b == a:
+                b = outside[rng.randint(len(outside))]
+        else:
+            b = tile[rng.randint(len(tile))]
+        qs = [a, b] if rng.randint(2) else [b, a]
+        tail.append(GateOp(_lib.GATE_DIAG2, qs, np.exp(1j * rng.uniform(0, 6, 4))))
+    return tail
+
+
+@pytest.mark.parametrize("n,tile_size,n_ops,n_tail", [(5, 3, 3, 10), (9, 6, 0, 40), (12, 8, 6, 1), (14, 11, 10, 192),
+                                                      (16, 12, 5, 100), (13, 4, 2, 60), (15, 11, 0, 7)])
+def test_pass_with_diagonal_tail(n, tile_size, n_ops, n_tail):
+    """qsv_apply_pass_tail: diagonal gates on qubits outside the tile, applied inside the pass (per tile they
+    collapse to factor pairs on the tile bits; the kernel rebuilds two small tables per tile)."""
+    rng = np.random.RandomState(31 * n + n_tail)
+    vec = rand_state(n, 5)
+    tile = sorted(int(q) for q in rng.choice(n, tile_size, replace=False))
+    if tile_size >= 8:
+        tile = sorted(set([0, 1, 2, 3]) | set(tile[4:]))
+        tile = tile + [q for q in range(n) if q not in tile][: tile_size - len(tile)]
+    ops = []
+    for _ in range(n_ops):
+        a, b = (int(x) for x in rng.choice(tile, 2, replace=False))
+        pick = rng.randint(3)
+        if pick == 0:
+            ops.append(GateOp(_lib.GATE_DENSE2, [a, b], rand_unitary(2, rng)))
+        elif pick == 1:
+            ops.append(GateOp(_lib.GATE_DIAG2, [a, b], np.exp(1j * rng.uniform(0, 6, 4))))
+        else:
+            ops.append(GateOp(_lib.GATE_DENSE1, [a], rand_unitary(1, rng)))
+    tail = _random_tail(n, tile, n_tail, rng)
+    st = make_state(n, vec)
+    st.apply_pass(tile, ops, tail=tail)
+    ref = vec.copy()
+    for op in ops + tail:
+        ref = oracle_apply(ref, op, n)
+    assert np.max(np.abs(st.download() - ref)) < TOL
+
+
+def test_tail_argument_errors():
+    st = make_state(10, rand_state(10, 1))
+    tile = list(range(8))
+    diag2 = lambda a, b: GateOp(_lib.GATE_DIAG2, [a, b], np.ones(4, dtype=complex))
+    with pytest.raises(_lib.QsvLibraryError, match="needs a qubit outside the tile"):
+        st.apply_pass(tile, [], tail=[diag2(1, 2)])
+    with pytest.raises(_lib.QsvLibraryError, match="must be diagonal"):
+        st.apply_pass(tile, [], tail=[GateOp(_lib.GATE_DENSE1, [9], np.eye(2, dtype=complex))])
+    with pytest.raises(_lib.QsvLibraryError, match="too many tail gates"):
+        st.apply_pass(tile, [], tail=[diag2(1, 9)] * 193)
+
+
+@pytest.mark.parametrize("n", [12, 17, 20])
+def test_qft_through_planner_tails(n):
+    """QFT in the simulator basis: merge_ops + tails bring it down to a handful of passes; same state as the
+    oracle applying the 5 n (n-1) / 2 + n + 3 (n // 2) basis gates one by one."""
+    from qiskit_sdk_py_b200 import circuits
+
+    ins = circuits.qft(n, state_seed=3)["experiments"][0]["instructions"]
+    ops = [o for o in (lower.lower_gate(i["name"], i["qubits"], i.get("params")) for i in ins) if o is not None]
+    st = make_state(n)
+    st.init_basis0()
+    st.apply_ops(ops)
+    assert st.passes_launched <= 10
+    ref = np.zeros(2 ** n, dtype=complex)
+    ref[0] = 1
+    for op in ops:
+        ref = oracle_apply(ref, op, n)
+    assert np.max(np.abs(st.download() - ref)) < 1e-11
+
+
 @pytest.mark.parametrize("n,k", [(3, 3), (5, 3), (9, 4), (12, 5), (13, 6), (14, 7), (9, 9), (15, 3)])
 def test_dense_k(n, k):
     """k-qubit `unitary` instructions, k >= 3 (qasm_simulator.py:543-546)."""
