@@ -803,6 +803,44 @@ static void embed_gate(const double* g4, int nb, int pa, int pb, double* out) {
     }
 }
 
+// any 1- or 2-qubit op as a dense complex matrix (2x2 or 4x4, row-major) in its own qubit order
+static void op_as_dense(int kind, const double* m, double* out) {
+  switch (kind) {
+    case QSV_GATE_DENSE1: memcpy(out, m, sizeof(double) * 8); break;
+    case QSV_GATE_DENSE2: memcpy(out, m, sizeof(double) * 32); break;
+    case QSV_GATE_DIAG1:
+      memset(out, 0, sizeof(double) * 8);
+      for (int i = 0; i < 2; i++) { out[2 * (2 * i + i)] = m[2 * i]; out[2 * (2 * i + i) + 1] = m[2 * i + 1]; }
+      break;
+    case QSV_GATE_DIAG2:
+      memset(out, 0, sizeof(double) * 32);
+      for (int i = 0; i < 4; i++) { out[2 * (4 * i + i)] = m[2 * i]; out[2 * (4 * i + i) + 1] = m[2 * i + 1]; }
+      break;
+    default: {  // QSV_GATE_CX: q0 = control = index bit 0, q1 = target (basicaertools.py:70-72)
+      memset(out, 0, sizeof(double) * 32);
+      static const int to[4] = {0, 3, 2, 1};
+      for (int c = 0; c < 4; c++) out[2 * (4 * to[c] + c)] = 1.0;
+    }
+  }
+}
+
+// `g2` (2x2 complex) on index bit `pa` embedded into `nb` index bits
+static void embed_gate1(const double* g2, int nb, int pa, double* out) {
+  const int dim = 1 << nb;
+  const int keep = (dim - 1) & ~(1 << pa);
+  for (int r = 0; r < dim; r++)
+    for (int c = 0; c < dim; c++) {
+      double re = 0.0, im = 0.0;
+      if ((r & keep) == (c & keep)) {
+        const int rg = (r >> pa) & 1, cg = (c >> pa) & 1;
+        re = g2[2 * (2 * rg + cg)];
+        im = g2[2 * (2 * rg + cg) + 1];
+      }
+      out[2 * (dim * r + c)] = re;
+      out[2 * (dim * r + c) + 1] = im;
+    }
+}
+
 // out = a * b (complex dim x dim, row-major); out must not alias a or b
 static void cmat_mul(const double* a, const double* b, int dim, double* out) {
   for (int r = 0; r < dim; r++)
@@ -1103,8 +1141,24 @@ static int lower_pass(PassDesc& d, PassPlan& plan, int n, const int32_t* tile_qu
       for (int j = i + 1; j < n_in; j++) {
         if (used[j]) continue;
         const HostOp& oj = hops_in[j];
-        if (oj.kind == QSV_GATE_DENSE2 && !(oj.touch & touched) && (oj.touch & cur_touch) &&
+        // any later gate that acts inside the block's bits is multiplied in (free: the block's cost does not
+        // depend on its matrix); a 2-qubit gate that shares a bit may grow a 2-bit block to three bits
+        const bool one_q = oj.kind == QSV_GATE_DENSE1 || oj.kind == QSV_GATE_DIAG1;
+        const bool inside = (oj.touch & ~cur_touch) == 0;
+        if (!(oj.touch & touched) && (oj.touch & cur_touch) && (inside || (!one_q && nb == 2)) &&
             popc_u(oj.touch | cur_touch) <= 3) {
+          double dense[32];
+          op_as_dense(oj.kind, mats_in + oj.moff, dense);
+          if (one_q) {
+            int pa = 0;
+            for (int k = 0; k < nb; k++)
+              if (ub[k] == oj.t0) pa = k;
+            embed_gate1(dense, nb, pa, emb);
+            cmat_mul(emb, cur, 1 << nb, tmp);
+            memcpy(cur, tmp, sizeof(double) * 2 * (1 << nb) * (1 << nb));
+            used[j] = true;
+            continue;
+          }
           if (popc_u(oj.touch | cur_touch) == 3 && nb == 2) {  // grow to three bits
             for (int q = 0; q < 32; q++) tmp[q] = cur[q];
             embed_gate(tmp, 3, 0, 1, cur);
@@ -1117,7 +1171,7 @@ static int lower_pass(PassDesc& d, PassPlan& plan, int n, const int32_t* tile_qu
             if (ub[k] == oj.t0) pa = k;
             if (ub[k] == oj.t1) pb2 = k;
           }
-          embed_gate(mats_in + oj.moff, nb, pa, pb2, emb);
+          embed_gate(dense, nb, pa, pb2, emb);
           cmat_mul(emb, cur, 1 << nb, tmp);
           memcpy(cur, tmp, sizeof(double) * 2 * (1 << nb) * (1 << nb));
           used[j] = true;
