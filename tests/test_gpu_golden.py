@@ -35,13 +35,59 @@ def test_bell_config1():
     assert res["results"][0]["data"]["counts"] == {"0x0": 511, "0x3": 513}
 
 
-@pytest.mark.parametrize("n", [26, 28])
+def _fits(n):
+    import gc
+
+    import torch
+
+    gc.collect()
+    torch.cuda.empty_cache()
+    free, _total = torch.cuda.mem_get_info()
+    return (16 << n) + (6 << 30) < free
+
+
+@pytest.mark.parametrize("n", [24, 30, 33])
+def test_qft_known_answer_at_full_size(n):
+    """A known-answer test that scales: the QFT circuit of BASELINE config 2's family (basis gates, final swaps)
+    maps |x> to the DFT column  amp[y] = exp(2 pi i x y / 2^n) / 2^(n/2)  -- checked here up to the 33-qubit
+    register of BASELINE config 4 (128 GiB, ~2700 instructions) on 512 sampled amplitudes, plus the norm."""
+    import torch
+
+    from qiskit_sdk_py_b200 import lower
+    from qiskit_sdk_py_b200.engine import DeviceState
+
+    if not _fits(n):
+        pytest.skip("not enough device memory for %d qubits" % n)
+    rng = np.random.RandomState(n)
+    x = int(rng.randint(1, 2 ** 31)) | (1 << (n - 1)) | 1
+    x &= (1 << n) - 1
+    ins = [{"name": "x", "qubits": [q]} for q in range(n) if (x >> q) & 1]
+    ins += circuits.qft(n)["experiments"][0]["instructions"]
+    ops = [o for o in (lower.lower_gate(i["name"], i["qubits"], i.get("params")) for i in ins) if o is not None]
+    st = DeviceState(n)
+    st.init_basis0()
+    st.apply_ops(ops)
+    assert st.passes_launched <= 20
+    assert abs(st.norm2() - 1.0) < 1e-10
+    ys = [0, 1, 2, (1 << n) - 1, 1 << (n - 1)] + [int(v) for v in rng.randint(0, 2 ** 31, 507) * 5 % (1 << n)]
+    idx = torch.tensor([2 * y for y in ys] + [2 * y + 1 for y in ys], dtype=torch.int64, device=st.state.device)
+    vals = st.state.index_select(0, idx).cpu().numpy()
+    got = vals[: len(ys)] + 1j * vals[len(ys):]
+    frac = np.array([((x * y) % (1 << n)) / float(1 << n) for y in ys])  # exact integer arithmetic for the phase
+    want = np.exp(2j * np.pi * frac) / np.sqrt(float(1 << n))
+    assert np.max(np.abs(got - want)) * np.sqrt(float(1 << n)) < 1e-9   # relative to the amplitude modulus
+    assert np.max(np.abs(got - want)) < helpers.AMP_TOL
+
+
+@pytest.mark.parametrize("n", [26, 28, 33])
 def test_large_properties(n):
     """Sizes beyond the reference's 24-qubit cap: norm preservation and the inverse-circuit echo
     (SURVEY 8(d) config 4 correctness plan)."""
     from qiskit_sdk_py_b200.engine import DeviceState
     from qiskit_sdk_py_b200 import lower
 
+    if not _fits(n):
+        pytest.skip("not enough device memory for %d qubits" % n)
     ins = circuits.quantum_volume_instructions(n, 4, seed=99)
     ops = [lower.lower_gate(i["name"], i["qubits"], i.get("params")) for i in ins]
     st = DeviceState(n)
