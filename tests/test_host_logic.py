@@ -65,8 +65,9 @@ def _permute_bits(vec, n, tile, dest):
     return np.ascontiguousarray(t.transpose(axes)).reshape(-1)
 
 
+@pytest.mark.parametrize("tails", [False, True])
 @pytest.mark.parametrize("n,tile", [(9, 6), (12, 8), (14, 11)])
-def test_planner_remap_and_restore(n, tile):
+def test_planner_remap_and_restore(n, tile, tails):
     """Passes with write-back qubit permutations (qsv_apply_pass_remap) + plan_restore, simulated
     physically with numpy: the result must equal the plain logical simulation."""
     from oracle import basicaer_oracle as orc
@@ -90,13 +91,19 @@ def test_planner_remap_and_restore(n, tile):
     for op in ops:
         ref = apply(ref, op)
     layout = list(range(n))
-    passes = plan_passes(ops, n, tile, layout=layout, remap=True)
+    passes = plan_passes(ops, n, tile, layout=layout, remap=True, tails=tails)
     assert any(p.dest for p in passes)
+    if tails and tile <= 6:
+        assert any(p.tail for p in passes)
     phys = vec0.copy()
     for p in passes + plan_restore(layout, n, tile):
         assert len(p.tile_qubits) == tile and {0, 1, 2, 3} <= set(p.tile_qubits)
         for op in p.ops:
             assert set(op.qubits) <= set(p.tile_qubits)
+            phys = apply(phys, op)
+        for op in p.tail:  # diagonal gates with a qubit outside the tile (or 1-qubit), after the pass's gates
+            assert op.kind in (_lib.GATE_DIAG1, _lib.GATE_DIAG2)
+            assert len(op.qubits) == 1 or not set(op.qubits) <= set(p.tile_qubits)
             phys = apply(phys, op)
         if p.dest:
             assert sorted(p.dest) == sorted(p.tile_qubits)
