@@ -9,7 +9,7 @@
 //
 // Kernel structure (tile_pass_kernel):
 //   * persistent: 2-4 CTAs per SM (one warp per 2^8 amplitudes of the tile), each walking a contiguous
-//     range of tiles with one tile buffer; while one CTA waits for HBM (cp.async load, write-back) the
+//     range of tiles with one tile buffer; while one CTA waits for HBM (TMA bulk load, write-back) the
 //     others run their gates, so memory phases overlap FP64 / shared-memory phases across CTAs;
 //   * the gates of a pass are grouped into STAGES.  In a stage every warp owns a sub-cube of 2^8
 //     amplitudes of the tile (8 "inner" tile bits; the warp id supplies the others) and applies all
@@ -22,7 +22,17 @@
 //     output amplitude, i.e. one 16-byte shared-memory store.  (Measured on B200: DMMA 37 TF/s, DFMA
 //     34 TF/s, no gain from mixing them -- tools/fp64_peak.cu -- but DMMA needs 8x fewer instructions
 //     and 2 registers of gate matrix per lane instead of 64.)
-//   * all index maps are linear over GF(2) (XOR masks), including a pass-specific bank swizzle.
+//   * on the host, pairs of 2-qubit gates that share a qubit are fused into 3-qubit blocks (8x8 complex =
+//     16x16 real: 8 DMMA per 64 amplitudes): the same FP64 work as the two gates but one shared-memory
+//     round trip instead of two, which is what bounds a single gate;
+//   * diagonal gates never touch the tensor path: runs of them are folded on the host into lookup tables
+//     over the tile bits they touch (one look-up + one complex multiply per amplitude per run), and
+//     diagonal gates on qubits OUTSIDE the tile ride along as the pass's "tail" (TailDesc): outside the
+//     tile a qubit is a constant bit of the tile's base address;
+//   * every index map is a sum of per-bit increments (padded shared-memory layout, see pad_of_bit).
+//
+// QSV_DEBUG_FLAGS (environment, profiling experiments only): 1 no write-back, 2 no loads, 4 no gates,
+// 8 no gate-pair fusion, 32 no L2 prefetch, 64 no diagonal-run tables.
 #include <stdlib.h>
 #include <string.h>
 
