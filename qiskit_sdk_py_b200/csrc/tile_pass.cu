@@ -238,6 +238,7 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
   __shared__ double2 tail_f[16][2];          // per tile: factor pair of every tile bit; [b] = scalar
   __shared__ double2 tail_tab[2][64];        // per tile: the two tables of the diagonal tail
   __shared__ uint16_t tail_ix[2][56];
+  __shared__ uint8_t tail_pk[2][kMaxTail];   // row-selecting physical bits of the tail entries
 
   const uint32_t tid = threadIdx.x;
   const uint32_t dbg = d.flags;  // 1 = no write-back, 2 = no loads, 4 = no gates
@@ -329,6 +330,10 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
   for (int idx = tid; d.tail.n && idx < 112; idx += kPT) {
     const int g2 = idx / 56, x = idx % 56;
     tail_ix[g2][x] = x < kWarps ? d.tail.xw[g2][x] : x < kWarps + 32 ? d.tail.xl[g2][x - kWarps] : d.tail.xit[g2][x - kWarps - 32];
+  }
+  for (int idx = tid; idx < d.tail.n; idx += kPT) {
+    tail_pk[0][idx] = d.tail.pk[idx];
+    tail_pk[1][idx] = d.tail.pk2[idx];
   }
   // bulk-copy pieces of this thread: piece p covers tile-local bits [0, pb); its index bits are the
   // tile-local bits pb.. ; thread t owns pieces t, t + kPT, ...
@@ -601,34 +606,42 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
 
     // ---- diagonal tail (see TailDesc): per-tile factors -> two small tables -> one sweep over the tile ----
     if (d.tail.n && !(dbg & 4u)) {
-      // (1) factor pair of every tile bit and the scalar: one warp per range, lanes over its entries
-      for (int jj = wid; jj <= b; jj += (int)(kPT >> 5)) {
-        double2 f0 = make_double2(1.0, 0.0), f1 = make_double2(1.0, 0.0);
-        const int e_begin = d.tail.start[jj], e_end = d.tail.start[jj + 1];
-        for (int e0 = e_begin; e0 < e_end; e0 += 32) {
-          const int e = e0 + (int)lane;
-          if (e < e_end) {
-            const uint32_t k1 = d.tail.pk[e], k2 = d.tail.pk2[e];
-            const uint32_t r1 = k1 == 0xffu ? 0u : (uint32_t)((base >> k1) & 1ull);
-            const uint32_t r2 = k2 == 0xffu ? 0u : (uint32_t)((base >> k2) & 1ull);
-            const double2* ent = tail_ent + (size_t)e * 4;
-            if (jj < b) {  // entry = [row][bit of the tile qubit]
-              f0 = cmul(ent[2 * r1], f0);
-              f1 = cmul(ent[2 * r1 + 1], f1);
-            } else {       // scalar entry = [row][second row]
-              f0 = cmul(ent[2 * r1 + r2], f0);
+      // (1) factor pair of every tile bit and the scalar: one HALF warp per range, its 16 lanes over the
+      // range's entries, then a shuffle product inside the half warp
+      {
+        const int half = (int)(lane >> 4), hl = (int)(lane & 15u), n_hw = 2 * (int)(kPT >> 5);
+        for (int jj0 = 0; jj0 <= b; jj0 += n_hw) {
+          const int jj = jj0 + 2 * (int)wid + half;
+          const bool live = jj <= b;
+          double2 f0 = make_double2(1.0, 0.0), f1 = make_double2(1.0, 0.0);
+          const int e_begin = live ? d.tail.start[jj] : 0, e_end = live ? d.tail.start[jj + 1] : 0;
+          for (int e0 = e_begin;; e0 += 16) {
+            const int e = e0 + hl;
+            const bool act = e < e_end;
+            if (!__any_sync(0xffffffffu, act)) break;
+            if (act) {
+              const uint32_t k1 = tail_pk[0][e], k2 = tail_pk[1][e];
+              const uint32_t r1 = k1 == 0xffu ? 0u : (uint32_t)((base >> k1) & 1ull);
+              const uint32_t r2 = k2 == 0xffu ? 0u : (uint32_t)((base >> k2) & 1ull);
+              const double2* ent = tail_ent + (size_t)e * 4;
+              if (jj < b) {  // entry = [row][bit of the tile qubit]
+                f0 = cmul(__ldg(ent + 2 * r1), f0);
+                f1 = cmul(__ldg(ent + 2 * r1 + 1), f1);
+              } else {       // scalar entry = [row][second row]
+                f0 = cmul(__ldg(ent + 2 * r1 + r2), f0);
+              }
             }
           }
-        }
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-          double2 g0, g1;
-          g0.x = __shfl_xor_sync(0xffffffffu, f0.x, off); g0.y = __shfl_xor_sync(0xffffffffu, f0.y, off);
-          g1.x = __shfl_xor_sync(0xffffffffu, f1.x, off); g1.y = __shfl_xor_sync(0xffffffffu, f1.y, off);
-          f0 = cmul(g0, f0);
-          f1 = cmul(g1, f1);
+          for (int off = 8; off > 0; off >>= 1) {
+            double2 g0, g1;
+            g0.x = __shfl_xor_sync(0xffffffffu, f0.x, off); g0.y = __shfl_xor_sync(0xffffffffu, f0.y, off);
+            g1.x = __shfl_xor_sync(0xffffffffu, f1.x, off); g1.y = __shfl_xor_sync(0xffffffffu, f1.y, off);
+            f0 = cmul(g0, f0);
+            f1 = cmul(g1, f1);
+          }
+          if (live && hl == 0) { tail_f[jj][0] = f0; tail_f[jj][1] = f1; }
         }
-        if (lane == 0) { tail_f[jj][0] = f0; tail_f[jj][1] = f1; }
       }
       __syncthreads();
       // (2) tables over the two groups of tile bits (the scalar goes into the first)
