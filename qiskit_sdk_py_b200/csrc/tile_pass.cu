@@ -193,6 +193,13 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
                : "d"(a), "d"(b));
 }
 
+// D(8x8) = A(8x4) * B(4x8) + C with C kept (the accumulator input is a different register pair)
+__device__ __forceinline__ void dmma884_c(double& d0, double& d1, double a, double b, double c0, double c1) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};\n"
+               : "=d"(d0), "=d"(d1)
+               : "d"(a), "d"(b), "d"(c0), "d"(c1));
+}
+
 // physical base address (in amplitudes) of tile t: spread t over the non-tile bits
 __device__ __forceinline__ u64 tile_base(const PassDesc& d, u64 t) {
   for (int j = 0; j < d.b; j++) {
@@ -288,20 +295,22 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
     if ((op.kind == QSV_GATE_DIAG1 || op.kind == QSV_GATE_DIAG2) && e >= 48 && e < 56)
       frag[op.foff * 64 + (e - 48)] = (op.kind == QSV_GATE_DIAG2 || e - 48 < 4) ? d.mats[op.moff + (e - 48)] : 0.0;
   }
-  // B fragments of fused 3-qubit blocks: the 8x8 complex block is the 16x16 real matrix [[Re,-Im],[Im,Re]];
-  // fragment (h, s) -- output half h, k-slice s -- holds Mreal[n = 8 h + (l >> 2)][k = 4 s + (l & 3)] in lane l
-  for (int idx = tid; idx < nops * 256; idx += kPT) {
-    const int o = idx >> 8, e = idx & 255;
+  // B fragments of fused 3-qubit blocks, 3-multiplication form of the complex product (M = P + iQ, amplitudes
+  // x + iy):  k1 = P (x + y),  re = k1 - (P + Q) y,  im = k1 + (Q - P) x  -- three real 8x8 products (6 DMMA per
+  // 64 amplitudes) instead of the 16x16 real matrix [[P,-Q],[Q,P]] (8 DMMA).  Fragment f = 2 p + s: product p
+  // (0: P, 1: -(P+Q), 2: Q-P), k-slice s; lane l holds Mp[row(n = l >> 2)][4 s + (l & 3)], where column n of
+  // the accumulator is output amplitude (n >> 1) + 4 (n & 1): a lane's two accumulator columns then differ in
+  // the block's third bit and its quad position gives the two low bits, as in the A operand.
+  for (int idx = tid; idx < nops * 192; idx += kPT) {
+    const int o = idx / 192, e = idx - 192 * o;
     const PassOp& op = d.ops[o];
     if (op.kind != kGateDense3) continue;
-    const int h = e >> 7, sl = (e >> 5) & 3, l = e & 31;
-    const int nrow = 8 * h + (l >> 2), kcol = 4 * sl + (l & 3);
-    const int r = nrow >> 1, c = kcol >> 1;
+    const int f = e >> 5, l = e & 31;
+    const int p = f >> 1, sl = f & 1;
+    const int nn = l >> 2;
+    const int r = (nn >> 1) + 4 * (nn & 1), c = 4 * sl + (l & 3);
     const double* m = d.mats + op.moff + 2 * (8 * r + c);
-    double v;
-    if ((nrow & 1) == 0) v = (kcol & 1) == 0 ? m[0] : -m[1];
-    else v = (kcol & 1) == 0 ? m[1] : m[0];
-    frag[op.foff * 64 + e] = v;
+    frag[op.foff * 64 + e] = p == 0 ? m[0] : p == 1 ? -(m[0] + m[1]) : m[1] - m[0];
   }
   for (int idx = tid; idx < nstages * 64; idx += kPT) {
     const int sidx = idx >> 6, e = idx & 63;
@@ -472,40 +481,39 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
           }
         } else if (rec.kind == kGateDense3) {
           // ---- fused pair of 2-qubit gates sharing a qubit: one 8x8 complex block per 8 amplitudes, i.e. one
-          // shared-memory round trip for two gates at the same FP64 work (8 DMMA per 64 amplitudes) ----
+          // shared-memory round trip for two gates, in the 3-multiplication form (see the fragment set-up):
+          // per 64 amplitudes 2 LDS.128 + 2 DADD + 6 DMMA + 2 STS.128 per lane.  Lane (g, c) reads amplitude c
+          // (bits t0, t1) of the two halves (bit t2) of group g and writes the same two slots. ----
           const double* fr = frag + (uint32_t)rec.moff * 64u;
-          double bq[8];
+          double bq[6];
 #pragma unroll
-          for (int q = 0; q < 8; q++) bq[q] = fr[q * 32 + lane];
+          for (int q = 0; q < 6; q++) bq[q] = fr[q * 32 + lane];
           const uint32_t v = opl[o][lane];
-          const uint32_t a_ld = (s_w + (v & 0xffffu)) << 4;
-          const uint32_t a_st = (s_w + (v >> 16)) << 4;
-          const uint32_t z1b = (uint32_t)rec.z1 << 4, z2b = (uint32_t)rec.c5 << 4;
+          char* const ta = reinterpret_cast<char*>(tile) + ((s_w + (v >> 16)) << 4);
+          const uint32_t z2b = (uint32_t)rec.c5 << 4;
           const uint32_t c3 = (uint32_t)rec.c3 << 4, c4 = (uint32_t)rec.c4 << 4;
           if (rec.ngl == 5u) {
 #pragma unroll
             for (int hb = 0; hb < 2; hb++) {
               const uint32_t xh = hb ? c4 : 0u;
               const uint32_t xo[2] = {xh, xh + c3};
-              double x[2][4];
+              double2 u0[2], u1[2];
 #pragma unroll
               for (int it = 0; it < 2; it++) {
-                const uint32_t a = a_ld + xo[it];
-                x[it][0] = *reinterpret_cast<const double*>(tb8 + a);
-                x[it][1] = *reinterpret_cast<const double*>(tb8 + (a + z1b));
-                x[it][2] = *reinterpret_cast<const double*>(tb8 + (a + z2b));
-                x[it][3] = *reinterpret_cast<const double*>(tb8 + (a + z1b + z2b));
+                u0[it] = *reinterpret_cast<const double2*>(ta + xo[it]);
+                u1[it] = *reinterpret_cast<const double2*>(ta + (xo[it] + z2b));
               }
 #pragma unroll
               for (int it = 0; it < 2; it++) {
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                  double d0 = 0.0, d1 = 0.0;
-#pragma unroll
-                  for (int sl = 0; sl < 4; sl++) dmma884(d0, d1, x[it][sl], bq[4 * h + sl]);
-                  *reinterpret_cast<double2*>(reinterpret_cast<char*>(tile) + (a_st + xo[it] + (h ? z2b : 0u))) =
-                      make_double2(d0, d1);
-                }
+                double k0 = 0.0, k1 = 0.0, r0, r1, i0, i1;
+                dmma884(k0, k1, u0[it].x + u0[it].y, bq[0]);
+                dmma884(k0, k1, u1[it].x + u1[it].y, bq[1]);
+                dmma884_c(r0, r1, u0[it].y, bq[2], k0, k1);
+                dmma884_c(i0, i1, u0[it].x, bq[4], k0, k1);
+                dmma884(r0, r1, u1[it].y, bq[3]);
+                dmma884(i0, i1, u1[it].x, bq[5]);
+                *reinterpret_cast<double2*>(ta + xo[it]) = make_double2(r0, i0);
+                *reinterpret_cast<double2*>(ta + (xo[it] + z2b)) = make_double2(r1, i1);
               }
             }
           } else {
@@ -516,22 +524,21 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
               if (it & 1u) xo += c3;
               if (it & 2u) xo += c4;
               const bool valid = (g | (it << 3)) < ng;
-              double x[4] = {0.0, 0.0, 0.0, 0.0};
+              double2 u0 = make_double2(0.0, 0.0), u1 = make_double2(0.0, 0.0);
               if (valid) {
-                const uint32_t a = a_ld + xo;
-                x[0] = *reinterpret_cast<const double*>(tb8 + a);
-                x[1] = *reinterpret_cast<const double*>(tb8 + (a + z1b));
-                x[2] = *reinterpret_cast<const double*>(tb8 + (a + z2b));
-                x[3] = *reinterpret_cast<const double*>(tb8 + (a + z1b + z2b));
+                u0 = *reinterpret_cast<const double2*>(ta + xo);
+                u1 = *reinterpret_cast<const double2*>(ta + (xo + z2b));
               }
-#pragma unroll
-              for (int h = 0; h < 2; h++) {
-                double d0 = 0.0, d1 = 0.0;
-#pragma unroll
-                for (int sl = 0; sl < 4; sl++) dmma884(d0, d1, x[sl], bq[4 * h + sl]);
-                if (valid)
-                  *reinterpret_cast<double2*>(reinterpret_cast<char*>(tile) + (a_st + xo + (h ? z2b : 0u))) =
-                      make_double2(d0, d1);
+              double k0 = 0.0, k1 = 0.0, r0, r1, i0, i1;
+              dmma884(k0, k1, u0.x + u0.y, bq[0]);
+              dmma884(k0, k1, u1.x + u1.y, bq[1]);
+              dmma884_c(r0, r1, u0.y, bq[2], k0, k1);
+              dmma884_c(i0, i1, u0.x, bq[4], k0, k1);
+              dmma884(r0, r1, u1.y, bq[3]);
+              dmma884(i0, i1, u1.x, bq[5]);
+              if (valid) {
+                *reinterpret_cast<double2*>(ta + xo) = make_double2(r0, i0);
+                *reinterpret_cast<double2*>(ta + (xo + z2b)) = make_double2(r1, i1);
               }
             }
           }
