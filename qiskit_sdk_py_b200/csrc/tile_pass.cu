@@ -221,18 +221,39 @@ struct __align__(16) OpRec {
 // run their gates, so the memory phases of one overlap the FP64 / shared-memory phases of the others.
 // A CTA owns a contiguous range of tiles.  The tile moves between HBM and shared memory with TMA bulk
 // copies of 256-byte pieces (one per two threads), which bypass the LSU/L1TEX pipe that the gates saturate.
+//
+// kG = 1: the CTA is one group of threads with ONE tile buffer (2-4 CTAs per SM).
+// kG = 3: one CTA per SM holds three independent warp GROUPS of 256 threads (named barriers), each with TWO
+// tile buffers, and all groups share the pass's read-only tables, which is what makes six 35 KiB buffers fit
+// in 227 KiB.  A group loads tile t+1 into its other buffer while it applies the gates of tile t, and the
+// write-back of tile t drains while tile t+1 is computed: neither the HBM load latency nor the store drain
+// is on the group's critical path, so the FP64 / shared-memory pipes stay busy.  Every thread loads and
+// stores the SAME shared-memory piece, so a buffer is recycled without any group-wide barrier: a thread waits
+// for its own store to have been read out (bulk wait_group.read) and then issues its own load.
+template <int kG>
 __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const PassDesc& d,
                                                const double2* __restrict__ tail_ent) {
-  // dynamic shared memory: the (padded) tile, then the per-pass tables (sized by the pass, so that short
-  // passes leave room for more resident CTAs)
-  extern __shared__ double2 tile[];
-  __shared__ __align__(8) uint64_t ld_bar;
+  // dynamic shared memory: the (padded) tile buffers, then the per-pass tables (sized by the pass, so that
+  // short passes leave room for more resident CTAs)
+  extern __shared__ double2 bufs[];
+  constexpr bool kDB = kG > 1;
+  constexpr int kBuf = kDB ? 2 : 1;
+  __shared__ __align__(8) uint64_t ld_bar[kG][kBuf];
   const int nops_all = d.nops, nst_all = d.nstages;
   const int b = d.b;
   const uint32_t tile_amps = 1u << b;
   uint32_t tile_slots = tile_amps;
   for (int j = 4; j < b; j++) tile_slots += pad_of_bit(j);
-  double* frag = reinterpret_cast<double*>(tile + tile_slots);                  // [nfrag][64] B fragments
+  const uint32_t ctid = threadIdx.x, cthreads = blockDim.x;  // CTA-wide (table set-up)
+  const uint32_t grp = kDB ? ctid >> 8 : 0u;                 // warp group
+  const uint32_t tid = kDB ? (ctid & 255u) : ctid;           // thread within the group
+  const uint32_t kPT = kDB ? 256u : cthreads;                // threads per group
+  double2* tile = bufs + (size_t)(grp * kBuf) * tile_slots;  // the group's current tile buffer
+  auto gsync = [&]() {
+    if constexpr (kDB) asm volatile("bar.sync %0, 256;\n" ::"r"(grp + 1u) : "memory");
+    else __syncthreads();
+  };
+  double* frag = reinterpret_cast<double*>(bufs + (size_t)(kG * kBuf) * tile_slots);  // [nfrag][64] B fragments
   OpRec* oprec = reinterpret_cast<OpRec*>(frag + (size_t)d.nfrag * 64);         // [nops]
   uint32_t (*opl)[32] = reinterpret_cast<uint32_t (*)[32]>(oprec + nops_all);   // [nops][32] lane slots
   uint32_t (*st_warp)[kWarps] = reinterpret_cast<uint32_t (*)[kWarps]>(opl + nops_all);  // [nstages][16]
@@ -242,22 +263,23 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
   const uintptr_t run_base = (reinterpret_cast<uintptr_t>(st_it + nst_all) + 15u) & ~(uintptr_t)15u;
   double2 (*runtab)[1 << kRunBits] = reinterpret_cast<double2 (*)[1 << kRunBits]>(run_base);
   uint16_t (*runix)[56] = reinterpret_cast<uint16_t (*)[56]>(runtab + d.nruns);
-  __shared__ double2 tail_f[16][2];          // per tile: factor pair of every tile bit; [b] = scalar
-  __shared__ double2 tail_tab[2][64];        // per tile: the two tables of the diagonal tail
+  __shared__ double2 tail_f_all[kG][16][2];    // per tile: factor pair of every tile bit; [b] = scalar
+  __shared__ double2 tail_tab_all[kG][2][64];  // per tile: the two tables of the diagonal tail
+  double2 (*tail_f)[2] = tail_f_all[grp];
+  double2 (*tail_tab)[64] = tail_tab_all[grp];
   __shared__ uint16_t tail_ix[2][56];
   __shared__ uint8_t tail_pk[2][kMaxTail];   // row-selecting physical bits of the tail entries
 
-  const uint32_t tid = threadIdx.x;
   const uint32_t dbg = d.flags;  // 1 = no write-back, 2 = no loads, 4 = no gates
   const int nops = d.nops, nstages = (dbg & 4u) ? 0 : d.nstages;
-  const uint32_t kPT = blockDim.x;
 
   // ---- per-kernel setup (amortised over all tiles of this CTA): every lane/warp dependent index of
   // the pass is tile-invariant, so it is digested once into shared-memory tables / registers ----
   u64 tile_mask = 0;  // physical bit mask of the tile qubits
   for (int j = 0; j < b; j++) tile_mask |= 1ull << d.tb[j];
-  if (tid == 0) mbar_init(&ld_bar, kPT);
-  for (int idx = tid; idx < nops * 64; idx += kPT) {
+  if (ctid == 0)
+    for (int q = 0; q < kG * kBuf; q++) mbar_init(&ld_bar[0][0] + q, kPT);
+  for (int idx = ctid; idx < nops * 64; idx += cthreads) {
     const int o = idx >> 6, e = idx & 63;
     const PassOp& op = d.ops[o];
     if (op.kind == QSV_GATE_DENSE2) {
@@ -301,7 +323,7 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
   // (0: P, 1: -(P+Q), 2: Q-P), k-slice s; lane l holds Mp[row(n = l >> 2)][4 s + (l & 3)], where column n of
   // the accumulator is output amplitude (n >> 1) + 4 (n & 1): a lane's two accumulator columns then differ in
   // the block's third bit and its quad position gives the two low bits, as in the A operand.
-  for (int idx = tid; idx < nops * 192; idx += kPT) {
+  for (int idx = ctid; idx < nops * 192; idx += cthreads) {
     const int o = idx / 192, e = idx - 192 * o;
     const PassOp& op = d.ops[o];
     if (op.kind != kGateDense3) continue;
@@ -312,7 +334,7 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
     const double* m = d.mats + op.moff + 2 * (8 * r + c);
     frag[op.foff * 64 + e] = p == 0 ? m[0] : p == 1 ? -(m[0] + m[1]) : m[1] - m[0];
   }
-  for (int idx = tid; idx < nstages * 64; idx += kPT) {
+  for (int idx = ctid; idx < nstages * 64; idx += cthreads) {
     const int sidx = idx >> 6, e = idx & 63;
     const PassStage& st = d.stages[sidx];
     uint32_t li = 0, sl = 0;
@@ -330,17 +352,17 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
       st_lane[sidx][e - 32] = li | (sl << 16);
     }
   }
-  for (int idx = tid; idx < d.nruns * (1 << kRunBits); idx += kPT) {
+  for (int idx = ctid; idx < d.nruns * (1 << kRunBits); idx += cthreads) {
     const int r = idx >> kRunBits, x = idx & ((1 << kRunBits) - 1);
     const DiagRun& run = d.runs[r];
     if (x < (1 << run.nbits)) runtab[r][x] = make_double2(d.mats[run.moff + 2 * x], d.mats[run.moff + 2 * x + 1]);
     if (x < 56) runix[r][x] = x < kWarps ? run.xw[x] : x < kWarps + 32 ? run.xl[x - kWarps] : run.xit[x - kWarps - 32];
   }
-  for (int idx = tid; d.tail.n && idx < 112; idx += kPT) {
+  for (int idx = ctid; d.tail.n && idx < 112; idx += cthreads) {
     const int g2 = idx / 56, x = idx % 56;
     tail_ix[g2][x] = x < kWarps ? d.tail.xw[g2][x] : x < kWarps + 32 ? d.tail.xl[g2][x - kWarps] : d.tail.xit[g2][x - kWarps - 32];
   }
-  for (int idx = tid; idx < d.tail.n; idx += kPT) {
+  for (int idx = ctid; idx < d.tail.n; idx += cthreads) {
     tail_pk[0][idx] = d.tail.pk[idx];
     tail_pk[1][idx] = d.tail.pk2[idx];
   }
@@ -372,36 +394,71 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
   const bool pf_on = !(dbg & 32u) && pc_ld0 < np_ld && (ld_bytes >> sh_ld) != 0u;
   const uint32_t lane = tid & 31u, wid = tid >> 5;
   const uint32_t g = lane >> 2;
-  const char* tb8 = reinterpret_cast<const char*>(tile) + (lane & 1u) * 8u;
+  const char* tb8 = reinterpret_cast<const char*>(tile) + (lane & 1u) * 8u;  // (re-pointed per tile when kDB)
   fence_proxy_async();  // make the mbarrier initialisation visible to the async proxy
   __syncthreads();
 
-  // contiguous range of tiles for this CTA; the tile base walks the non-tile bits: next = ((base | M) + 1) & ~M
+  // contiguous range of tiles for this group; the tile base walks the non-tile bits: next = ((base | M) + 1) & ~M
   const u64 n_tiles = d.n_tiles;
-  const u64 per = (n_tiles + gridDim.x - 1) / gridDim.x;
-  const u64 t_begin = (u64)blockIdx.x * per;
+  const u64 n_groups = (u64)gridDim.x * kG;
+  const u64 per = (n_tiles + n_groups - 1) / n_groups;
+  const u64 t_begin = ((u64)blockIdx.x * kG + grp) * per;
   const u64 t_end = t_begin + per < n_tiles ? t_begin + per : n_tiles;
   u64 base = t_begin < n_tiles ? tile_base(d, t_begin) : 0;
   uint32_t parity = 0;
-  for (u64 t = t_begin; t < t_end; t++, base = ((base | tile_mask) + 1) & ~tile_mask) {
+  if constexpr (kDB) {  // prologue: the first tile goes into buffer 0
+    if (ld_on && t_begin < t_end) {
+      mbar_arrive_expect_tx(&ld_bar[grp][0], my_ld_bytes);
+      if (own_ld) bulk_load(tile + s_ld0, sv + base + g_ld0, ld_bytes, &ld_bar[grp][0]);
+    }
+  }
+  uint32_t t_idx = 0;
+  for (u64 t = t_begin; t < t_end; t++, t_idx++, base = ((base | tile_mask) + 1) & ~tile_mask) {
+    bool next_issued = true;
+    // kDB: load of the group's NEXT tile into its other buffer, issued by every thread for its own piece once
+    // its write-back piece of the previous tile has left that buffer (no barrier needed, see above)
+    auto issue_next = [&]() {
+      if constexpr (kDB) {
+        bulk_wait_read();
+        const u64 nb = ((base | tile_mask) + 1) & ~tile_mask;
+        const uint32_t nxt = (t_idx & 1u) ^ 1u;
+        mbar_arrive_expect_tx(&ld_bar[grp][nxt], my_ld_bytes);
+        if (own_ld)
+          bulk_load(bufs + (size_t)(grp * kBuf + nxt) * tile_slots + s_ld0, sv + nb + g_ld0, ld_bytes, &ld_bar[grp][nxt]);
+        next_issued = true;
+      }
+    };
+    if constexpr (kDB) {
+      // ---- this tile was requested one tile ago ----
+      const uint32_t cur = t_idx & 1u;
+      tile = bufs + (size_t)(grp * kBuf + cur) * tile_slots;
+      tb8 = reinterpret_cast<const char*>(tile) + (lane & 1u) * 8u;
+      if (ld_on) {
+        if (wid == 0) mbar_wait(&ld_bar[grp][cur], (t_idx >> 1) & 1u);
+        gsync();
+      }
+      next_issued = !(ld_on && t + 1 < t_end);
+      if (nstages == 0 && !next_issued) issue_next();
+    }
     // ---- load: one HBM read of the tile (TMA bulk copies, completion on the mbarrier) ----
-    if (t != t_begin) {
+    if (!kDB && t != t_begin) {
       bulk_wait_read();   // my write-back pieces of the previous tile have left shared memory
       __syncthreads();    // ... and so have everybody else's
     }
-    if (ld_on) {
-      mbar_arrive_expect_tx(&ld_bar, my_ld_bytes);
-      if (own_ld) bulk_load(tile + s_ld0, sv + base + g_ld0, ld_bytes, &ld_bar);
+    if (!kDB && ld_on) {
+      uint64_t* const bar = &ld_bar[0][0];
+      mbar_arrive_expect_tx(bar, my_ld_bytes);
+      if (own_ld) bulk_load(tile + s_ld0, sv + base + g_ld0, ld_bytes, bar);
       for (uint32_t pc = tid + kPT; pc < np_ld; pc += kPT) {  // small pieces only (tile without the low qubits)
         u64 go = 0;
         uint32_t so = 0;
         for (int j = 0; j + (int)pb_ld < b; j++)
           if ((pc >> j) & 1u) { go |= 1ull << d.tb[pb_ld + j]; so += d.cj[pb_ld + j]; }
-        bulk_load(tile + so, sv + base + go, ld_bytes, &ld_bar);
+        bulk_load(tile + so, sv + base + go, ld_bytes, bar);
       }
       // one warp polls the mbarrier (acquiring the TMA writes); everybody else parks on the hardware
       // barrier instead of burning issue slots that the other CTAs of this SM need for their gates
-      if (wid == 0) mbar_wait(&ld_bar, parity);
+      if (wid == 0) mbar_wait(bar, parity);
       parity ^= 1u;
       __syncthreads();
       // pull the next tile of this CTA into L2 while the gates run, so that its bulk load sees L2 latency
@@ -416,7 +473,7 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
 
     int o = 0;
     for (int sidx = 0; sidx < nstages; sidx++) {
-      if (sidx > 0) __syncthreads();  // stage boundary: warps re-partition the tile
+      if (sidx > 0) gsync();  // stage boundary: warps re-partition the tile
       const uint32_t n_inner = d.stages[sidx].n_inner, n_outer = d.stages[sidx].n_outer;
       const int o_end = o + d.stages[sidx].n_ops;
       const bool warp_on = wid < (1u << n_outer);  // small tiles: fewer sub-cubes than warps
@@ -608,8 +665,14 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
             }
           }
         }
+        // kDB: the first op of the tile is done, so the write-back of the previous tile has long left the
+        // other buffer: request the next tile now, it has the rest of this tile's gates to arrive
+        if constexpr (kDB)
+          if (!next_issued) issue_next();
       }
     }
+    if constexpr (kDB)
+      if (!next_issued) issue_next();
 
     // ---- diagonal tail (see TailDesc): per-tile factors -> two small tables -> one sweep over the tile ----
     if (d.tail.n && !(dbg & 4u)) {
@@ -650,7 +713,7 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
           if (live && hl == 0) { tail_f[jj][0] = f0; tail_f[jj][1] = f1; }
         }
       }
-      __syncthreads();
+      gsync();
       // (2) tables over the two groups of tile bits (the scalar goes into the first)
       for (int idx = tid; idx < 128; idx += kPT) {
         const int g2 = idx >> 6, x = idx & 63;
@@ -661,7 +724,7 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
           tail_tab[g2][x] = v;
         }
       }
-      __syncthreads();
+      gsync();
       // (3) sweep, in the element order of the last stage
       const int sl_idx = nstages - 1;
       if (wid < (1u << d.stages[sl_idx].n_outer)) {
@@ -683,7 +746,7 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
     // ---- write-back: one HBM write of the tile (TMA bulk copies), optionally with the tile qubits
     // permuted: position j receives the content of tile bit src_of[j] (a free qubit remap) ----
     fence_proxy_async();  // the gates' generic-proxy stores must be visible to the async proxy
-    __syncthreads();
+    gsync();
     if (st_on) {
       if (own_st) bulk_store(sv + base + g_st0, tile + s_st0, st_bytes);
       for (uint32_t pc = tid + kPT; pc < np_st; pc += kPT) {
@@ -701,10 +764,10 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
 
 // One body, three launch shapes: several resident CTAs per SM (4 x 256 threads for the default 11-qubit
 // tile) keep more tiles in flight, which is what hides the HBM round trip of each CTA.
-template <int kBlock, int kMinBlocks>
+template <int kBlock, int kMinBlocks, int kG = 1>
 __global__ void __launch_bounds__(kBlock, kMinBlocks)
 tile_pass_kernel(double2* __restrict__ sv, const __grid_constant__ PassDesc d, const double2* __restrict__ tail_ent) {
-  tile_pass_body(sv, d, tail_ent);
+  tile_pass_body<kG>(sv, d, tail_ent);
 }
 
 // ---- dense k-qubit gate, 3 <= k <= 12: out-of-place inside the tile (two smem buffers) ----
@@ -945,6 +1008,14 @@ static int build_stages(const HostOp* ops, int n_ops, int b, int* order, PassSta
   return n_stages;
 }
 
+// Three double-buffered warp groups per SM (see tile_pass_body) are used when the pass has the default
+// 11-qubit tile, enough tiles to fill the machine, an unpermuted write-back with one piece per thread at most
+// (a thread recycles the shared-memory piece it owns), and tables that fit beside six tile buffers.
+constexpr int kGroupTileQubits = 11;
+constexpr u64 kGroupMinTiles = 2048;
+constexpr size_t kGroupStaticSmem = 3 * 2 * 8 + 3 * 16 * 2 * 16 + 3 * 2 * 64 * 16 + 2 * 56 * 2 + 2 * kMaxTail;
+constexpr size_t kMaxSmemPerBlock = 232448;  // 227 KiB (sm_100 opt-in limit, static + dynamic)
+
 static bool g_attr_set[64] = {false};
 static int g_sm_count[64] = {0};
 
@@ -972,6 +1043,12 @@ static int ensure_attrs() {
     QSV_CUDA(cudaFuncSetAttribute(tile_pass_kernel<512, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     QSV_CUDA(cudaFuncSetAttribute(tile_pass_kernel<256, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     QSV_CUDA(cudaFuncSetAttribute(tile_pass_kernel<128, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    cudaFuncAttributes fa;
+    QSV_CUDA(cudaFuncGetAttributes(&fa, tile_pass_kernel<768, 1, 3>));
+    if (fa.sharedSizeBytes > kGroupStaticSmem + 64) return fail(QSV_ERANGE, "tile_pass_kernel<768,1,3>: static shared memory grew");
+    QSV_CUDA(cudaFuncSetAttribute(tile_pass_kernel<768, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(kMaxSmemPerBlock - fa.sharedSizeBytes)));
+    QSV_CUDA(cudaFuncSetAttribute(tile_pass_kernel<768, 1, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     QSV_CUDA(cudaFuncSetAttribute(dense_k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(2 * (sizeof(double2) << 12) + 4096 * sizeof(uint32_t))));
     g_attr_set[dev] = true;
@@ -982,7 +1059,9 @@ static int ensure_attrs() {
 struct PassPlan {
   size_t smem;
   int threads, n_in, n_fused3;
+  bool groups;  // three double-buffered warp groups per CTA (tile_pass_kernel<768, 1, 3>)
 };
+
 
 // Host-only lowering of a pass (no CUDA call): validates the arguments, fuses gates, builds the stages and
 // every index table of the kernel into `d`.
@@ -1565,6 +1644,18 @@ static int lower_pass(PassDesc& d, PassPlan& plan, int n, const int32_t* tile_qu
   // one warp per 2^8 amplitudes: 512 threads for b = 12, 256 for b = 11, ...; at least one warp
   plan.smem = smem;
   plan.threads = std::max(32, std::min(kMaxPT, 1 << std::max(0, b - 3)));
+  plan.groups = false;
+  if (b == kGroupTileQubits && d.n_tiles >= kGroupMinTiles && !(d.flags & 16u) && d.pb_ld == d.pb_st &&
+      ((size_t)1 << (b - d.pb_ld)) <= 256) {
+    bool ident = true;
+    for (int j = 0; j < b; j++) ident &= d.src_of[j] == j;
+    const size_t smem3 = smem + 5 * tile_slots * sizeof(double2);
+    if (ident && smem3 + kGroupStaticSmem + 64 <= kMaxSmemPerBlock) {
+      plan.groups = true;
+      plan.smem = smem3;
+      plan.threads = 768;
+    }
+  }
   plan.n_in = n_in;
   plan.n_fused3 = 0;
   for (int k = 0; k < n_gates; k++) plan.n_fused3 += d.ops[k].kind == kGateDense3;
@@ -1587,6 +1678,12 @@ static int launch_pass(double* sv, int n, const int32_t* tile_qubits, int n_tile
   const double2* d_tail = reinterpret_cast<const double2*>(dev_scratch);
   const size_t smem = plan.smem;
   const int threads = plan.threads;
+  if (plan.groups) {
+    const unsigned grid3 = std::min<unsigned>((d.n_tiles + 2) / 3, (unsigned)sm_count());
+    tile_pass_kernel<768, 1, 3><<<grid3, 768, smem, stream>>>(reinterpret_cast<double2*>(sv), d, d_tail);
+    QSV_LAUNCHED();
+    return 0;
+  }
   int per_sm = 1;
   if (threads >= 512) {
     QSV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tile_pass_kernel<512, 2>, threads, smem));

@@ -207,6 +207,50 @@ def test_pass_with_diagonal_tail(n, tile_size, n_ops, n_tail):
     assert np.max(np.abs(st.download() - ref)) < TOL
 
 
+@pytest.mark.parametrize("n,seed,n_tail", [(22, 1, 0), (22, 2, 25), (23, 3, 0), (24, 4, 60)])
+def test_group_kernel_passes(n, seed, n_tail, monkeypatch):
+    """Passes with an 11-qubit tile and >= 2048 tiles run on the three-group double-buffered variant of the pass
+    kernel (tile_pass_kernel<768,1,3>): same result as the oracle, and bit for bit the result of the
+    single-buffer variant (QSV_DEBUG_FLAGS=16), whose arithmetic per tile is identical."""
+    from qiskit_sdk_py_b200.engine import DeviceState
+
+    rng = np.random.RandomState(seed)
+    vec = rand_state(n, 40 + seed)
+    plan = []
+    for _ in range(3):
+        tile = [0, 1, 2, 3] + sorted(int(q) for q in rng.choice(np.arange(4, n), 7, replace=False))
+        ops = []
+        for _ in range(int(rng.randint(1, 9))):
+            a, b = (int(x) for x in rng.choice(tile, 2, replace=False))
+            pick = rng.randint(5)
+            if pick <= 1:
+                ops.append(GateOp(_lib.GATE_DENSE2, [a, b], rand_unitary(2, rng)))
+            elif pick == 2:
+                ops.append(GateOp(_lib.GATE_DIAG2, [a, b], np.exp(1j * rng.uniform(0, 6, 4))))
+            elif pick == 3:
+                ops.append(GateOp(_lib.GATE_DENSE1, [a], rand_unitary(1, rng)))
+            else:
+                ops.append(GateOp(_lib.GATE_CX, [a, b], None))
+        plan.append((tile, ops, _random_tail(n, tile, n_tail, rng)))
+    plan.append(([0, 1, 2, 3] + list(range(n - 7, n)), [], []))  # copy-only pass
+    results = []
+    for flags in ("0", "16"):
+        monkeypatch.setenv("QSV_DEBUG_FLAGS", flags)
+        for tile, ops, tail in plan:
+            assert DeviceState.pass_info(n, tile, ops)["threads"] == (768 if flags == "0" else 256)
+        st = make_state(n, vec)
+        for tile, ops, tail in plan:
+            st.apply_pass(tile, ops, tail=tail or None)
+        results.append(st.download())
+        del st
+    ref = vec.copy()
+    for tile, ops, tail in plan:
+        for op in ops + tail:
+            ref = oracle_apply(ref, op, n)
+    assert np.max(np.abs(results[0] - ref)) < TOL
+    assert np.array_equal(results[0], results[1])
+
+
 def test_tail_argument_errors():
     st = make_state(10, rand_state(10, 1))
     tile = list(range(8))
