@@ -293,6 +293,27 @@ def main():
     assert abs(total - 1.0) < 1e-9, total
     counts_top = int(np.bincount(samples % 4096).max())
 
+    # FP64 work of the pass launches.  `nominal`: 32 flop per amplitude per SU(4) gate (a 4x4 complex matrix on
+    # groups of 4 amplitudes).  `executed`: what the kernel issues after gate fusion -- a lone 2-qubit op is 2
+    # DMMA.8x8x4 per 32 amplitudes (32 flop/amplitude); a fused 3-qubit block (two or more gates) in the
+    # 3-multiplication form is 6 DMMA + 2 DADD per 64 amplitudes (49 flop/amplitude).
+    infos = [DeviceState.pass_info(n, p.tile_qubits, p.ops) for p in passes]
+    n_blocks = sum(i["fused3"] for i in infos)
+    n_single = sum(i["ops"] - i["fused3"] for i in infos)
+    flops_nominal = n_gates * 32.0 * 2 ** n
+    flops_executed = (n_single * 32.0 + n_blocks * 49.0) * 2 ** n
+    fp64_info = {
+        "achieved_tflops": flops_executed / (pass_ms * 1e-3) / 1e12, "peak_tflops": FP64_DMMA_PEAK_TFLOPS,
+        "frac": flops_executed / (pass_ms * 1e-3) / 1e12 / FP64_DMMA_PEAK_TFLOPS,
+        "nominal_tflops": flops_nominal / (pass_ms * 1e-3) / 1e12,
+        "kernel_ops": {"fused_3qubit_blocks": n_blocks, "2qubit_ops": n_single,
+                       "group_variant_passes": sum(i["threads"] == 768 for i in infos)},
+        "peak_source": "measured on B200 with tools/fp64_peak.cu (profiles/r1_fp64_peak_dfma_vs_dmma.txt)",
+        "flops": "executed: 32 flop/amplitude per lone 2-qubit op (2 DMMA.8x8x4 per 32 amplitudes), 49 per fused "
+                 "3-qubit block in the 3-multiplication form (6 DMMA + 2 DADD per 64 amplitudes); nominal: 32 per "
+                 "SU(4) gate",
+    }
+
     # ---- end-to-end leg through the plugin-facing call, host buffers in and out ------------------
     e2e = None
     if not args.no_e2e:
@@ -360,11 +381,7 @@ def main():
             "algorithmic_bytes_per_launch": bytes_per_gate_pass, "launch_ms": per_launch_ms,
             "launches_per_step": len(passes), "pass_section_ms": pass_ms,
             # the fused pass is FP64-bound, not HBM-bound: the same launches against the measured DMMA peak
-            "fp64": {"achieved_tflops": n_gates * 32.0 * 2 ** n / (pass_ms * 1e-3) / 1e12,
-                     "peak_tflops": FP64_DMMA_PEAK_TFLOPS,
-                     "frac": n_gates * 32.0 * 2 ** n / (pass_ms * 1e-3) / 1e12 / FP64_DMMA_PEAK_TFLOPS,
-                     "peak_source": "measured on B200 with tools/fp64_peak.cu (profiles/r1_fp64_peak_dfma_vs_dmma.txt)",
-                     "flops_per_gate": "32 * 2^n (16 complex multiply-adds per group of 4 amplitudes)"},
+            "fp64": fp64_info,
         },
         "cpu_baseline": cpu,
         "e2e": e2e,

@@ -32,7 +32,8 @@
 //   * every index map is a sum of per-bit increments (padded shared-memory layout, see pad_of_bit).
 //
 // QSV_DEBUG_FLAGS (environment, profiling experiments only): 1 no write-back, 2 no loads, 4 no gates,
-// 8 no gate-pair fusion, 32 no L2 prefetch, 64 no diagonal-run tables.
+// 8 no gate-pair fusion, 16 no warp-group variant, 32 no L2 prefetch, 64 no diagonal-run tables, 128 warp-group
+// variant requests the next tile after the first op instead of before it.
 #include <stdlib.h>
 #include <string.h>
 
@@ -438,7 +439,9 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
         gsync();
       }
       next_issued = !(ld_on && t + 1 < t_end);
-      if (nstages == 0 && !next_issued) issue_next();
+      // request the next tile right away: the write-back of the previous tile (issued one barrier ago) drains
+      // quickly, and the load then has the whole of this tile's gates to arrive (flag 128: after the first op)
+      if ((nstages == 0 || !(dbg & 128u)) && !next_issued) issue_next();
     }
     // ---- load: one HBM read of the tile (TMA bulk copies, completion on the mbarrier) ----
     if (!kDB && t != t_begin) {
@@ -665,8 +668,7 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
             }
           }
         }
-        // kDB: the first op of the tile is done, so the write-back of the previous tile has long left the
-        // other buffer: request the next tile now, it has the rest of this tile's gates to arrive
+        // kDB with debug flag 128: request the next tile only now, after the first op of this tile
         if constexpr (kDB)
           if (!next_issued) issue_next();
       }

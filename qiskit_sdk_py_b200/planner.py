@@ -21,7 +21,11 @@ from . import _lib
 from .lower import GateOp, matrix_op
 
 DEFAULT_TILE_QUBITS = 11
-LOW_QUBITS = 4  # 16 amplitudes = 256 B contiguous runs (measured: 128 B runs 4.06 TB/s, 256 B 5.03, contiguous 5.27)
+import os as _os
+
+# 16 amplitudes = 256 B contiguous runs (measured: 128 B runs 4.06 TB/s, 256 B 5.03, contiguous 5.27).
+# QSV_LOW_QUBITS overrides it for planner experiments (fewer pinned qubits = fewer passes, smaller TMA pieces).
+LOW_QUBITS = int(_os.environ.get("QSV_LOW_QUBITS", "4"))
 
 
 class Pass:

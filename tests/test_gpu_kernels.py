@@ -207,7 +207,7 @@ def test_pass_with_diagonal_tail(n, tile_size, n_ops, n_tail):
     assert np.max(np.abs(st.download() - ref)) < TOL
 
 
-@pytest.mark.parametrize("n,seed,n_tail", [(22, 1, 0), (22, 2, 25), (23, 3, 0), (24, 4, 60)])
+@pytest.mark.parametrize("n,seed,n_tail", [(22, 1, 0), (22, 2, 25), (23, 3, 0), (22, 4, 60)])
 def test_group_kernel_passes(n, seed, n_tail, monkeypatch):
     """Passes with an 11-qubit tile and >= 2048 tiles run on the three-group double-buffered variant of the pass
     kernel (tile_pass_kernel<768,1,3>): same result as the oracle, and bit for bit the result of the
