@@ -44,7 +44,7 @@ SIM_SEED = 42
 REF_QUBITS = 24          # reference cap (qasm_simulator.py:64)
 REF_GATES_PER_STEP = 6   # bounded sample per reference step (~0.4 s per gate at n=24)
 FP64_DMMA_PEAK_TFLOPS = 37.0      # measured: tools/fp64_peak.cu on B200 (DMMA.8x8x4), profiles/r1_fp64_peak_dfma_vs_dmma.txt
-TRAFFIC_BYTES_PER_AMP = 32.38     # measured DRAM bytes per amplitude per pass (ncu, n=28)
+TRAFFIC_BYTES_PER_AMP = 31.78     # measured DRAM bytes per amplitude per pass (ncu, n=28; writes still in L2 at kernel end are not counted)
 
 
 def measured_peaks():
@@ -306,6 +306,12 @@ def main():
         "achieved_tflops": flops_executed / (pass_ms * 1e-3) / 1e12, "peak_tflops": FP64_DMMA_PEAK_TFLOPS,
         "frac": flops_executed / (pass_ms * 1e-3) / 1e12 / FP64_DMMA_PEAK_TFLOPS,
         "nominal_tflops": flops_nominal / (pass_ms * 1e-3) / 1e12,
+        # the pass runs at the 1 kW power cap: DMMA peak at the SM clock measured during the timed region
+        # (148 SMs x 4 sub-partitions x one DMMA.8x8x4 = 512 flop per 16 cycles)
+        "peak_tflops_at_measured_clock": (148 * 128 * clock_info["sm_mhz"] * 1e6 / 1e12
+                                          if clock_info.get("sm_mhz") else None),
+        "frac_at_measured_clock": (flops_executed / (pass_ms * 1e-3) / (148 * 128 * clock_info["sm_mhz"] * 1e6)
+                                   if clock_info.get("sm_mhz") else None),
         "kernel_ops": {"fused_3qubit_blocks": n_blocks, "2qubit_ops": n_single,
                        "group_variant_passes": sum(i["threads"] == 768 for i in infos)},
         "peak_source": "measured on B200 with tools/fp64_peak.cu (profiles/r1_fp64_peak_dfma_vs_dmma.txt)",
@@ -376,8 +382,8 @@ def main():
         "roofline": {
             "bound": "hbm", "kernel": "tile_pass_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": achieved / peak, "traffic": TRAFFIC_BYTES_PER_AMP * 2 ** n, "peak_source": peak_src,
-            "traffic_source": "ncu --set full at n=28: dram__bytes_read 4.446 GB + write 4.246 GB per launch = "
-                              "32.4 B/amplitude (profiles/r1_tile_pass_kernel_ncu_full_summary.txt), scaled to 2^n",
+            "traffic_source": "ncu --set full at n=28: dram__bytes_read 4.295 GB + write 4.236 GB per launch = "
+                              "31.8 B/amplitude (profiles/r1_tile_pass_kernel_ncu_full_summary.txt), scaled to 2^n",
             "algorithmic_bytes_per_launch": bytes_per_gate_pass, "launch_ms": per_launch_ms,
             "launches_per_step": len(passes), "pass_section_ms": pass_ms,
             # the fused pass is FP64-bound, not HBM-bound: the same launches against the measured DMMA peak

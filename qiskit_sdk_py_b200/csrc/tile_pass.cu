@@ -114,6 +114,12 @@ struct PassDesc {
   uint8_t tbs[16];      // the tile's physical bits in ascending order (tile base computation)
   uint16_t cj[16];      // shared-memory slot increment of tile-local bit j (see slot layout below)
   uint8_t src_of[16];   // write-back permutation: tile-local position j receives the content of bit src_of[j]
+  // warp-group variant: offsets of bulk-copy piece p (its index bits = the tile-local bits pb_ld..b-1), in
+  // BYTES from the tile base in HBM / from the start of the tile buffer.  They live in the kernel parameters
+  // so that the issuing lane's address arithmetic stays in uniform registers (no per-lane waterfall loop
+  // around the bulk-copy instruction).
+  uint64_t pc_g[256];
+  uint16_t pc_s[256];
   DiagRun runs[kMaxRuns];
   TailDesc tail;
   PassStage stages[kMaxStages];
@@ -187,6 +193,19 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
+// one lane of the (converged) warp, the same one every time
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // D(8x8) += A(8x4) * B(4x8) on the FP64 tensor path (SASS: DMMA.8x8x4).
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -246,7 +265,7 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
   uint32_t tile_slots = tile_amps;
   for (int j = 4; j < b; j++) tile_slots += pad_of_bit(j);
   const uint32_t ctid = threadIdx.x, cthreads = blockDim.x;  // CTA-wide (table set-up)
-  const uint32_t grp = kDB ? ctid >> 8 : 0u;                 // warp group
+  const uint32_t grp = kDB ? __shfl_sync(0xffffffffu, ctid >> 8, 0) : 0u;  // warp group (warp-uniform value)
   const uint32_t tid = kDB ? (ctid & 255u) : ctid;           // thread within the group
   const uint32_t kPT = kDB ? 256u : cthreads;                // threads per group
   double2* tile = bufs + (size_t)(grp * kBuf) * tile_slots;  // the group's current tile buffer
@@ -279,7 +298,7 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
   u64 tile_mask = 0;  // physical bit mask of the tile qubits
   for (int j = 0; j < b; j++) tile_mask |= 1ull << d.tb[j];
   if (ctid == 0)
-    for (int q = 0; q < kG * kBuf; q++) mbar_init(&ld_bar[0][0] + q, kPT);
+    for (int q = 0; q < kG * kBuf; q++) mbar_init(&ld_bar[0][0] + q, kDB ? kPT >> 5 : kPT);  // kDB: one arrival per warp
   for (int idx = ctid; idx < nops * 64; idx += cthreads) {
     const int o = idx >> 6, e = idx & 63;
     const PassOp& op = d.ops[o];
@@ -394,6 +413,8 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
   const uint32_t pf_off = (tid & ((1u << sh_ld) - 1u)) * (ld_bytes >> sh_ld);
   const bool pf_on = !(dbg & 32u) && pc_ld0 < np_ld && (ld_bytes >> sh_ld) != 0u;
   const uint32_t lane = tid & 31u, wid = tid >> 5;
+  const uint32_t wid_u = kDB ? __shfl_sync(0xffffffffu, wid, 0) : wid;  // warp-uniform for the compiler
+  const uint32_t ppw = np_ld / (kPT >> 5);                             // kDB: bulk-copy pieces per warp
   const uint32_t g = lane >> 2;
   const char* tb8 = reinterpret_cast<const char*>(tile) + (lane & 1u) * 8u;  // (re-pointed per tile when kDB)
   fence_proxy_async();  // make the mbarrier initialisation visible to the async proxy
@@ -409,8 +430,15 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
   uint32_t parity = 0;
   if constexpr (kDB) {  // prologue: the first tile goes into buffer 0
     if (ld_on && t_begin < t_end) {
-      mbar_arrive_expect_tx(&ld_bar[grp][0], my_ld_bytes);
-      if (own_ld) bulk_load(tile + s_ld0, sv + base + g_ld0, ld_bytes, &ld_bar[grp][0]);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&ld_bar[grp][0], ppw * ld_bytes);
+        const double2* gsrc = sv + base;
+        for (uint32_t i = 0; i < ppw; i++) {
+          const uint32_t p = wid_u * ppw + i;
+          bulk_load(reinterpret_cast<char*>(tile) + d.pc_s[p], reinterpret_cast<const char*>(gsrc) + d.pc_g[p], ld_bytes,
+                    &ld_bar[grp][0]);
+        }
+      }
     }
   }
   uint32_t t_idx = 0;
@@ -420,12 +448,19 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
     // its write-back piece of the previous tile has left that buffer (no barrier needed, see above)
     auto issue_next = [&]() {
       if constexpr (kDB) {
-        bulk_wait_read();
-        const u64 nb = ((base | tile_mask) + 1) & ~tile_mask;
-        const uint32_t nxt = (t_idx & 1u) ^ 1u;
-        mbar_arrive_expect_tx(&ld_bar[grp][nxt], my_ld_bytes);
-        if (own_ld)
-          bulk_load(bufs + (size_t)(grp * kBuf + nxt) * tile_slots + s_ld0, sv + nb + g_ld0, ld_bytes, &ld_bar[grp][nxt]);
+        if (elect_one()) {  // the lane that also issued the write-back of these pieces
+          bulk_wait_read();
+          const u64 nb = ((base | tile_mask) + 1) & ~tile_mask;
+          const uint32_t nxt = (t_idx & 1u) ^ 1u;
+          mbar_arrive_expect_tx(&ld_bar[grp][nxt], ppw * ld_bytes);
+          const double2* gsrc = sv + nb;
+          double2* sdst = bufs + (size_t)(grp * kBuf + nxt) * tile_slots;
+          for (uint32_t i = 0; i < ppw; i++) {
+            const uint32_t p = wid_u * ppw + i;
+            bulk_load(reinterpret_cast<char*>(sdst) + d.pc_s[p], reinterpret_cast<const char*>(gsrc) + d.pc_g[p],
+                      ld_bytes, &ld_bar[grp][nxt]);
+          }
+        }
         next_issued = true;
       }
     };
@@ -749,7 +784,17 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
     // permuted: position j receives the content of tile bit src_of[j] (a free qubit remap) ----
     fence_proxy_async();  // the gates' generic-proxy stores must be visible to the async proxy
     gsync();
-    if (st_on) {
+    if (kDB && st_on) {
+      if (elect_one()) {  // one lane per warp, its warp's pieces, addresses in uniform registers
+        double2* gdst = sv + base;
+        for (uint32_t i = 0; i < ppw; i++) {
+          const uint32_t p = wid_u * ppw + i;
+          bulk_store(reinterpret_cast<char*>(gdst) + d.pc_g[p], reinterpret_cast<const char*>(tile) + d.pc_s[p], st_bytes);
+        }
+        bulk_commit();
+      }
+    }
+    if (!kDB && st_on) {
       if (own_st) bulk_store(sv + base + g_st0, tile + s_st0, st_bytes);
       for (uint32_t pc = tid + kPT; pc < np_st; pc += kPT) {
         u64 go = 0;
@@ -1153,6 +1198,15 @@ static int lower_pass(PassDesc& d, PassPlan& plan, int n, const int32_t* tile_qu
   while (pb < 4 && pb < b && pos_phys[pb] == pb) pb++;
   d.pb_ld = (uint32_t)pb;
   d.pb_st = (uint32_t)pb;
+  if (b - pb <= 8)
+    for (int p = 0; p < (1 << (b - pb)); p++) {
+      uint64_t go = 0;
+      uint32_t so = 0;
+      for (int j = 0; j + pb < b; j++)
+        if ((p >> j) & 1) { go |= 1ull << pos_phys[pb + j]; so += (1u << (pb + j)) + pad_of_bit(pb + j); }
+      d.pc_g[p] = go * sizeof(double2);
+      d.pc_s[p] = (uint16_t)(so * sizeof(double2));
+    }
   // write-back permutation: content of tile_qubits[i] goes to dest_qubits[i]
   for (int j = 0; j < 16; j++) d.src_of[j] = (uint8_t)j;
   if (dest_qubits) {
