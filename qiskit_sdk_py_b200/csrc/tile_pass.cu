@@ -7,24 +7,33 @@
 // (/root/reference/qiskit/providers/basicaer/qasm_simulator.py:145-161), each of which is one
 // out-of-place np.einsum over the whole vector.
 //
-// Kernel structure (tile_pass_kernel):
-//   * persistent: 2-4 CTAs per SM (one warp per 2^8 amplitudes of the tile), each walking a contiguous
-//     range of tiles with one tile buffer; while one CTA waits for HBM (TMA bulk load, write-back) the
-//     others run their gates, so memory phases overlap FP64 / shared-memory phases across CTAs;
+// Kernel structure (tile_pass_kernel, one body, two launch shapes):
+//   * warp-group shape (tile_pass_kernel<768,1,3>; 11-qubit tiles, >= 2048 tiles, unpermuted write-back): one
+//     persistent CTA per SM holds THREE independent groups of 8 warps (named barriers), each with TWO tile
+//     buffers, all sharing the pass's read-only tables (that is what lets six 35 KiB buffers fit in 227 KiB).
+//     A group requests tile t+1 into its other buffer as soon as tile t has landed, and the write-back of
+//     tile t-1 drains while tile t is computed; a buffer is recycled without a barrier because the lane that
+//     wrote a piece back is the lane that loads the next tile's same piece (it waits for its own bulk
+//     async-group).  One elected lane per warp issues the warp's TMA pieces from uniform registers (offsets
+//     in the kernel parameters), so there is no per-lane waterfall loop around the bulk-copy instruction;
+//   * single-buffer shape (every other pass): 2-4 persistent CTAs per SM (one warp per 2^8 amplitudes of the
+//     tile), each walking a contiguous range of tiles with one tile buffer; while one CTA waits for HBM (TMA
+//     bulk load, write-back) the others run their gates;
 //   * the gates of a pass are grouped into STAGES.  In a stage every warp owns a sub-cube of 2^8
 //     amplitudes of the tile (8 "inner" tile bits; the warp id supplies the others) and applies all
 //     the stage's gates -- whose qubits are inner bits -- to it with only __syncwarp() between gates.
 //     Warps therefore drift apart and the shared-memory traffic of one warp overlaps the FP64 tensor
-//     work of another; block-wide barriers are needed only between stages;
+//     work of another; group-wide barriers are needed only between stages;
 //   * dense gates run on the FP64 tensor path (mma.sync m8n8k4 f64, SASS DMMA.8x8x4): a 4x4 complex
 //     gate is the 8x8 real matrix [[Re,-Im],[Im,Re]]; one warp step multiplies 8 groups x 8 real
 //     components (A operand, two k-slices) by the gate (B operand) and every lane receives one complex
 //     output amplitude, i.e. one 16-byte shared-memory store.  (Measured on B200: DMMA 37 TF/s, DFMA
 //     34 TF/s, no gain from mixing them -- tools/fp64_peak.cu -- but DMMA needs 8x fewer instructions
 //     and 2 registers of gate matrix per lane instead of 64.)
-//   * on the host, pairs of 2-qubit gates that share a qubit are fused into 3-qubit blocks (8x8 complex =
-//     16x16 real: 8 DMMA per 64 amplitudes): the same FP64 work as the two gates but one shared-memory
-//     round trip instead of two, which is what bounds a single gate;
+//   * on the host, pairs of 2-qubit gates that share a qubit are fused into 3-qubit blocks (8x8 complex):
+//     one shared-memory round trip instead of two, and the block is applied in the 3-multiplication form of
+//     the complex product (P(x+y), (P+Q)y, (Q-P)x: three real 8x8 products = 6 DMMA + 2 DADD per 64 amplitudes
+//     instead of 8 DMMA for the 16x16 real form);
 //   * diagonal gates never touch the tensor path: runs of them are folded on the host into lookup tables
 //     over the tile bits they touch (one look-up + one complex multiply per amplitude per run), and
 //     diagonal gates on qubits OUTSIDE the tile ride along as the pass's "tail" (TailDesc): outside the
