@@ -42,7 +42,8 @@
 //
 // QSV_DEBUG_FLAGS (environment, profiling experiments only): 1 no write-back, 2 no loads, 4 no gates,
 // 8 no gate-pair fusion, 16 no warp-group variant, 32 no L2 prefetch, 64 no diagonal-run tables, 128 warp-group
-// variant requests the next tile after the first op instead of before it.
+// variant requests the next tile after the first op instead of before it, 256 warp-group variant waits for a tile
+// with every thread polling the mbarrier instead of one polling warp + a group barrier.
 #include <stdlib.h>
 #include <string.h>
 
@@ -478,7 +479,10 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
       const uint32_t cur = t_idx & 1u;
       tile = bufs + (size_t)(grp * kBuf + cur) * tile_slots;
       tb8 = reinterpret_cast<const char*>(tile) + (lane & 1u) * 8u;
-      if (ld_on) {
+      // one warp polls the mbarrier, the others park on the group barrier (debug flag 256: every thread polls
+      // the mbarrier itself and there is no barrier here -- measured the same, profiles/r1_qv30_variants.txt)
+      if (ld_on && (dbg & 256u)) mbar_wait(&ld_bar[grp][cur], (t_idx >> 1) & 1u);
+      if (ld_on && !(dbg & 256u)) {
         if (wid == 0) mbar_wait(&ld_bar[grp][cur], (t_idx >> 1) & 1u);
         gsync();
       }

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Small driver for compute-sanitizer runs of the pass kernel (both launch shapes):
-    compute-sanitizer --tool memcheck python tools/sanitize_probe.py
+"""Small self-checking driver of the pass kernel in both launch shapes (written for
+`compute-sanitizer --tool memcheck python tools/sanitize_probe.py`; the sanitizer is closed on this GPU pool,
+so it is run plain -- gpurun_out/r1n_memcheck.txt records the refusal).
 A 22-qubit state (2048 tiles of 11 qubits: warp-group shape) and a 16-qubit state (single-buffer shape) each
 take a few passes with fused blocks, lone gates, diagonal runs, cx and a diagonal tail; the result is checked
 against the numpy oracle so that the run also fails on wrong answers."""
