@@ -220,10 +220,17 @@ class ShardedState:
         """Apply GateOps (logical qubits, program order).  Gates that need no exchange are fused into
         local passes -- commuting over deferred gates on disjoint qubits only -- then the global qubits
         the deferred gates need are swapped in, and so on."""
-        remaining = [op for op in ops]
-        for op in remaining:
-            if op.kind == "densek":
-                raise _lib.QsvLibraryError("k >= 3 qubit unitaries are not supported on a sharded state")
+        ops = list(ops)
+        for k, op in enumerate(ops):
+            if op.kind == "densek":  # a k >= 3 qubit unitary is a barrier: run what precedes it, then it
+                if len(op.qubits) > self.n_local:
+                    raise _lib.QsvLibraryError("a %d-qubit unitary does not fit in a shard of %d qubits"
+                                               % (len(op.qubits), self.n_local))
+                self.apply_ops(ops[:k])
+                self._apply_dense_k(op)
+                self.apply_ops(ops[k + 1:])
+                return
+        remaining = ops
         while remaining:
             run, deferred, blocked = [], [], set()
             for op in remaining:
@@ -386,6 +393,100 @@ class ShardedState:
             logical |= ((phys >> self.pos[q]) & 1) << q
         return logical, total
 
+    # -- the interface simulator.py drives (same method set as engine.DeviceState), so that the BasicAer
+    # -- mirror classes run SPMD on a sharded state: every rank executes the same run(qobj) ----------
+    MAX_MARGINAL_QUBITS = 28  # 2 GiB of float64 bins per rank
+
+    @property
+    def passes_launched(self):
+        return getattr(self.shard, "passes_launched", None)
+
+    @property
+    def gates_applied(self):
+        return getattr(self.shard, "gates_applied", None)
+
+    def upload(self, amplitudes, phase=1.0 + 0.0j):
+        """Every rank holds the full host vector (it comes from the Qobj) and uploads its own slab."""
+        amps = np.asarray(amplitudes, dtype=complex).reshape(-1)
+        if amps.size != (1 << self.n):
+            raise _lib.QsvLibraryError("upload: expected 2^%d amplitudes" % self.n)
+        self.pos = list(range(self.n))
+        size = 1 << self.n_local
+        self.shard.upload(amps[self.rank * size:(self.rank + 1) * size], phase)
+
+    def marginal(self, measured_sorted):
+        """Marginal probabilities of the measured LOGICAL qubits (bin bit pos <-> measured_sorted[pos], the
+        reference's layout, qasm_simulator.py:202-209), identical on every rank: the rank's own marginal over
+        its local measured bits is scattered to the bins its rank bits select, then all-reduced."""
+        torch = self._torch
+        m = len(measured_sorted)
+        if m > self.MAX_MARGINAL_QUBITS:
+            raise _lib.QsvLibraryError("marginal over %d qubits does not fit on a rank" % m)
+        dev = self.shard.comm_device()
+        local = [(i, self.pos[q]) for i, q in enumerate(measured_sorted) if self.pos[q] < self.n_local]
+        glob = [(i, self.pos[q]) for i, q in enumerate(measured_sorted) if self.pos[q] >= self.n_local]
+        phys_sorted = sorted(p for _, p in local)
+        probs_local = self.shard.marginal(phys_sorted).to(dev)
+        bins = torch.arange(1 << len(phys_sorted), dtype=torch.int64, device=dev)
+        dest = torch.zeros_like(bins)
+        for i, p in local:
+            dest |= ((bins >> phys_sorted.index(p)) & 1) << i
+        dest += sum(self._rank_bit(p) << i for i, p in glob)
+        full = torch.zeros(1 << m, dtype=torch.float64, device=dev)
+        full[dest] = probs_local  # dest is injective: a plain scatter
+        self._dist.all_reduce(full, op=self._dist.ReduceOp.SUM, group=self.group)
+        return full
+
+    def sample(self, measured_sorted, uniforms, exact_order=True, check_norm=True):
+        """engine.DeviceState.sample on the sharded state; every rank returns the same bin indices.
+        Fewer than all qubits measured: the all-reduced marginal is sampled with the single-GPU sampler
+        (numpy's cumsum order when ``exact_order``), on every rank alike.  All qubits measured (or a marginal
+        too large for one rank): blocked-order sampling of the full index, rank-major (``sample_all``) -- the
+        same distribution, and the same bins as the reference up to the rounding of the running sums."""
+        measured_sorted = list(measured_sorted)
+        m = len(measured_sorted)
+        if m == self.n or m > self.MAX_MARGINAL_QUBITS:
+            self.restore_identity_layout()
+            logical, total = self.sample_all(uniforms)
+            if m == self.n:
+                return logical, total
+            bins = np.zeros_like(logical)
+            for i, q in enumerate(measured_sorted):
+                bins |= ((logical >> q) & 1) << i
+            return bins, total
+        probs = self.marginal(measured_sorted)
+        samples, total = self.shard.sample_probs(probs, m, uniforms, exact_order=exact_order, check_norm=check_norm)
+        # every rank computed the same thing from the same all-reduced marginal; rank 0's copy is authoritative
+        torch = self._torch
+        t = torch.as_tensor(np.ascontiguousarray(samples), device=self.shard.comm_device())
+        self._dist.broadcast(t, src=self._dist.get_global_rank(self.group, 0) if self.group is not None else 0,
+                             group=self.group)
+        return t.cpu().numpy(), total
+
+    def chop(self, threshold):
+        self.shard.chop(threshold)
+
+    def download(self):
+        """Full statevector in logical order on every rank (sizes that fit in host memory)."""
+        return self.gather_statevector()
+
+    def snapshot(self):
+        return (self.shard.snapshot(), list(self.pos))
+
+    def restore(self, snap):
+        self.shard.restore(snap[0])
+        self.pos = list(snap[1])
+
+    def _apply_dense_k(self, op):
+        """k >= 3 qubit ``unitary``: make its qubits local (victims: the highest local bits it does not use),
+        then the shard's dense k-qubit kernel."""
+        for q in op.qubits:
+            if self.pos[q] >= self.n_local:
+                used = {self.pos[x] for x in op.qubits}
+                victim = max(p for p in range(self.n_local) if p not in used)
+                self.swap_global_local(self.pos[q], victim)  # updates self.pos
+        self.shard.apply_ops([GateOp(op.kind, [self.pos[q] for q in op.qubits], op.matrix)])
+
     def gather_statevector(self):
         """Full logical-order statevector on every rank (small n only; tests)."""
         torch = self._torch
@@ -397,6 +498,43 @@ class ShardedState:
 
 
 # ------------------------------------------------------------------------------------------------
+def distributed_simulator(backend="qasm_simulator", shard_factory=None, group=None,
+                          chunk_amps=DEFAULT_CHUNK_AMPS, **kwargs):
+    """The BasicAer mirror simulators (simulator.QasmSimulatorB200 / StatevectorSimulatorB200) on a state
+    sharded over the ranks of ``group`` (default: the world).  SPMD: every rank constructs the simulator and
+    calls ``run(qobj)`` with the same Qobj; every rank returns the same result dict (counts, memory and -- for
+    sizes that fit in host memory -- the statevector).  The qubit cap grows by log2(world) over the
+    single-GPU cap.  ``torch.distributed`` must be initialised (NCCL on GPUs); ``shard_factory(n_local)``
+    defaults to engine.DeviceState on the current CUDA device.  A seed the backend draws itself is rank 0's."""
+    import torch
+    import torch.distributed as dist
+
+    from . import simulator
+    from .engine import DeviceState
+
+    world = dist.get_world_size(group)
+    g = int(round(math.log2(world)))
+    if backend not in ("qasm_simulator", "statevector_simulator"):
+        raise LookupError("distributed_simulator: only the qasm and statevector simulators are sharded")
+    factory = shard_factory or DeviceState
+
+    def state_factory(n_qubits):
+        if n_qubits - g < 2:  # tiny circuits: pad with idle qubits so that every rank holds >= 2 local qubits
+            raise simulator.BasicAerError("a circuit on a %d-rank sharded state needs at least %d qubits"
+                                          % (world, g + 2))
+        return ShardedState(n_qubits, factory, chunk_amps=chunk_amps, group=group)
+
+    def seed_sync(seed):
+        dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+        t = torch.tensor([seed], dtype=torch.int64, device=dev)
+        dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        return int(t.item())
+
+    cls = simulator.QasmSimulatorB200 if backend == "qasm_simulator" else simulator.StatevectorSimulatorB200
+    kwargs.setdefault("max_qubits", simulator.max_qubits_for_device() + g)
+    return cls(state_factory=state_factory, seed_sync=seed_sync, **kwargs)
+
+
 def bench_main(args, metric, unit, measured_peaks, clock_sampler_cls):
     """bench.py leg for N > 1 GPUs: weak scaling, args.qubits local qubits per GPU."""
     import json

@@ -250,15 +250,21 @@ class DeviceState:
     def sample(self, measured_sorted, uniforms, exact_order=True, check_norm=True):
         """searchsorted(cumsum(p)/sum(p), uniforms, 'right') over the marginal of the measured qubits.
         Returns (int64 ndarray of bin indices, total probability)."""
+        m = len(measured_sorted)
+        if m == self.n:
+            return self._sample_from(self.state, 1, self.n, uniforms, exact_order, check_norm)
+        self._probs = self.marginal(measured_sorted)
+        return self._sample_from(self._probs, 0, m, uniforms, exact_order, check_norm)
+
+    def sample_probs(self, probs, log2_bins, uniforms, exact_order=True, check_norm=True):
+        """The same sampler over a device tensor of 2^log2_bins probabilities (the all-reduced marginal of a
+        sharded state, dist.ShardedState.sample)."""
+        return self._sample_from(probs, 0, int(log2_bins), uniforms, exact_order, check_norm)
+
+    def _sample_from(self, src, from_amps, log2_bins, uniforms, exact_order, check_norm):
         torch = self._torch
         uniforms = np.ascontiguousarray(uniforms, dtype=np.float64)
         shots = int(uniforms.size)
-        m = len(measured_sorted)
-        if m == self.n:
-            src, from_amps, log2_bins = self.state, 1, self.n
-        else:
-            self._probs = self.marginal(measured_sorted)
-            src, from_amps, log2_bins = self._probs, 0, m
         ws_bytes = self.lib.qsv_sample_workspace_bytes(log2_bins, shots)
         if self._sample_ws is None or self._sample_ws.numel() * 8 < ws_bytes:
             self._sample_ws = torch.empty(ws_bytes // 8 + 8, dtype=torch.float64, device=self.device)

@@ -85,8 +85,11 @@ class QasmSimulatorB200:
     }  # qasm_simulator.py:133-143
 
     def __init__(self, state_factory=None, max_qubits=None, exact_sampling_max_qubits=40,
-                 tile_qubits=None):
+                 tile_qubits=None, seed_sync=None):
         self._state_factory = state_factory or self._device_state
+        # multi-process (sharded) runs: every rank executes the same run(qobj); a seed the backend draws itself
+        # (qasm_simulator.py:499-502) must then be the same on all ranks -- seed_sync(seed) -> rank 0's seed
+        self._seed_sync = seed_sync
         self._max_qubits = max_qubits
         self._tile_qubits = tile_qubits
         # up to this many sampled qubits the CDF is accumulated in numpy's cumsum order (bit-exact
@@ -375,6 +378,8 @@ class QasmSimulatorB200:
             seed_simulator = self._qobj_config["seed_simulator"]
         else:
             seed_simulator = np.random.randint(2147483647, dtype="int32")
+            if self._seed_sync is not None:
+                seed_simulator = self._seed_sync(int(seed_simulator))
         self._local_random.seed(seed=seed_simulator)
         self._validate_measure_sampling(experiment)
 

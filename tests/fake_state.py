@@ -135,13 +135,29 @@ class FakeState:
         idx = self._sub_index(local_qubits, pattern, begin, count)
         self.vec[idx] = buf[: 2 * count].numpy().copy().view(np.complex128)
 
-    def sample(self, measured_sorted, uniforms, exact_order=True, check_norm=True):
+    def _marginal_np(self, measured_sorted):
         n = self.n
         axis = list(range(n))
         for q in reversed(measured_sorted):
             axis.remove(n - 1 - q)
-        p = np.reshape(np.sum(np.abs(self.vec.reshape([2] * n)) ** 2, axis=tuple(axis)),
-                       2 ** len(measured_sorted))
+        return np.reshape(np.sum(np.abs(self.vec.reshape([2] * n)) ** 2, axis=tuple(axis)),
+                          2 ** len(measured_sorted))
+
+    def marginal(self, measured_sorted):
+        import torch
+
+        return torch.from_numpy(np.ascontiguousarray(self._marginal_np(list(measured_sorted)), dtype=np.float64))
+
+    def sample(self, measured_sorted, uniforms, exact_order=True, check_norm=True):
+        return self._sample_np(self._marginal_np(measured_sorted), uniforms)
+
+    def sample_probs(self, probs, log2_bins, uniforms, exact_order=True, check_norm=True):
+        p = probs.numpy().copy()
+        assert p.size == 1 << log2_bins
+        return self._sample_np(p, uniforms)
+
+    @staticmethod
+    def _sample_np(p, uniforms):
         cdf = p.cumsum()
         total = cdf[-1]
         cdf /= total

@@ -19,3 +19,4 @@ def test_two_rank_nccl_matches_oracle():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
     assert out.stdout.count("dist ok") == 3
+    assert out.stdout.count("spmd ok") == 1
