@@ -72,8 +72,8 @@ class _B200Backend(BackendV1):
 
     SIMULATOR_CLS = None
 
-    def __init__(self, configuration=None, provider=None, simulator_kwargs=None, **fields):
-        self._sim = self.SIMULATOR_CLS(**(simulator_kwargs or {}))
+    def __init__(self, configuration=None, provider=None, simulator_kwargs=None, simulator_instance=None, **fields):
+        self._sim = simulator_instance or self.SIMULATOR_CLS(**(simulator_kwargs or {}))
         super().__init__(
             configuration=(configuration or
                            QasmBackendConfiguration.from_dict(self._sim.configuration_dict())),
@@ -154,9 +154,16 @@ SIMULATORS = [QasmSimulatorB200Backend, StatevectorSimulatorB200Backend, Unitary
 class B200Provider(ProviderV1):
     """Provider for the B200 backends; same lookup rules as BasicAerProvider."""
 
-    def __init__(self, simulator_kwargs=None):
+    def __init__(self, simulator_kwargs=None, distributed=False, group=None, distributed_kwargs=None):
+        """``distributed=True`` (inside a ``torch.distributed`` job, one process per GPU): the qasm and
+        statevector backends keep their state sharded over the ranks of ``group`` (dist.distributed_simulator);
+        every rank makes the same calls and gets the same Result, and ``n_qubits`` grows by log2(world).  The
+        unitary backend stays on the local GPU."""
         super().__init__()
         self._simulator_kwargs = simulator_kwargs
+        self._distributed = bool(distributed)
+        self._group = group
+        self._distributed_kwargs = dict(distributed_kwargs or {})
         self._backends = self._verify_backends()
 
     def get_backend(self, name=None, **kwargs):
@@ -196,7 +203,14 @@ class B200Provider(ProviderV1):
         ret = OrderedDict()
         for backend_cls in SIMULATORS:
             try:
-                backend_instance = backend_cls(provider=self, simulator_kwargs=self._simulator_kwargs)
+                sim = None
+                if self._distributed and backend_cls is not UnitarySimulatorB200Backend:
+                    from . import dist
+
+                    sim = dist.distributed_simulator(backend_cls.SIMULATOR_CLS.NAME, group=self._group,
+                                                     **self._distributed_kwargs)
+                backend_instance = backend_cls(provider=self, simulator_kwargs=self._simulator_kwargs,
+                                               simulator_instance=sim)
             except Exception as err:
                 raise QiskitError(f"Backend {backend_cls} could not be instantiated: {err}") from err
             ret[backend_instance.name()] = backend_instance

@@ -180,3 +180,56 @@ def test_simulators_run_spmd_on_sharded_state(tmp_path, world):
     mp.spawn(_spmd_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     res = np.load(os.path.join(str(tmp_path), "spmd_%d.npy" % world))
     assert res[0] == len(SPMD_CASES[world]) + len(SPMD_FULL_MEASURE[world])
+
+
+def _provider_worker(rank, world, port, out_dir):
+    for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle", "ref_env")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import warnings
+
+    import ref_import
+
+    ref_import.import_reference()
+    warnings.simplefilter("ignore")
+    import qiskit
+    from fake_state import FakeState
+    from qiskit_sdk_py_b200.provider import B200Provider
+
+    provider = B200Provider(simulator_kwargs={"state_factory": FakeState, "max_qubits": 12}, distributed=True,
+                            distributed_kwargs={"shard_factory": lambda k: FakeState(k, tile_qubits=4),
+                                                "chunk_amps": 8, "max_qubits": 24})
+    qc = qiskit.QuantumCircuit(4, 4)
+    qc.h(3)
+    qc.cx(3, 0)
+    qc.ry(0.7, 2)
+    qc.cx(2, 1)
+    qc.measure([0, 1, 2, 3], [0, 1, 2, 3])
+    ours = qiskit.execute(qc, provider.get_backend("qasm_simulator"), shots=500, seed_simulator=9, memory=True).result()
+    ref = qiskit.execute(qc, qiskit.BasicAer.get_backend("qasm_simulator"), shots=500, seed_simulator=9,
+                         memory=True).result()
+    assert ours.get_counts() == ref.get_counts() and ours.get_memory() == ref.get_memory()
+    qc2 = qiskit.QuantumCircuit(5)
+    qc2.h(4)
+    qc2.cx(4, 1)
+    qc2.rz(0.3, 4)
+    qc2.ccx(4, 3, 0)
+    sv = qiskit.execute(qc2, provider.get_backend("statevector_simulator")).result().get_statevector()
+    sv_ref = qiskit.execute(qc2, qiskit.BasicAer.get_backend("statevector_simulator")).result().get_statevector()
+    assert np.max(np.abs(np.asarray(sv) - np.asarray(sv_ref))) < 1e-12
+    assert provider.get_backend("qasm_simulator").configuration().n_qubits == 24
+    if rank == 0:
+        np.save(os.path.join(out_dir, "provider_%d.npy" % world), np.array([1]))
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/qiskit"), reason="reference/qiskit not present")
+def test_distributed_provider_with_reference_execute(tmp_path):
+    """B200Provider(distributed=True) under the reference's own execute(): 2 gloo ranks, same seeded counts,
+    memory and statevector as BasicAer on every rank."""
+    port = _free_port()
+    mp.spawn(_provider_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(os.path.join(str(tmp_path), "provider_2.npy"))
