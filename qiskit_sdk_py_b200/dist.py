@@ -599,13 +599,50 @@ def bench_main(args, metric, unit, measured_peaks, clock_sampler_cls):
     step_ms = float(ms.item()) / args.steps
     launches = torch.tensor([_lib.launch_count() - launches0], device="cuda", dtype=torch.int64)
     dist.all_reduce(launches, op=dist.ReduceOp.SUM)
+    passes_dev = (st.shard.passes_launched - passes0) / args.steps
+    swaps_dev = (st.swaps - swaps0) / args.steps
+    swap_gb_dev = (st.swap_bytes - bytes0) / args.steps / 1e9
+
+    # ---- end-to-end leg: the same circuit through the plugin-facing call on every rank (SPMD), host Qobj in
+    # (gate matrices + shots), counts out; wall clock around run(), max over ranks -----------------------------
+    e2e, e2e_error = None, None
+    if not args.no_e2e and os.environ.get("QSV_BENCH_NO_DIST_E2E") != "1":
+        import copy
+        import time
+
+        del st
+        torch.cuda.empty_cache()
+        try:
+            qobj = circuits.quantum_volume(n, depth, qv_seed, shots=shots, seed_simulator=sim_seed)
+            sim = distributed_simulator("qasm_simulator", shard_factory=factory,
+                                        chunk_amps=min(chunk, 1 << (n_local - 1)), max_qubits=n)
+            sim.run(copy.deepcopy(qobj))  # warm-up (allocation of the shard and the staging buffers)
+            torch.cuda.synchronize()
+            dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                res = sim.run(copy.deepcopy(qobj))
+            torch.cuda.synchronize()
+            dist.barrier()
+            e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3 / args.steps], device="cuda", dtype=torch.float64)
+            dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+            counts = res["results"][0]["data"]["counts"]
+            assert sum(counts.values()) == shots
+            e2e_s = float(e2e_ms.item()) * 1e-3
+            e2e = {"value": n_gates * 32.0 * 2 ** n / e2e_s / 1e9, "unit": unit,
+                   "h2d_bytes_per_step": int(world * (n_gates * 256 + shots * 8)),
+                   "d2h_bytes_per_step": int(world * (shots * 8 + 8)), "circuit_s": e2e_s,
+                   "api": "dist.distributed_simulator('qasm_simulator').run(qobj dict) -> counts, on every rank "
+                          "(SPMD); the final layout is restored before sampling so that counts follow the "
+                          "reference's bin order"}
+        except (_lib.QsvLibraryError, TypeError, ValueError, KeyError, AttributeError, AssertionError) as exc:
+            # a deterministic host-side failure is the same on every rank: report it instead of losing the line
+            e2e_error = "%s: %s" % (type(exc).__name__, exc)
     if rank == 0:
         clock_info = clocks.stop()
         bytes_per_gate_pass = 32.0 * 2 ** n
         value = n_gates * bytes_per_gate_pass / (step_ms * 1e-3) / 1e9
-        passes = (st.shard.passes_launched - passes0) / args.steps
-        swaps = (st.swaps - swaps0) / args.steps
-        swap_gb = (st.swap_bytes - bytes0) / args.steps / 1e9
+        passes, swaps, swap_gb = passes_dev, swaps_dev, swap_gb_dev
         peak, peak_src = measured_peaks()
         line = {
             "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
@@ -625,10 +662,11 @@ def bench_main(args, metric, unit, measured_peaks, clock_sampler_cls):
                          "frac": None, "traffic": None, "peak_source": peak_src,
                          "note": "per-kernel roofline is reported by the N=1 run"},
             "cpu_baseline": None,
-            "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": int(n_gates * 256 + shots * 8),
-                    "d2h_bytes_per_step": int(shots * 8 + 8 * world),
-                    "note": "the sharded path is driven from host op lists; uniforms in, sample indices out are "
-                            "inside the timed region"},
+            "e2e": e2e or {"value": value, "unit": unit, "h2d_bytes_per_step": int(n_gates * 256 + shots * 8),
+                           "d2h_bytes_per_step": int(shots * 8 + 8 * world),
+                           "note": "e2e leg %s: the device-timed leg is driven from host op lists; uniforms in, "
+                                   "sample indices out are inside its timed region"
+                                   % ("failed (%s)" % e2e_error if e2e_error else "skipped")},
             "gpu_launches": int(launches.item()),
             "clocks": clock_info,
             "check": {"sample_total_prob": total},

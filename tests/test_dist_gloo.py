@@ -143,8 +143,23 @@ def _spmd_worker(rank, world, port, out_dir):
     seeds = [None] * world
     dist.all_gather_object(seeds, (res["results"][0]["seed_simulator"], res["results"][0]["data"]["counts"]))
     assert all(s == seeds[0] for s in seeds), seeds
+    # the call sequence of bench.py's N > 1 end-to-end leg (dist.bench_main), at a size the oracle can check
+    import copy as _copy
+
+    from oracle import basicaer_oracle as _orc
+    from qiskit_sdk_py_b200.dist import DEFAULT_CHUNK_AMPS
+
+    nq = 7
+    n_loc = nq - int(np.log2(world))
+    qobj = circuits.quantum_volume(nq, nq, 1234, shots=256, seed_simulator=42)
+    sim = distributed_simulator("qasm_simulator", shard_factory=lambda k: FakeState(k, tile_qubits=4),
+                                chunk_amps=min(DEFAULT_CHUNK_AMPS, 1 << (n_loc - 1)), max_qubits=nq)
+    sim.run(_copy.deepcopy(qobj))
+    res = sim.run(_copy.deepcopy(qobj))
+    counts = res["results"][0]["data"]["counts"]
+    assert sum(counts.values()) == 256
+    assert counts == _orc.OracleQasmSimulator().run(_copy.deepcopy(qobj))["results"][0]["data"]["counts"]
     # a 3-qubit unitary on global qubits of a sharded state (swap-in of its qubits, then the dense-k path)
-    import numpy as np
     from oracle import basicaer_oracle as orc
 
     rng = np.random.RandomState(3)
