@@ -84,6 +84,17 @@ class ShardedState:
         else:
             self.shard.init_basis0(0.0 + 0.0j)
 
+    def init_identity(self, n_half, phase=1.0 + 0.0j):
+        """The identity matrix as a vector of 2 n_half qubits (row index = the high half; unitary simulator,
+        unitary_simulator.py:190-199), built with exact arithmetic from |0..0>: the map |0> -> |0> + |1> on every
+        row qubit (entries 0/1, not a Hadamard), then CX row_j -> column_j gives sum_k |k>|k>."""
+        if 2 * n_half != self.n:
+            raise _lib.QsvLibraryError("init_identity: the state has %d qubits, not 2 * %d" % (self.n, n_half))
+        self.init_basis0(phase)
+        fan = np.array([[1, 0], [1, 0]], dtype=complex)
+        self.apply_ops([GateOp(_lib.GATE_DENSE1, [n_half + j], fan) for j in range(n_half)] +
+                       [GateOp(_lib.GATE_CX, [n_half + j, j], None) for j in range(n_half)])
+
     # -- the exchange step -------------------------------------------------------------
     def swap_global_local(self, phys_global, phys_local):
         """Swap physical bits (global j, local L): exchange the half with bit L != my bit j."""
@@ -514,9 +525,18 @@ def distributed_simulator(backend="qasm_simulator", shard_factory=None, group=No
 
     world = dist.get_world_size(group)
     g = int(round(math.log2(world)))
-    if backend not in ("qasm_simulator", "statevector_simulator"):
-        raise LookupError("distributed_simulator: only the qasm and statevector simulators are sharded")
+    if backend not in ("qasm_simulator", "statevector_simulator", "unitary_simulator"):
+        raise LookupError("The '%s' backend is not installed in your system." % backend)
     factory = shard_factory or DeviceState
+    if backend == "unitary_simulator":  # a 2n-qubit vector, sharded the same way
+        def unitary_state_factory(n2):
+            if n2 - g < 2:
+                raise simulator.BasicAerError("a unitary on a %d-rank sharded state needs at least %d qubits"
+                                              % (world, (g + 3) // 2))
+            return ShardedState(n2, factory, chunk_amps=chunk_amps, group=group)
+
+        kwargs.setdefault("max_qubits", (simulator.max_qubits_for_device() + g) // 2)
+        return simulator.UnitarySimulatorB200(state_factory=unitary_state_factory, **kwargs)
 
     def state_factory(n_qubits):
         if n_qubits - g < 2:  # tiny circuits: pad with idle qubits so that every rank holds >= 2 local qubits

@@ -155,10 +155,10 @@ class B200Provider(ProviderV1):
     """Provider for the B200 backends; same lookup rules as BasicAerProvider."""
 
     def __init__(self, simulator_kwargs=None, distributed=False, group=None, distributed_kwargs=None):
-        """``distributed=True`` (inside a ``torch.distributed`` job, one process per GPU): the qasm and
-        statevector backends keep their state sharded over the ranks of ``group`` (dist.distributed_simulator);
-        every rank makes the same calls and gets the same Result, and ``n_qubits`` grows by log2(world).  The
-        unitary backend stays on the local GPU."""
+        """``distributed=True`` (inside a ``torch.distributed`` job, one process per GPU): the three
+        backends keep their state sharded over the ranks of ``group`` (dist.distributed_simulator);
+        every rank makes the same calls and gets the same Result, and ``n_qubits`` grows by log2(world) (the
+        unitary backend's 2n-qubit vector is sharded the same way: log2(world) / 2 more qubits)."""
         super().__init__()
         self._simulator_kwargs = simulator_kwargs
         self._distributed = bool(distributed)
@@ -204,7 +204,7 @@ class B200Provider(ProviderV1):
         for backend_cls in SIMULATORS:
             try:
                 sim = None
-                if self._distributed and backend_cls is not UnitarySimulatorB200Backend:
+                if self._distributed:
                     from . import dist
 
                     sim = dist.distributed_simulator(backend_cls.SIMULATOR_CLS.NAME, group=self._group,

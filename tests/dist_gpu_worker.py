@@ -67,7 +67,8 @@ def main():
 
     names = ["if_statement", "memory_two_registers", "qasm_initial_statevector", "reset_midcircuit",
              "sampler_marginal_subset", "sampler_partial_qubit", "sv_global_phase", "sv_reset_midcircuit", "teleport",
-             "transpiled_init_reset_cond_counts", "qv_8_state", "random_12_state", "qft_12_counts", "qv_11_counts"]
+             "transpiled_init_reset_cond_counts", "qv_8_state", "random_12_state", "qft_12_counts", "qv_11_counts",
+             "unitary_random", "unitary_global_phase_x4", "random_6_unitary", "unitary_initial_unitary"]
     for name in names:
         case = golden_io.load_case(name)
         result = helpers.run_case_with(lambda backend: distributed_simulator(backend, chunk_amps=1 << 9), case)

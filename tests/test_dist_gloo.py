@@ -105,6 +105,8 @@ SPMD_CASES = {
         "sampler_single_qubit", "sv_global_phase", "transpiled_init_reset_cond_counts", "qv_8_state",
         "random_9_state", "transpiled_qft_lib_9_state", "transpiled_lib_gates_l0_state"],
 }
+SPMD_UNITARY = ["random_2_unitary", "random_4_unitary", "unitary_five_circuits", "unitary_global_phase_x4",
+                "unitary_initial_unitary", "unitary_random", "multi_registers_unitary"]
 # all qubits measured: the sharded sampler walks the ranks' slabs in blocked order, so a uniform within ~1e-16
 # of a CDF step may land in the neighbouring bin -- counts are compared exactly here as well (none of these
 # fixtures has such a tie)
@@ -129,7 +131,7 @@ def _spmd_worker(rank, world, port, out_dir):
                                      max_qubits=24)
 
     done = 0
-    for name in SPMD_CASES[world] + SPMD_FULL_MEASURE[world]:
+    for name in SPMD_CASES[world] + SPMD_FULL_MEASURE[world] + SPMD_UNITARY:
         case = golden_io.load_case(name)
         result = helpers.run_case_with(factory, case)
         helpers.compare_result(result, case, amp_tol=1e-12)
@@ -188,13 +190,13 @@ def _spmd_worker(rank, world, port, out_dir):
 
 @pytest.mark.parametrize("world", [2, 4])
 def test_simulators_run_spmd_on_sharded_state(tmp_path, world):
-    """dist.distributed_simulator: QasmSimulatorB200 / StatevectorSimulatorB200 with the state sharded over
-    `world` gloo ranks reproduce the reference's golden outputs (mid-circuit measure, reset, conditionals,
+    """dist.distributed_simulator: QasmSimulatorB200 / StatevectorSimulatorB200 / UnitarySimulatorB200 with the
+    state sharded over `world` gloo ranks reproduce the reference's golden outputs (mid-circuit measure, reset, conditionals,
     partial-register sampling, initial_statevector, global phase, memory) on every rank."""
     port = _free_port()
     mp.spawn(_spmd_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     res = np.load(os.path.join(str(tmp_path), "spmd_%d.npy" % world))
-    assert res[0] == len(SPMD_CASES[world]) + len(SPMD_FULL_MEASURE[world])
+    assert res[0] == len(SPMD_CASES[world]) + len(SPMD_FULL_MEASURE[world]) + len(SPMD_UNITARY)
 
 
 def _provider_worker(rank, world, port, out_dir):
@@ -236,6 +238,13 @@ def _provider_worker(rank, world, port, out_dir):
     sv_ref = qiskit.execute(qc2, qiskit.BasicAer.get_backend("statevector_simulator")).result().get_statevector()
     assert np.max(np.abs(np.asarray(sv) - np.asarray(sv_ref))) < 1e-12
     assert provider.get_backend("qasm_simulator").configuration().n_qubits == 24
+    qc3 = qiskit.QuantumCircuit(3)
+    qc3.h(2)
+    qc3.cx(2, 0)
+    qc3.t(1)
+    un = qiskit.execute(qc3, provider.get_backend("unitary_simulator")).result().get_unitary()
+    un_ref = qiskit.execute(qc3, qiskit.BasicAer.get_backend("unitary_simulator")).result().get_unitary()
+    assert np.max(np.abs(np.asarray(un) - np.asarray(un_ref))) < 1e-12
     if rank == 0:
         np.save(os.path.join(out_dir, "provider_%d.npy" % world), np.array([1]))
     dist.destroy_process_group()
