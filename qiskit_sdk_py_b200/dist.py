@@ -324,14 +324,17 @@ class ShardedState:
     def restore_identity_layout(self):
         """Undo every remap so that logical qubit q sits at physical bit q again (needed before the
         state is read out or sampled in logical index order)."""
+        # home qubits that sit in ANOTHER global bit are brought into a local bit first (one at a time) ...
         for phys in range(self.n_local, self.n):
             q_home = phys  # logical qubit whose home is this global bit
-            if self.pos[q_home] == phys:
-                continue
-            if self.pos[q_home] >= self.n_local:
-                # it sits in another global bit: bring it local first
-                self.swap_global_local(self.pos[q_home], self.n_local - 1)
-            self.swap_global_local(phys, self.pos[q_home])
+            if self.pos[q_home] != phys and self.pos[q_home] >= self.n_local:
+                homes = {self.pos[q] for q in range(self.n_local, self.n)}
+                victim = max(p for p in range(self.n_local) if p not in homes)
+                self.swap_global_local(self.pos[q_home], victim)
+        # ... then every misplaced global bit receives its home qubit in ONE fused exchange
+        pairs = [(phys, self.pos[phys]) for phys in range(self.n_local, self.n) if self.pos[phys] != phys]
+        if pairs:
+            self.swap_many(pairs)
         # now fix the local permutation with SWAP gates
         swap = np.array([[1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=complex)
         ops = []
