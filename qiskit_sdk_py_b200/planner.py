@@ -25,7 +25,10 @@ import os as _os
 
 # 16 amplitudes = 256 B contiguous runs (measured: 128 B runs 4.06 TB/s, 256 B 5.03, contiguous 5.27).
 # QSV_LOW_QUBITS overrides it for planner experiments (fewer pinned qubits = fewer passes, smaller TMA pieces).
-LOW_QUBITS = int(_os.environ.get("QSV_LOW_QUBITS", "4"))
+try:
+    LOW_QUBITS = min(4, max(0, int(_os.environ.get("QSV_LOW_QUBITS", "4"))))
+except ValueError:
+    LOW_QUBITS = 4
 
 
 class Pass:
