@@ -480,8 +480,14 @@ class ShardedState:
     def chop(self, threshold):
         self.shard.chop(threshold)
 
+    MAX_GATHER_QUBITS = 31  # 32 GiB of complex128 per rank on the host
+
     def download(self):
         """Full statevector in logical order on every rank (sizes that fit in host memory)."""
+        if self.n > self.MAX_GATHER_QUBITS:
+            raise _lib.QsvLibraryError(
+                "the full statevector of %d qubits (%d GiB) is not gathered on every rank; sample it "
+                "(qasm_simulator) or read the shards" % (self.n, 16 * 2 ** self.n >> 30))
         return self.gather_statevector()
 
     def snapshot(self):
