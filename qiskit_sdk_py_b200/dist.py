@@ -664,7 +664,8 @@ def bench_main(args, metric, unit, measured_peaks, clock_sampler_cls):
                    "api": "dist.distributed_simulator('qasm_simulator').run(qobj dict) -> counts, on every rank "
                           "(SPMD); the final layout is restored before sampling so that counts follow the "
                           "reference's bin order"}
-        except (_lib.QsvLibraryError, TypeError, ValueError, KeyError, AttributeError, AssertionError) as exc:
+        except (_lib.QsvLibraryError, RuntimeError, TypeError, ValueError, KeyError, AttributeError,
+                AssertionError) as exc:  # RuntimeError: e.g. an out-of-memory error, alike on all ranks
             # a deterministic host-side failure is the same on every rank: report it instead of losing the line
             e2e_error = "%s: %s" % (type(exc).__name__, exc)
     if rank == 0:
