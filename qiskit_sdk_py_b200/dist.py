@@ -369,6 +369,33 @@ class ShardedState:
     def norm2(self):
         return self._allreduce([self.shard.norm2()])[0]
 
+    def expval_pauli(self, pauli):
+        """<psi|P|psi> for a Pauli label ("XIZY": leftmost character = highest LOGICAL qubit), as
+        engine.DeviceState.expval_pauli (Statevector._expectation_value_pauli, statevector.py:377-408).  Qubits
+        with X or Y are made local first (victims: local qubits with I or Z); a Z on a global qubit is the sign
+        of the rank's bit; the ranks' partial sums are all-reduced."""
+        label = pauli.upper()
+        if len(label) != self.n or any(c not in "IXYZ" for c in label):
+            raise ValueError("Pauli label must have %d characters from IXYZ" % self.n)
+        char = {q: c for q, c in enumerate(reversed(label))}
+        flips = [q for q in range(self.n) if char[q] in "XY"]
+        if len(flips) > self.n_local:
+            raise _lib.QsvLibraryError("a Pauli with %d X/Y factors does not fit in a shard of %d qubits"
+                                       % (len(flips), self.n_local))
+        for q in flips:
+            if self.pos[q] >= self.n_local:
+                victim = max(p for p in range(self.n_local) if char[self._logical_at(p)] in "IZ")
+                self.swap_global_local(self.pos[q], victim)
+        if all(c == "I" for c in label):
+            return float(np.sqrt(self.norm2()))  # the reference returns the norm here (statevector.py:397-398)
+        local = "".join(char[self._logical_at(p)] for p in reversed(range(self.n_local)))
+        sign = 1.0
+        for p in range(self.n_local, self.n):
+            if char[self._logical_at(p)] == "Z" and self._rank_bit(p):
+                sign = -sign
+        part = self.shard.norm2() if all(c == "I" for c in local) else self.shard.expval_pauli(local)
+        return self._allreduce([sign * part])[0]
+
     def collapse(self, qubit, outcome, prob, is_reset=False):
         self.ensure_local(qubit)
         self.shard.collapse(self.pos[qubit], outcome, prob, is_reset)

@@ -94,6 +94,9 @@ class FakeState:
     def scale(self, factor):
         self.vec = self.vec * complex(factor)
 
+    def expval_pauli(self, pauli):
+        return orc.expval_pauli(self.vec, pauli)
+
     def norm2(self):
         return float(np.sum(np.abs(self.vec) ** 2))
 

@@ -65,6 +65,17 @@ def _worker(rank, world, port, n, seed, out_dir):
     assert abs(total - 1.0) < 1e-12
     hist = np.bincount(samples, minlength=2 ** n) / 4000.0
     assert np.abs(hist - p).max() < 0.05
+    # Pauli expectation values on the permuted layout: X / Y on global qubits are swapped in, Z on a global
+    # qubit is the sign of the rank bit (reference: quantum_info/states/statevector.py:377-408 via the oracle)
+    prng = np.random.RandomState(100 + n)
+    labels = ["I" * n, "Z" * n, "X" + "I" * (n - 1), "Y" + "Z" * (n - 1), "I" * (n - 1) + "X"]
+    labels += ["".join(prng.choice(list("IXYZ"), n)) for _ in range(6)]
+    for label in labels:
+        if sum(c in "XY" for c in label) > st.n_local:
+            continue
+        want = orc.expval_pauli(ref, label)
+        got = st.expval_pauli(label)
+        assert abs(got - want) < 1e-12, (label, got, want)
     # collapse a (possibly global) qubit
     qm = n - 1
     probs = st.prob_qubit(qm)
