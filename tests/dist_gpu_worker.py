@@ -48,6 +48,10 @@ def main():
             p0, p1 = st.prob_qubit(q)
             mask = ((idx >> q) & 1).astype(bool)
             assert abs(p0 - p[~mask].sum()) < 1e-12 and abs(p1 - p[mask].sum()) < 1e-12
+        prng = np.random.RandomState(n)
+        for label in ["Z" * n, "X" + "I" * (n - 1), "Y" + "Z" * (n - 1)] + \
+                ["".join(prng.choice(list("IXYZ"), n)) for _ in range(3)]:
+            assert abs(st.expval_pauli(label) - orc.expval_pauli(ref, label)) < 1e-12, label
         u = np.random.RandomState(1).random_sample(20000)
         samples, total = st.sample_all(u)
         assert abs(total - 1.0) < 1e-12
