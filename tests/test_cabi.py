@@ -155,3 +155,16 @@ def test_quantum_volume_pass_statistics():
     assert tot["gates"] == 528
     assert tot["gates"] - tot["ops"] >= 0.35 * tot["gates"]
     assert tot["stages"] <= 1.5 * len(passes)
+
+
+def test_pass_lowering_fuzz():
+    """Random tiles / gate lists / write-back permutations through the host-only lowering (qsv_pass_info):
+    no crash, and the invariants of the lowering hold (tools/fuzz_lowering.py is the long version, also run
+    under AddressSanitizer)."""
+    import subprocess
+    import sys
+
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_lowering.py"), "7", "400"],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "done bad= 0" in out.stdout
