@@ -202,6 +202,19 @@ int qsv_norm2(const double* sv, int n_qubits, void* ws, double* host_out, void* 
 /* Number of kernels launched by this library in the calling process (bench.py's gpu_launches). */
 uint64_t qsv_launch_count(void);
 
+/* Select an equivalent variant of the pass kernel (tests and tools/; no reference counterpart): bit 8 = no
+ * gate-pair fusion, 16 = single-buffer shape instead of the warp-group shape, 32 = no L2 prefetch, 64 = no
+ * diagonal-run tables, 512 = warp groups without producer warps.  None of these changes results.  Bits 1, 2, 4
+ * (no stores / no loads / no gates: timing experiments) are accepted by the debug library only. */
+int qsv_debug_set_flags(uint32_t flags);
+
+/* Profiling aid (tools/ only; no reference counterpart): per-phase clock totals of the last warp-group pass,
+ * [CTA][group][role][8] uint64 -- role 0/1 = compute warps 0 and 7 (0 wait for the tile, 1 gates, 2 loop
+ * overhead), role 2 = the group's TMA producer warp (0 wait for the gates, 1 issue stores, 2 wait for the
+ * stores to read the buffer, 3 issue loads).  Only the debug library (libqsv_dbg.so, -DQSV_PROFILE) records
+ * them; the production library returns QSV_ERANGE. */
+int qsv_debug_profile(uint64_t* host_out, size_t n_words);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,7 +8,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqsv.so")
+# QSV_LIB_PATH selects another build of the same library (tools/ use the profiling build libqsv_dbg.so)
+LIB_PATH = os.environ.get("QSV_LIB_PATH") or os.path.join(_HERE, "libqsv.so")
 
 QSV_EINVAL = -1
 QSV_ERANGE = -2
@@ -88,6 +89,8 @@ SIGNATURES = {
     "qsv_unpack_bits": (_c_int, [_c_void_p, _c_int, _p_int32, _c_int, ctypes.c_uint32, _c_void_p, _c_size_t,
                                  _c_size_t, _c_void_p]),
     "qsv_norm2": (_c_int, [_c_void_p, _c_int, _c_void_p, _p_double, _c_void_p]),
+    "qsv_debug_set_flags": (_c_int, [ctypes.c_uint32]),
+    "qsv_debug_profile": (_c_int, [ctypes.POINTER(ctypes.c_uint64), _c_size_t]),
 }
 
 _lib = None

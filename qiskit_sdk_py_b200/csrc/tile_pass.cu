@@ -40,10 +40,11 @@
 //     tile a qubit is a constant bit of the tile's base address;
 //   * every index map is a sum of per-bit increments (padded shared-memory layout, see pad_of_bit).
 //
-// QSV_DEBUG_FLAGS (environment, profiling experiments only): 1 no write-back, 2 no loads, 4 no gates,
-// 8 no gate-pair fusion, 16 no warp-group variant, 32 no L2 prefetch, 64 no diagonal-run tables, 128 warp-group
-// variant requests the next tile after the first op instead of before it, 256 warp-group variant waits for a tile
-// with every thread polling the mbarrier instead of one polling warp + a group barrier.
+// Debug flags (qsv_debug_set_flags; the debug library also reads QSV_DEBUG_FLAGS): 1 no write-back, 2 no loads,
+// 4 no gates (these three only in the debug library), 8 no gate-pair fusion, 16 no warp-group variant, 32 no L2
+// prefetch, 64 no diagonal-run tables, 512 warp-group variant of round 1 (the compute warps issue their own bulk
+// copies; then also 128 = request the next tile after the first op instead of before it, 256 = every thread polls
+// the load mbarrier instead of one polling warp + a group barrier).
 #include <stdlib.h>
 #include <string.h>
 
@@ -55,6 +56,41 @@ namespace qsv {
 
 thread_local char g_err[512] = "";
 unsigned long long g_launches = 0;
+
+// Kernel-variant / profiling knobs (bit values: see the top of this file).  They are set explicitly through
+// qsv_debug_set_flags(); the production library accepts only the bits that select an equivalent kernel variant
+// (results unchanged) and never reads the environment, so a stray variable cannot change results.  The debug
+// library (libqsv_dbg.so, -DQSV_DEBUG_BUILD, used by tools/) also takes QSV_DEBUG_FLAGS and the bits that switch
+// loads / stores / gates off.
+[[maybe_unused]] constexpr uint32_t kResultChangingFlags = 1u | 2u | 4u;
+static uint32_t g_debug_flags = 0;
+static bool g_debug_flags_set = false;
+static uint32_t debug_flags() {
+  if (g_debug_flags_set) return g_debug_flags;
+#ifdef QSV_DEBUG_BUILD
+  static const uint32_t env_flags = [] {
+    const char* e = getenv("QSV_DEBUG_FLAGS");
+    return e ? (uint32_t)atoi(e) : 0u;
+  }();
+  return env_flags;
+#else
+  return 0u;
+#endif
+}
+
+#ifdef QSV_PROFILE
+// per (CTA, group, role) phase totals in clocks; role 0 = compute warp 0, 1 = compute warp 7, 2 = producer
+constexpr int kProfSlots = 8;
+__device__ unsigned long long g_prof[160 * 3 * 3 * kProfSlots];
+#define PROF_DECL unsigned long long prof_acc[kProfSlots] = {0}; long long prof_t0 = clock64();
+#define PROF_MARK(slot) do { const long long t1_ = clock64(); prof_acc[slot] += (unsigned long long)(t1_ - prof_t0); prof_t0 = t1_; } while (0)
+#define PROF_FLUSH(role) do { if ((threadIdx.x & 31u) == 0 && blockIdx.x < 160) \
+    for (int q_ = 0; q_ < kProfSlots; q_++) g_prof[((blockIdx.x * 3 + grp) * 3 + (role)) * kProfSlots + q_] = prof_acc[q_]; } while (0)
+#else
+#define PROF_DECL
+#define PROF_MARK(slot) do { } while (0)
+#define PROF_FLUSH(role) do { } while (0)
+#endif
 
 constexpr int kMaxOps = QSV_MAX_PASS_GATES;
 constexpr int kMaxIn = 1536;   // doubles of matrix payload per pass as passed in (48 dense 2-qubit gates)
@@ -175,6 +211,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t done;
   do {
@@ -260,7 +299,7 @@ struct __align__(16) OpRec {
 // is on the group's critical path, so the FP64 / shared-memory pipes stay busy.  Every thread loads and
 // stores the SAME shared-memory piece, so a buffer is recycled without any group-wide barrier: a thread waits
 // for its own store to have been read out (bulk wait_group.read) and then issues its own load.
-template <int kG>
+template <int kG, bool kProd>
 __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const PassDesc& d,
                                                const double2* __restrict__ tail_ent) {
   // dynamic shared memory: the (padded) tile buffers, then the per-pass tables (sized by the pass, so that
@@ -269,13 +308,17 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
   constexpr bool kDB = kG > 1;
   constexpr int kBuf = kDB ? 2 : 1;
   __shared__ __align__(8) uint64_t ld_bar[kG][kBuf];
+  __shared__ __align__(8) uint64_t done_bar[kProd ? kG : 1][kBuf];  // kProd: "gates of this buffer's tile are done"
   const int nops_all = d.nops, nst_all = d.nstages;
   const int b = d.b;
   const uint32_t tile_amps = 1u << b;
   uint32_t tile_slots = tile_amps;
   for (int j = 4; j < b; j++) tile_slots += pad_of_bit(j);
   const uint32_t ctid = threadIdx.x, cthreads = blockDim.x;  // CTA-wide (table set-up)
-  const uint32_t grp = kDB ? __shfl_sync(0xffffffffu, ctid >> 8, 0) : 0u;  // warp group (warp-uniform value)
+  // kProd: threads [0, 256 kG) are the compute warps of the groups, warp 8 kG + g is the TMA producer of group g
+  const bool is_prod = kProd && ctid >= 256u * kG;
+  const uint32_t grp_raw = is_prod ? ((ctid - 256u * kG) >> 5) : (ctid >> 8);
+  const uint32_t grp = kDB ? __shfl_sync(0xffffffffu, grp_raw, 0) : 0u;  // warp group (warp-uniform value)
   const uint32_t tid = kDB ? (ctid & 255u) : ctid;           // thread within the group
   const uint32_t kPT = kDB ? 256u : cthreads;                // threads per group
   double2* tile = bufs + (size_t)(grp * kBuf) * tile_slots;  // the group's current tile buffer
@@ -307,8 +350,12 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
   // the pass is tile-invariant, so it is digested once into shared-memory tables / registers ----
   u64 tile_mask = 0;  // physical bit mask of the tile qubits
   for (int j = 0; j < b; j++) tile_mask |= 1ull << d.tb[j];
-  if (ctid == 0)
-    for (int q = 0; q < kG * kBuf; q++) mbar_init(&ld_bar[0][0] + q, kDB ? kPT >> 5 : kPT);  // kDB: one arrival per warp
+  if (ctid == 0) {
+    // kDB: one arrival per issuing warp (kProd: the producer's single arrive.expect_tx)
+    for (int q = 0; q < kG * kBuf; q++) mbar_init(&ld_bar[0][0] + q, kProd ? 1u : kDB ? kPT >> 5 : kPT);
+    if constexpr (kProd)
+      for (int q = 0; q < kG * kBuf; q++) mbar_init(&done_bar[0][0] + q, kPT >> 5);  // one arrival per compute warp
+  }
   for (int idx = ctid; idx < nops * 64; idx += cthreads) {
     const int o = idx >> 6, e = idx & 63;
     const PassOp& op = d.ops[o];
@@ -438,7 +485,70 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
   const u64 t_end = t_begin + per < n_tiles ? t_begin + per : n_tiles;
   u64 base = t_begin < n_tiles ? tile_base(d, t_begin) : 0;
   uint32_t parity = 0;
-  if constexpr (kDB) {  // prologue: the first tile goes into buffer 0
+  if constexpr (kProd) {
+    // ---- TMA producer warp of group `grp`: the compute warps of the group never issue a bulk copy, never poll
+    // for a store to drain and need no group-wide barrier per tile.  Per tile t (buffer t & 1): wait until the
+    // group's 8 compute warps have arrived on done_bar (gates finished, generic-proxy writes fenced), write the
+    // tile back, wait until the bulk stores have READ the buffer, then request tile t + 2 into it. ----
+    if (is_prod) {
+      if (t_begin >= t_end) return;
+      const uint32_t n_pc = np_ld;  // pieces per tile (np_ld == np_st in this shape)
+      u64 base_st = base;           // tile being written back
+      u64 base_ld = base;           // tile being requested
+      auto issue_load = [&](uint32_t buf) {
+        if (elect_one()) {
+          if (ld_on) {
+            mbar_arrive_expect_tx(&ld_bar[grp][buf], n_pc * ld_bytes);
+            const char* gsrc = reinterpret_cast<const char*>(sv + base_ld);
+            char* sdst = reinterpret_cast<char*>(bufs + (size_t)(grp * kBuf + buf) * tile_slots);
+            for (uint32_t p = 0; p < n_pc; p++)
+              bulk_load(sdst + d.pc_s[p], gsrc + d.pc_g[p], ld_bytes, &ld_bar[grp][buf]);
+          } else {
+            mbar_arrive(&ld_bar[grp][buf]);  // profiling without loads: keep the hand-shake
+          }
+        }
+      };
+      // prologue: tiles t_begin and t_begin + 1
+      issue_load(0);
+      base_ld = ((base_ld | tile_mask) + 1) & ~tile_mask;
+      if (t_begin + 1 < t_end) {
+        issue_load(1);
+        base_ld = ((base_ld | tile_mask) + 1) & ~tile_mask;
+      }
+      uint32_t i = 0;
+      PROF_DECL
+      for (u64 t = t_begin; t < t_end; t++, i++) {
+        const uint32_t buf = i & 1u;
+        mbar_wait(&done_bar[grp][buf], (i >> 1) & 1u);
+        PROF_MARK(0);
+        if (elect_one()) {
+          if (st_on) {
+            char* gdst = reinterpret_cast<char*>(sv + base_st);
+            const char* ssrc = reinterpret_cast<const char*>(bufs + (size_t)(grp * kBuf + buf) * tile_slots);
+            for (uint32_t p = 0; p < n_pc; p++) bulk_store(gdst + d.pc_g[p], ssrc + d.pc_s[p], st_bytes);
+            bulk_commit();
+          }
+        }
+        __syncwarp();
+        PROF_MARK(1);
+        if (elect_one())
+          if (t + 2 < t_end) bulk_wait_read();  // the buffer has been read out: it may be overwritten
+        __syncwarp();
+        PROF_MARK(2);
+        base_st = ((base_st | tile_mask) + 1) & ~tile_mask;
+        if (t + 2 < t_end) {
+          issue_load(buf);
+          base_ld = ((base_ld | tile_mask) + 1) & ~tile_mask;
+        }
+        __syncwarp();
+        PROF_MARK(3);
+      }
+      if (elect_one()) bulk_wait_read();
+      PROF_FLUSH(2);
+      return;
+    }
+  }
+  if constexpr (kDB && !kProd) {  // prologue: the first tile goes into buffer 0
     if (ld_on && t_begin < t_end) {
       if (elect_one()) {
         mbar_arrive_expect_tx(&ld_bar[grp][0], ppw * ld_bytes);
@@ -452,12 +562,13 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
     }
   }
   uint32_t t_idx = 0;
+  PROF_DECL
   for (u64 t = t_begin; t < t_end; t++, t_idx++, base = ((base | tile_mask) + 1) & ~tile_mask) {
     bool next_issued = true;
     // kDB: load of the group's NEXT tile into its other buffer, issued by every thread for its own piece once
     // its write-back piece of the previous tile has left that buffer (no barrier needed, see above)
     auto issue_next = [&]() {
-      if constexpr (kDB) {
+      if constexpr (kDB && !kProd) {
         if (elect_one()) {  // the lane that also issued the write-back of these pieces
           bulk_wait_read();
           const u64 nb = ((base | tile_mask) + 1) & ~tile_mask;
@@ -474,7 +585,16 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
         next_issued = true;
       }
     };
-    if constexpr (kDB) {
+    if constexpr (kProd) {
+      // ---- the group's producer warp requested this tile two tiles ago; every thread acquires the TMA writes ----
+      const uint32_t cur = t_idx & 1u;
+      tile = bufs + (size_t)(grp * kBuf + cur) * tile_slots;
+      tb8 = reinterpret_cast<const char*>(tile) + (lane & 1u) * 8u;
+      PROF_MARK(2);
+      mbar_wait(&ld_bar[grp][cur], (t_idx >> 1) & 1u);
+      PROF_MARK(0);
+    }
+    if constexpr (kDB && !kProd) {
       // ---- this tile was requested one tile ago ----
       const uint32_t cur = t_idx & 1u;
       tile = bufs + (size_t)(grp * kBuf + cur) * tile_slots;
@@ -796,6 +916,14 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
     // ---- write-back: one HBM write of the tile (TMA bulk copies), optionally with the tile qubits
     // permuted: position j receives the content of tile bit src_of[j] (a free qubit remap) ----
     fence_proxy_async();  // the gates' generic-proxy stores must be visible to the async proxy
+    if constexpr (kProd) {
+      // hand the buffer to the producer warp: one arrival per compute warp (release), no group-wide barrier --
+      // the next tile lives in the other buffer
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&done_bar[grp][t_idx & 1u]);
+      PROF_MARK(1);
+      continue;
+    }
     gsync();
     if (kDB && st_on) {
       if (elect_one()) {  // one lane per warp, its warp's pieces, addresses in uniform registers
@@ -820,14 +948,16 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
     }
   }
   bulk_wait_read();
+  if constexpr (kProd)
+    if (wid == 0 || wid == 7) PROF_FLUSH(wid == 0 ? 0 : 1);
 }
 
 // One body, three launch shapes: several resident CTAs per SM (4 x 256 threads for the default 11-qubit
 // tile) keep more tiles in flight, which is what hides the HBM round trip of each CTA.
-template <int kBlock, int kMinBlocks, int kG = 1>
+template <int kBlock, int kMinBlocks, int kG = 1, bool kProd = false>
 __global__ void __launch_bounds__(kBlock, kMinBlocks)
 tile_pass_kernel(double2* __restrict__ sv, const __grid_constant__ PassDesc d, const double2* __restrict__ tail_ent) {
-  tile_pass_body<kG>(sv, d, tail_ent);
+  tile_pass_body<kG, kProd>(sv, d, tail_ent);
 }
 
 // ---- dense k-qubit gate, 3 <= k <= 12: out-of-place inside the tile (two smem buffers) ----
@@ -1073,7 +1203,8 @@ static int build_stages(const HostOp* ops, int n_ops, int b, int* order, PassSta
 // (a thread recycles the shared-memory piece it owns), and tables that fit beside six tile buffers.
 constexpr int kGroupTileQubits = 11;
 constexpr u64 kGroupMinTiles = 2048;
-constexpr size_t kGroupStaticSmem = 3 * 2 * 8 + 3 * 16 * 2 * 16 + 3 * 2 * 64 * 16 + 2 * 56 * 2 + 2 * kMaxTail;
+constexpr size_t kGroupStaticSmem = 2 * 3 * 2 * 8 + 3 * 16 * 2 * 16 + 3 * 2 * 64 * 16 + 2 * 56 * 2 + 2 * kMaxTail;
+constexpr int kGroupThreads = 3 * 256 + 3 * 32;  // three groups of 8 compute warps + one TMA producer warp each
 constexpr size_t kMaxSmemPerBlock = 232448;  // 227 KiB (sm_100 opt-in limit, static + dynamic)
 
 static bool g_attr_set[64] = {false};
@@ -1109,6 +1240,13 @@ static int ensure_attrs() {
     QSV_CUDA(cudaFuncSetAttribute(tile_pass_kernel<768, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(kMaxSmemPerBlock - fa.sharedSizeBytes)));
     QSV_CUDA(cudaFuncSetAttribute(tile_pass_kernel<768, 1, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    QSV_CUDA(cudaFuncGetAttributes(&fa, tile_pass_kernel<kGroupThreads, 1, 3, true>));
+    if (fa.sharedSizeBytes > kGroupStaticSmem + 64)
+      return fail(QSV_ERANGE, "tile_pass_kernel<864,1,3,true>: static shared memory grew");
+    QSV_CUDA(cudaFuncSetAttribute(tile_pass_kernel<kGroupThreads, 1, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(kMaxSmemPerBlock - fa.sharedSizeBytes)));
+    QSV_CUDA(cudaFuncSetAttribute(tile_pass_kernel<kGroupThreads, 1, 3, true>,
+                                  cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     QSV_CUDA(cudaFuncSetAttribute(dense_k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(2 * (sizeof(double2) << 12) + 4096 * sizeof(uint32_t))));
     g_attr_set[dev] = true;
@@ -1280,7 +1418,7 @@ static int lower_pass(PassDesc& d, PassPlan& plan, int n, const int32_t* tile_qu
     }
     moff += ndbl;
   }
-  if (const char* e = getenv("QSV_DEBUG_FLAGS")) d.flags = (uint32_t)atoi(e);
+  d.flags = debug_flags();
 
   // ---- pair fusion: hops_in (program order) -> hops (fused, still a valid order) ----
   HostOp hops[kMaxOps];
@@ -1722,7 +1860,7 @@ static int lower_pass(PassDesc& d, PassPlan& plan, int n, const int32_t* tile_qu
     if (ident && smem3 + kGroupStaticSmem + 64 <= kMaxSmemPerBlock) {
       plan.groups = true;
       plan.smem = smem3;
-      plan.threads = 768;
+      plan.threads = kGroupThreads;
     }
   }
   plan.n_in = n_in;
@@ -1749,7 +1887,11 @@ static int launch_pass(double* sv, int n, const int32_t* tile_qubits, int n_tile
   const int threads = plan.threads;
   if (plan.groups) {
     const unsigned grid3 = std::min<unsigned>((d.n_tiles + 2) / 3, (unsigned)sm_count());
-    tile_pass_kernel<768, 1, 3><<<grid3, 768, smem, stream>>>(reinterpret_cast<double2*>(sv), d, d_tail);
+    if (d.flags & 512u)  // A/B: compute warps issue their own bulk copies (round-1 shape)
+      tile_pass_kernel<768, 1, 3><<<grid3, 768, smem, stream>>>(reinterpret_cast<double2*>(sv), d, d_tail);
+    else
+      tile_pass_kernel<kGroupThreads, 1, 3, true><<<grid3, kGroupThreads, smem, stream>>>(reinterpret_cast<double2*>(sv), d,
+                                                                                         d_tail);
     QSV_LAUNCHED();
     return 0;
   }
@@ -1868,6 +2010,29 @@ int qsv_apply_pass_tail(double* sv, int n, const int32_t* tile_qubits, int n_til
 }
 
 size_t qsv_tail_scratch_bytes(void) { return sizeof(double) * 8 * kMaxTail; }
+
+int qsv_debug_set_flags(uint32_t flags) {
+#ifndef QSV_DEBUG_BUILD
+  if (flags & kResultChangingFlags)
+    return fail(QSV_EINVAL, "qsv_debug_set_flags: bits 1, 2, 4 (no stores / loads / gates) need the debug library");
+#endif
+  g_debug_flags = flags;
+  g_debug_flags_set = true;
+  return 0;
+}
+
+int qsv_debug_profile(uint64_t* host_out, size_t n_words) {
+#ifdef QSV_PROFILE
+  if (!host_out || n_words > sizeof(g_prof) / 8) return fail(QSV_EINVAL, "qsv_debug_profile: bad arguments");
+  QSV_CUDA(cudaDeviceSynchronize());
+  QSV_CUDA(cudaMemcpyFromSymbol(host_out, g_prof, n_words * 8));
+  return 0;
+#else
+  (void)host_out;
+  (void)n_words;
+  return fail(QSV_ERANGE, "qsv_debug_profile: this library was built without -DQSV_PROFILE");
+#endif
+}
 
 int qsv_pass_info(int n, const int32_t* tile_qubits, int n_tile, const qsv_gate_t* gates, int n_gates,
                   const int32_t* dest_qubits, int32_t* info) {

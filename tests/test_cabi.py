@@ -116,23 +116,42 @@ def test_pass_lowering_is_host_only_and_fuses_gate_pairs():
         DeviceState.pass_info(20, tile, [dense(4, 15)])
 
 
-def test_pass_kernel_variant_selection(monkeypatch):
-    """Host-only: which passes run on the three-group double-buffered variant of the pass kernel (768 threads,
+GROUP_THREADS = 3 * 256 + 3 * 32  # three groups of 8 compute warps + one TMA producer warp each
+
+
+def test_pass_kernel_variant_selection():
+    """Host-only: which passes run on the three-group double-buffered variant of the pass kernel (864 threads,
     six tile buffers) and which on the single-buffer variant (one warp per 2^8 amplitudes of the tile)."""
     from qiskit_sdk_py_b200.engine import DeviceState
 
     tile = list(range(11))
     big = DeviceState.pass_info(22, tile, [])
-    assert big["threads"] == 768 and big["smem_bytes"] > 6 * 2048 * 16
+    assert big["threads"] == GROUP_THREADS and big["smem_bytes"] > 6 * 2048 * 16
     assert DeviceState.pass_info(21, tile, [])["threads"] == 256                       # too few tiles
     assert DeviceState.pass_info(24, list(range(12)), [])["threads"] == 512            # 12-qubit tile
     assert DeviceState.pass_info(24, list(range(10)), [])["threads"] == 128            # 10-qubit tile
     assert DeviceState.pass_info(24, [0, 1] + list(range(5, 14)), [])["threads"] == 256  # 64-byte pieces
-    assert DeviceState.pass_info(24, [0, 1, 2] + list(range(5, 13)), [])["threads"] == 768  # 128-byte pieces
+    assert DeviceState.pass_info(24, [0, 1, 2] + list(range(5, 13)), [])["threads"] == GROUP_THREADS  # 128-byte pieces
     remap = DeviceState.pass_info(24, tile, [], dest=[1, 0] + list(range(2, 11)))
     assert remap["threads"] == 256                                                     # permuted write-back
-    monkeypatch.setenv("QSV_DEBUG_FLAGS", "16")
-    assert DeviceState.pass_info(22, tile, [])["threads"] == 256
+    lib = _lib.load()
+    assert lib.qsv_debug_set_flags(16) == 0
+    try:
+        assert DeviceState.pass_info(22, tile, [])["threads"] == 256
+        # the bits that switch loads / stores / gates off exist only in the debug library
+        assert lib.qsv_debug_set_flags(1) == _lib.QSV_EINVAL
+        assert DeviceState.pass_info(22, tile, [])["threads"] == 256
+    finally:
+        assert lib.qsv_debug_set_flags(0) == 0
+    assert DeviceState.pass_info(22, tile, [])["threads"] == GROUP_THREADS
+
+
+def test_environment_cannot_change_results(monkeypatch):
+    """the production library must ignore QSV_DEBUG_FLAGS (flags 1/2/4 would silently corrupt results)."""
+    from qiskit_sdk_py_b200.engine import DeviceState
+
+    monkeypatch.setenv("QSV_DEBUG_FLAGS", "23")
+    assert DeviceState.pass_info(22, list(range(11)), [])["threads"] == GROUP_THREADS
 
 
 def test_quantum_volume_pass_statistics():
@@ -151,7 +170,7 @@ def test_quantum_volume_pass_statistics():
         for key in tot:
             tot[key] += info[key]
         # every pass fits the three-group double-buffered variant: six tile buffers + the pass's tables
-        assert info["threads"] == 768 and info["smem_bytes"] <= 227 * 1024 - 8400
+        assert info["threads"] == GROUP_THREADS and info["smem_bytes"] <= 227 * 1024 - 8400
     assert tot["gates"] == 528
     assert tot["gates"] - tot["ops"] >= 0.35 * tot["gates"]
     assert tot["stages"] <= 1.5 * len(passes)

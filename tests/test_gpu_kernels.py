@@ -208,10 +208,11 @@ def test_pass_with_diagonal_tail(n, tile_size, n_ops, n_tail):
 
 
 @pytest.mark.parametrize("n,seed,n_tail", [(22, 1, 0), (22, 2, 25), (23, 3, 0), (22, 4, 60)])
-def test_group_kernel_passes(n, seed, n_tail, monkeypatch):
+def test_group_kernel_passes(n, seed, n_tail):
     """Passes with an 11-qubit tile and >= 2048 tiles run on the three-group double-buffered variant of the pass
-    kernel (tile_pass_kernel<768,1,3>): same result as the oracle, and bit for bit the result of the
-    single-buffer variant (QSV_DEBUG_FLAGS=16), whose arithmetic per tile is identical."""
+    kernel (tile_pass_kernel<864,1,3,true>: 8 compute warps + a TMA producer warp per group): same result as the
+    oracle, and bit for bit the result of the variant without producer warps (flag 512) and of the single-buffer
+    variant (flag 16), whose arithmetic per tile is identical."""
     from qiskit_sdk_py_b200.engine import DeviceState
 
     rng = np.random.RandomState(seed)
@@ -234,21 +235,26 @@ def test_group_kernel_passes(n, seed, n_tail, monkeypatch):
         plan.append((tile, ops, _random_tail(n, tile, n_tail, rng)))
     plan.append(([0, 1, 2, 3] + list(range(n - 7, n)), [], []))  # copy-only pass
     results = []
-    for flags in ("0", "16"):
-        monkeypatch.setenv("QSV_DEBUG_FLAGS", flags)
-        for tile, ops, tail in plan:
-            assert DeviceState.pass_info(n, tile, ops)["threads"] == (768 if flags == "0" else 256)
-        st = make_state(n, vec)
-        for tile, ops, tail in plan:
-            st.apply_pass(tile, ops, tail=tail or None)
-        results.append(st.download())
-        del st
+    lib = _lib.load()
+    try:
+        for flags, threads in ((0, 864), (512, 768), (16, 256)):
+            assert lib.qsv_debug_set_flags(flags) == 0
+            for tile, ops, tail in plan:
+                assert DeviceState.pass_info(n, tile, ops)["threads"] == (threads if flags != 512 else 864)
+            st = make_state(n, vec)
+            for tile, ops, tail in plan:
+                st.apply_pass(tile, ops, tail=tail or None)
+            results.append(st.download())
+            del st
+    finally:
+        lib.qsv_debug_set_flags(0)
     ref = vec.copy()
     for tile, ops, tail in plan:
         for op in ops + tail:
             ref = oracle_apply(ref, op, n)
     assert np.max(np.abs(results[0] - ref)) < TOL
     assert np.array_equal(results[0], results[1])
+    assert np.array_equal(results[0], results[2])
 
 
 def test_tail_argument_errors():

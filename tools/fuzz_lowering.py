@@ -49,7 +49,7 @@ for it in range(int(sys.argv[2]) if len(sys.argv)>2 else 2000):
         if "payload too large" in msg or "grid too large" in msg: continue
         print("ERR",n,tile,len(ops),msg); bad+=1; continue
     assert info["gates"]==len(ops) and info["ops"]<=max(1,len(ops)) and info["fused3"]<=info["ops"], info
-    assert info["threads"] in (32,64,128,256,512,768), info
+    assert info["threads"] in (32,64,128,256,512,864), info
     assert info["smem_bytes"]<=232448, info
     assert info["stages"]<=max(1,info["ops"]), info
 print("done bad=",bad)
