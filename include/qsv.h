@@ -17,7 +17,8 @@
  *     qubits[0] is the LEAST significant bit of the row/column index (qasm_simulator.py:145-161).
  *   - Plain pointers and sizes only.  `sv` / `probs` / `ws` are DEVICE pointers owned by the caller;
  *     `host_*` are HOST pointers owned by the caller.  `stream` is a cudaStream_t passed as void*
- *     (NULL = default stream).  The library keeps no per-state handle and allocates no device memory.
+ *     (NULL = default stream).  The library keeps no per-state handle and allocates no device memory behind the
+ *     caller's back; qsv_alloc / qsv_free are there for callers that have no allocator of their own.
  *   - Every function returns 0 on success, a negative QSV_E* code for argument errors, or a positive
  *     cudaError_t.  qsv_last_error() returns a thread-local message for the last failure.
  *   - One host thread per state at a time (the reference backends are not re-entrant either;
@@ -154,9 +155,9 @@ int qsv_marginal(const double* sv, int n_qubits, const int32_t* measured_sorted,
  * for the caller-supplied uniforms u (RandomState.random_sample(shots)).
  *   src            : from_amplitudes != 0 -> 2^log2_bins complex amplitudes, p_i = |psi_i|^2
  *                    (all qubits measured); else 2^log2_bins doubles (a marginal from qsv_marginal).
- *   exact_order    : flags.  Bit 0 set -> the CDF is accumulated strictly left to right in float64,
- *                    like numpy's cumsum, so samples equal the reference's bit for bit (serial, meant
- *                    for log2_bins <= ~26); clear -> blocked parallel scan (any size).  Bit 1 set ->
+ *   exact_order    : flags.  Bit 0 set -> the CDF is numpy's cumsum bit for bit (one float64 running sum, left to
+ *                    right, evaluated in parallel; p_i = np.abs(psi_i)**2 with numpy's rounding), so samples
+ *                    equal the reference's; clear -> blocked parallel scan.  Bit 1 set ->
  *                    skip the sum-to-1 check (a shard of a multi-GPU state sums to less than 1).
  *   host_total     : receives cdf[-1] before normalisation (must be ~1).
  * Returns QSV_ENORM if |total - 1| > sqrt(eps) as numpy's choice() does.  Synchronises the stream. */
@@ -164,6 +165,29 @@ size_t qsv_sample_workspace_bytes(int log2_bins, int shots);
 int qsv_sample(const double* src, int from_amplitudes, int log2_bins, const double* host_uniforms,
                int shots, int64_t* host_out_idx, int exact_order, void* ws, double* host_total,
                void* stream);
+
+/* The phases of qsv_sample's exact-order path, callable one by one so that the CDF can run across the SHARDS of
+ * a sharded state in the reference's bin order (numpy's cumsum is one running sum over all 2^n bins; shard r
+ * continues where shard r-1 stopped).  All use the workspace of qsv_sample_workspace_bytes(log2_bins, shots),
+ * which carries the state from one phase to the next; src / from_amplitudes / log2_bins as in qsv_sample.
+ *   qsv_cdf_prepare   blocked sums of the 1024-bin chunks and their prefix; host_approx_total = the array's sum
+ *                     (rounded differently from the running sum: only used to steer the next phase).
+ *   qsv_cdf_classify  per chunk: can the running sum be advanced by an integer number of ulps?  approx_offset =
+ *                     approximate running sum before this array (sum of the previous shards' approx totals).
+ *   qsv_cdf_chain     the running sum itself, bit for bit numpy's, starting from exact_start (0 for the first
+ *                     shard, else the previous shard's host_exact_end); serial in the shards, milliseconds each.
+ *   qsv_cdf_search    searchsorted(cdf / total, u, 'right') restricted to this array: bin index, or -1 if the
+ *                     shot falls before the array (exact_start / total > u), -2 if after it.
+ * Together they replace RandomState.choice in _add_sample_measure (qasm_simulator.py:213) for n > 33 qubits.
+ * Each synchronises the stream. */
+int qsv_cdf_prepare(const double* src, int from_amplitudes, int log2_bins, void* ws, double* host_approx_total,
+                    void* stream);
+int qsv_cdf_classify(const double* src, int from_amplitudes, int log2_bins, double approx_offset, void* ws,
+                     void* stream);
+int qsv_cdf_chain(const double* src, int from_amplitudes, int log2_bins, double exact_start, void* ws,
+                  double* host_exact_end, void* stream);
+int qsv_cdf_search(const double* src, int from_amplitudes, int log2_bins, double exact_start, double total,
+                   const double* host_uniforms, int shots, int64_t* host_out_idx, void* ws, void* stream);
 
 /* <psi| P |psi> for the Pauli string with Z (or Y) on the bits of z_mask and X (or Y) on the bits of x_mask,
  * times (phase_re + i phase_im) for the with-X case.  Replaces the serial Cython loops
@@ -196,8 +220,22 @@ int qsv_pack_bits(const double* sv, int n_local, const int32_t* local_qubits, in
 int qsv_unpack_bits(double* sv, int n_local, const int32_t* local_qubits, int k, uint32_t pattern,
                     const double* dev_buf, size_t chunk_begin, size_t chunk_amps, void* stream);
 
+/* dev_dst (2^log2_dst doubles) = 0 everywhere except dev_dst[base | sum_i bit_i(s) << dest_bit[i]] = dev_src[s]
+ * for s in [0, 2^m): a shard's marginal over its local measured qubits lands in the bins of the full marginal that
+ * its rank bits (base) select; the ranks' arrays are then all-reduced (qasm_simulator.py:202-209 across shards). */
+int qsv_scatter_bits(const double* dev_src, int m, const int32_t* dest_bit, uint64_t base, double* dev_dst,
+                     int log2_dst, void* stream);
+
 /* Sum of |psi|^2 over the local shard (for distributed normalisation / sampling). */
 int qsv_norm2(const double* sv, int n_qubits, void* ws, double* host_out, void* stream);
+
+/* Device memory for callers without an allocator of their own (an FFI consumer per INTEGRATION.md; the Python host
+ * uses them for state snapshots): cudaMalloc / cudaFree / cudaMemcpyAsync device-to-device on `stream`.  The
+ * snapshot / restore of a shot's starting state (qasm_simulator.py:512-519 re-initialises per shot) is one
+ * qsv_copy_d2d. */
+int qsv_alloc(void** dev_out, size_t bytes);
+int qsv_free(void* dev_ptr);
+int qsv_copy_d2d(void* dev_dst, const void* dev_src, size_t bytes, void* stream);
 
 /* Number of kernels launched by this library in the calling process (bench.py's gpu_launches). */
 uint64_t qsv_launch_count(void);

@@ -78,6 +78,11 @@ SIGNATURES = {
     "qsv_sample_workspace_bytes": (_c_size_t, [_c_int, _c_int]),
     "qsv_sample": (_c_int, [_c_void_p, _c_int, _c_int, _c_void_p, _c_int, _c_void_p, _c_int, _c_void_p,
                             _p_double, _c_void_p]),
+    "qsv_cdf_prepare": (_c_int, [_c_void_p, _c_int, _c_int, _c_void_p, _p_double, _c_void_p]),
+    "qsv_cdf_classify": (_c_int, [_c_void_p, _c_int, _c_int, _c_double, _c_void_p, _c_void_p]),
+    "qsv_cdf_chain": (_c_int, [_c_void_p, _c_int, _c_int, _c_double, _c_void_p, _p_double, _c_void_p]),
+    "qsv_cdf_search": (_c_int, [_c_void_p, _c_int, _c_int, _c_double, _c_double, _c_void_p, _c_int, _c_void_p,
+                                _c_void_p, _c_void_p]),
     "qsv_chop": (_c_int, [_c_void_p, _c_int, _c_double, _c_void_p]),
     "qsv_download": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_void_p]),
     "qsv_pack_half": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_size_t, _c_size_t, _c_void_p]),
@@ -89,6 +94,10 @@ SIGNATURES = {
     "qsv_unpack_bits": (_c_int, [_c_void_p, _c_int, _p_int32, _c_int, ctypes.c_uint32, _c_void_p, _c_size_t,
                                  _c_size_t, _c_void_p]),
     "qsv_norm2": (_c_int, [_c_void_p, _c_int, _c_void_p, _p_double, _c_void_p]),
+    "qsv_scatter_bits": (_c_int, [_c_void_p, _c_int, _p_int32, ctypes.c_uint64, _c_void_p, _c_int, _c_void_p]),
+    "qsv_alloc": (_c_int, [ctypes.POINTER(_c_void_p), _c_size_t]),
+    "qsv_free": (_c_int, [_c_void_p]),
+    "qsv_copy_d2d": (_c_int, [_c_void_p, _c_void_p, _c_size_t, _c_void_p]),
     "qsv_debug_set_flags": (_c_int, [ctypes.c_uint32]),
     "qsv_debug_profile": (_c_int, [ctypes.POINTER(ctypes.c_uint64), _c_size_t]),
 }

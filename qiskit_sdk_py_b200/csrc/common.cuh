@@ -33,7 +33,19 @@ inline int fail(int code, const char* msg) {
   } while (0)
 
 constexpr int kThreads = 256;
-constexpr int kNumSMs = 148;  // B200
+
+// SM count of the current device (148 on a B200), queried once per device; grids are sized from it.
+inline int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (!cached[dev]) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    cached[dev] = v;
+  }
+  return cached[dev];
+}
 
 typedef unsigned long long u64;
 

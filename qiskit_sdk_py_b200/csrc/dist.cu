@@ -60,6 +60,25 @@ unpack_bits_kernel(double2* __restrict__ sv, const __grid_constant__ SubDesc d, 
   for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j < count; j += stride) sv[sub_index(d, begin + j)] = buf[j];
 }
 
+// dst[base | deposit(s)] = src[s]: the marginal of a shard over its local measured bits goes to the bins its
+// rank bits select in the marginal of the whole register (the others stay zero; the shards are then all-reduced)
+struct ScatterDesc {
+  int32_t m;
+  int32_t dest_bit[40];
+  uint64_t base;
+};
+
+__global__ void __launch_bounds__(kThreads)
+scatter_bits_kernel(const double* __restrict__ src, const __grid_constant__ ScatterDesc d, double* __restrict__ dst) {
+  const u64 bins = 1ull << d.m;
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 sidx = (u64)blockIdx.x * blockDim.x + threadIdx.x; sidx < bins; sidx += stride) {
+    u64 t = d.base;
+    for (int i = 0; i < d.m; i++) t |= ((sidx >> i) & 1ull) << d.dest_bit[i];
+    dst[t] = src[sidx];
+  }
+}
+
 static int make_sub(int n_local, const int32_t* local_qubits, int k, uint32_t pattern, SubDesc* d) {
   if (k < 1 || k > 8 || k >= n_local || !local_qubits) return -1;
   int order[8];
@@ -80,7 +99,7 @@ static int make_sub(int n_local, const int32_t* local_qubits, int k, uint32_t pa
 
 static int grid_for(u64 n) {
   u64 blocks = (n + kThreads - 1) / kThreads;
-  const u64 cap = (u64)kNumSMs * 16;
+  const u64 cap = (u64)sm_count() * 16;
   return (int)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
 }
 
@@ -110,6 +129,29 @@ int qsv_unpack_half(double* sv, int n_local, int L, int bitv, const double* dev_
   if (count == 0) return 0;
   unpack_half_kernel<<<grid_for(count), kThreads, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<double2*>(sv), L, (u64)bitv, reinterpret_cast<const double2*>(dev_buf), begin, count);
+  QSV_LAUNCHED();
+  return 0;
+}
+
+int qsv_scatter_bits(const double* dev_src, int m, const int32_t* dest_bit, uint64_t base, double* dev_dst,
+                     int log2_dst, void* stream) {
+  if (!dev_src || !dev_dst || m < 0 || m > 40 || log2_dst < m || log2_dst > 40 || (m > 0 && !dest_bit) ||
+      base >= (1ull << log2_dst))
+    return fail(QSV_EINVAL, "qsv_scatter_bits: bad arguments");
+  ScatterDesc d;
+  d.m = m;
+  d.base = base;
+  uint64_t seen = 0;
+  for (int i = 0; i < m; i++) {
+    const int b = dest_bit[i];
+    if (b < 0 || b >= log2_dst || ((seen >> b) & 1ull) || ((base >> b) & 1ull))
+      return fail(QSV_EINVAL, "qsv_scatter_bits: dest bits must be distinct, below log2_dst and clear in base");
+    seen |= 1ull << b;
+    d.dest_bit[i] = b;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  QSV_CUDA(cudaMemsetAsync(dev_dst, 0, sizeof(double) << log2_dst, s));
+  scatter_bits_kernel<<<grid_for(1ull << m), kThreads, 0, s>>>(dev_src, d, dev_dst);
   QSV_LAUNCHED();
   return 0;
 }

@@ -12,7 +12,7 @@
 
 namespace qsv {
 
-constexpr int kReduceBlocks = kNumSMs * 8;   // fixed grid -> deterministic two-stage reduction
+constexpr int kReduceBlocks = 1184;           // fixed grid (8 per SM of a B200) -> deterministic two-stage reduction
 constexpr int kChunkLog2 = 10;               // sampler chunk: 1024 bins
 constexpr int kChunk = 1 << kChunkLog2;
 
@@ -167,11 +167,28 @@ marginal_finish_kernel(const double* __restrict__ partial, u64 bins, int log2_pa
 }
 
 // ---- sampler ----
-template <bool kAmps>
+// |z|^2 exactly as the reference computes it: np.abs(psi) ** 2 (qasm_simulator.py:207).  numpy's complex128
+// absolute (SIMD loop of loops_unary_complex.dispatch.c; AVX2/AVX-512 builds fuse the multiply-add) is
+//     a = max * sqrt(fma(r, r, 1)),  r = min / max,  max/min of (|re|, |im|),  0 if max == 0
+// -- not hypot() and not sqrt(re^2 + im^2); each differs from it in the last bit for about a third of random
+// inputs -- and ** 2 is a * a.  Division, fma, sqrt and product are correctly rounded on both sides, so the
+// probabilities agree bit for bit (tests/test_gpu_kernels.py::test_exact_cdf_from_amplitudes_is_numpy_abs2).
+__device__ __forceinline__ double numpy_abs2(double2 a) {
+  const double ax = fabs(a.x), ay = fabs(a.y);
+  const double mx = fmax(ax, ay), mn = fmin(ax, ay);
+  if (mx == 0.0) return 0.0;
+  const double r = __ddiv_rn(mn, mx);
+  const double h = __dmul_rn(__dsqrt_rn(__fma_rn(r, r, 1.0)), mx);
+  return __dmul_rn(h, h);
+}
+
+// kExact: the sampler's exact-order path (bitwise the reference's probabilities); otherwise re^2 + im^2 with one
+// rounding less, for sums that are compared with a tolerance or only steer the exact path.
+template <bool kAmps, bool kExact = true>
 __device__ __forceinline__ double load_p(const void* src, u64 i) {
   if (kAmps) {
     const double2 a = reinterpret_cast<const double2*>(src)[i];
-    return fma(a.x, a.x, a.y * a.y);
+    return kExact ? numpy_abs2(a) : fma(a.x, a.x, a.y * a.y);
   }
   return reinterpret_cast<const double*>(src)[i];
 }
@@ -181,11 +198,11 @@ __device__ __forceinline__ double load_p(const void* src, u64 i) {
 // the running sum at the end of every chunk.
 template <bool kAmps>
 __global__ void __launch_bounds__(1024)
-cdf_sequential_kernel(const void* __restrict__ src, u64 bins, double* __restrict__ chunk_end) {
+cdf_sequential_kernel(const void* __restrict__ src, u64 bins, double start, double* __restrict__ chunk_end) {
   __shared__ double buf[2][kChunk];
   const u64 nchunks = (bins + kChunk - 1) / kChunk;
   const int tid = threadIdx.x;
-  double run = 0.0;
+  double run = start;
   // prologue: stage chunk 0
   for (int i = tid; i < kChunk; i += 1024) buf[0][i] = (u64)i < bins ? load_p<kAmps>(src, i) : 0.0;
   __syncthreads();
@@ -223,12 +240,13 @@ constexpr int kModeZero = 0, kModeInt = 1, kModeSlow = 2;
 
 template <bool kAmps>
 __global__ void __launch_bounds__(kThreads)
-chunk_classify_kernel(const void* __restrict__ src, u64 bins, const double* __restrict__ aprefix,
+chunk_classify_kernel(const void* __restrict__ src, u64 bins, const double* __restrict__ aprefix, double offset,
                       int* __restrict__ meta, long long* __restrict__ inc) {
   __shared__ long long s_sum[kThreads / 32];
   __shared__ int s_flag[kThreads / 32];
   const u64 c = blockIdx.x;
-  const double a_prev = c > 0 ? aprefix[c - 1] : 0.0, a_cur = aprefix[c];
+  // `offset`: (approximate) running sum before this array -- the shards before this one of a sharded state
+  const double a_prev = offset + (c > 0 ? aprefix[c - 1] : 0.0), a_cur = offset + aprefix[c];
   const double lo = a_prev * (1.0 - 9.313225746154785e-10), hi = a_cur * (1.0 + 9.313225746154785e-10);  // 2^-30 margins
   int k = 0;
   bool int_ok = lo > 0.0;
@@ -317,11 +335,11 @@ template <bool kAmps>
 __global__ void __launch_bounds__(32)
 chunk_chain_kernel(const void* __restrict__ src, u64 bins, u64 nchunks, const int* __restrict__ meta,
                    const long long* __restrict__ inc, const int* __restrict__ smeta,
-                   const long long* __restrict__ sinc, double* __restrict__ chunk_end,
+                   const long long* __restrict__ sinc, double start, double* __restrict__ chunk_end,
                    long long* __restrict__ sstart, int* __restrict__ err) {
   const int lane = threadIdx.x;
   const u64 nsuper = (nchunks + 31) >> 5;
-  double run = 0.0;  // identical in every lane
+  double run = start;  // identical in every lane; `start` = the exact running sum where this array begins
   // inside a run of INT (super-)chunks of one binade the running sum is carried as an integer (units of
   // the ulp): the dependent chain is then a single integer add per step
   long long s_int = 0;
@@ -420,7 +438,7 @@ chunk_sum_kernel(const void* __restrict__ src, u64 bins, double* __restrict__ ch
   double acc = 0.0, dummy = 0.0;
   for (int i = threadIdx.x; i < kChunk; i += kThreads) {
     const u64 idx = c * kChunk + i;
-    if (idx < bins) acc += load_p<kAmps>(src, idx);
+    if (idx < bins) acc += load_p<kAmps, false>(src, idx);
   }
   block_sum2(acc, dummy);
   if (threadIdx.x == 0) chunk_sum[c] = acc;
@@ -458,37 +476,49 @@ __global__ void seg_add_kernel(double* __restrict__ data, u64 n, const double* _
   if (seg > 0) data[i] += seg_incl[seg - 1];
 }
 
-// One thread per shot: first bin with cdf[bin] / total > u  (searchsorted side='right').
-template <bool kAmps>
+// One thread per shot: first bin with cdf[bin] / total > u  (searchsorted side='right').  `start` / `total`: the
+// running sum where this array begins and the grand total (0 and chunk_end[last] for a whole state; a shard of a
+// sharded state begins where the previous shard ended).  Shots that fall before this array get -1, after it -2.
+template <bool kAmps, bool kExact>
 __global__ void __launch_bounds__(kThreads)
-sample_kernel(const void* __restrict__ src, u64 bins, const double* __restrict__ chunk_end, u64 nchunks,
-              const double* __restrict__ uniforms, int shots, long long* __restrict__ out) {
+sample_kernel(const void* __restrict__ src, u64 bins, const double* __restrict__ chunk_end, u64 nchunks, double start,
+              double total, const double* __restrict__ uniforms, int shots, long long* __restrict__ out) {
   const int sidx = blockIdx.x * blockDim.x + threadIdx.x;
   if (sidx >= shots) return;
-  const double total = chunk_end[nchunks - 1];
   const double u = uniforms[sidx];
+  if (start / total > u) {
+    out[sidx] = -1;
+    return;
+  }
   // first chunk whose end value exceeds u
   u64 lo = 0, hi = nchunks;  // answer in [lo, hi]
   while (lo < hi) {
     const u64 mid = (lo + hi) >> 1;
     if (chunk_end[mid] / total > u) hi = mid; else lo = mid + 1;
   }
-  if (lo >= nchunks) {  // u >= 1 cannot happen for random_sample(); mirror searchsorted -> len
-    out[sidx] = (long long)bins;
+  if (lo >= nchunks) {  // a later shard (for a whole state: u >= 1, which random_sample() never returns)
+    out[sidx] = -2;
     return;
   }
-  double run = lo > 0 ? chunk_end[lo - 1] : 0.0;
+  double run = lo > 0 ? chunk_end[lo - 1] : start;
   const u64 begin = lo * kChunk;
   const u64 end = begin + kChunk < bins ? begin + kChunk : bins;
-  u64 ans = end - 1;
+  // exact order: the walk repeats the adds that produced chunk_end[lo], so it always finds the bin.  Blocked
+  // order: chunk_end comes from a tree sum, the walk may end a rounding error short -- then the last bin of the
+  // chunk with p > 0 is the answer (never a bin the reference cannot emit)
+  u64 ans = end - 1, last_nonzero = end - 1;
+  bool found = false;
   for (u64 i = begin; i < end; i++) {
-    run += load_p<kAmps>(src, i);
+    const double pv = load_p<kAmps, kExact>(src, i);
+    if (pv > 0.0) last_nonzero = i;
+    run += pv;
     if (run / total > u) {
       ans = i;
+      found = true;
       break;
     }
   }
-  out[sidx] = (long long)ans;
+  out[sidx] = (long long)(found ? ans : last_nonzero);
 }
 
 struct SampleWs {
@@ -539,6 +569,93 @@ static size_t sample_ws_layout(int log2_bins, int shots, void* ws, SampleWs* out
   return off;
 }
 
+// ---- the phases of the exact-order sampler (each usable on a shard of a sharded state) ----
+// (1) chunk sums + inclusive scan -> ws.aprefix (approximate prefix, steers the classification); total to the host
+template <bool kAmps>
+static int cdf_prepare(const void* src, int log2_bins, void* ws, double* host_total, cudaStream_t s) {
+  const u64 bins = 1ull << log2_bins;
+  const u64 nchunks = (bins + kChunk - 1) / kChunk;
+  SampleWs w;
+  sample_ws_layout(log2_bins, 0, ws, &w);
+  const u64 nseg = (nchunks + 1023) / 1024;
+  chunk_sum_kernel<kAmps><<<(unsigned)nchunks, kThreads, 0, s>>>(src, bins, w.aprefix);
+  QSV_LAUNCHED();
+  seg_scan_kernel<<<(unsigned)((nseg + 127) / 128), 128, 0, s>>>(w.aprefix, nchunks, w.seg1);
+  QSV_LAUNCHED();
+  if (nseg > 1) {
+    serial_scan_kernel<<<1, 32, 0, s>>>(w.seg1, nseg);
+    QSV_LAUNCHED();
+    seg_add_kernel<<<(unsigned)((nchunks + 255) / 256), 256, 0, s>>>(w.aprefix, nchunks, w.seg1);
+    QSV_LAUNCHED();
+  }
+  if (host_total) {
+    QSV_CUDA(cudaMemcpyAsync(host_total, w.aprefix + (nchunks - 1), sizeof(double), cudaMemcpyDeviceToHost, s));
+    QSV_CUDA(cudaStreamSynchronize(s));
+  }
+  return 0;
+}
+
+// (2) mode / binade / integer increment of every chunk, given the approximate running sum before the array
+template <bool kAmps>
+static int cdf_classify(const void* src, int log2_bins, double approx_offset, void* ws, cudaStream_t s) {
+  const u64 bins = 1ull << log2_bins;
+  const u64 nchunks = (bins + kChunk - 1) / kChunk;
+  SampleWs w;
+  sample_ws_layout(log2_bins, 0, ws, &w);
+  QSV_CUDA(cudaMemsetAsync(w.meta + nchunks, 0, sizeof(int), s));
+  chunk_classify_kernel<kAmps><<<(unsigned)nchunks, kThreads, 0, s>>>(src, bins, w.aprefix, approx_offset, w.meta, w.inc);
+  QSV_LAUNCHED();
+  const u64 nsuper = (nchunks + 31) / 32;
+  super_classify_kernel<<<(unsigned)((nsuper * 32 + kThreads - 1) / kThreads), kThreads, 0, s>>>(
+      nchunks, w.meta, w.inc, w.smeta, w.sinc, w.pref);
+  QSV_LAUNCHED();
+  return 0;
+}
+
+// (3) the sequential chain from the exact running sum `start`; chunk ends -> ws.chunk_end, last one to the host
+template <bool kAmps>
+static int cdf_chain(const void* src, int log2_bins, double start, void* ws, double* host_end, cudaStream_t s) {
+  const u64 bins = 1ull << log2_bins;
+  const u64 nchunks = (bins + kChunk - 1) / kChunk;
+  SampleWs w;
+  sample_ws_layout(log2_bins, 0, ws, &w);
+  chunk_chain_kernel<kAmps><<<1, 32, 0, s>>>(src, bins, nchunks, w.meta, w.inc, w.smeta, w.sinc, start, w.chunk_end,
+                                             w.sstart, w.meta + nchunks);
+  QSV_LAUNCHED();
+  chunk_fill_kernel<<<(unsigned)((nchunks + kThreads - 1) / kThreads), kThreads, 0, s>>>(nchunks, w.smeta, w.sstart,
+                                                                                         w.pref, w.chunk_end);
+  QSV_LAUNCHED();
+  int err = 0;
+  QSV_CUDA(cudaMemcpyAsync(&err, w.meta + nchunks, sizeof(int), cudaMemcpyDeviceToHost, s));
+  QSV_CUDA(cudaStreamSynchronize(s));
+  if (err) {  // cannot happen by construction; keep the plain sequential kernel as the safety net
+    cdf_sequential_kernel<kAmps><<<1, 1024, 0, s>>>(src, bins, start, w.chunk_end);
+    QSV_LAUNCHED();
+  }
+  if (host_end) {
+    QSV_CUDA(cudaMemcpyAsync(host_end, w.chunk_end + (nchunks - 1), sizeof(double), cudaMemcpyDeviceToHost, s));
+    QSV_CUDA(cudaStreamSynchronize(s));
+  }
+  return 0;
+}
+
+// (4) searchsorted(cdf / total, u, 'right') restricted to this array: -1 = before it, -2 = after it
+template <bool kAmps, bool kExact>
+static int cdf_search(const void* src, int log2_bins, double start, double total, const double* host_uniforms, int shots,
+                      int64_t* host_out, void* ws, cudaStream_t s) {
+  const u64 bins = 1ull << log2_bins;
+  const u64 nchunks = (bins + kChunk - 1) / kChunk;
+  SampleWs w;
+  sample_ws_layout(log2_bins, shots, ws, &w);
+  QSV_CUDA(cudaMemcpyAsync(w.uniforms, host_uniforms, (size_t)shots * sizeof(double), cudaMemcpyHostToDevice, s));
+  sample_kernel<kAmps, kExact><<<(shots + kThreads - 1) / kThreads, kThreads, 0, s>>>(src, bins, w.chunk_end, nchunks, start,
+                                                                                      total, w.uniforms, shots, w.out);
+  QSV_LAUNCHED();
+  QSV_CUDA(cudaMemcpyAsync(host_out, w.out, (size_t)shots * sizeof(long long), cudaMemcpyDeviceToHost, s));
+  QSV_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
 template <bool kAmps>
 static int sample_impl(const void* src, int log2_bins, const double* host_uniforms, int shots,
                        int64_t* host_out, int flags, void* ws, double* host_total, cudaStream_t s) {
@@ -547,40 +664,11 @@ static int sample_impl(const void* src, int log2_bins, const double* host_unifor
   const u64 nchunks = (bins + kChunk - 1) / kChunk;
   SampleWs w;
   sample_ws_layout(log2_bins, shots, ws, &w);
-  QSV_CUDA(cudaMemcpyAsync(w.uniforms, host_uniforms, (size_t)shots * sizeof(double), cudaMemcpyHostToDevice, s));
+  double total = 0.0;
   if (exact) {
-    // approximate prefix of the chunk sums (only used to classify chunks), then the exact chain
-    const u64 nseg = (nchunks + 1023) / 1024;
-    chunk_sum_kernel<kAmps><<<(unsigned)nchunks, kThreads, 0, s>>>(src, bins, w.aprefix);
-    QSV_LAUNCHED();
-    seg_scan_kernel<<<(unsigned)((nseg + 127) / 128), 128, 0, s>>>(w.aprefix, nchunks, w.seg1);
-    QSV_LAUNCHED();
-    if (nseg > 1) {
-      serial_scan_kernel<<<1, 32, 0, s>>>(w.seg1, nseg);
-      QSV_LAUNCHED();
-      seg_add_kernel<<<(unsigned)((nchunks + 255) / 256), 256, 0, s>>>(w.aprefix, nchunks, w.seg1);
-      QSV_LAUNCHED();
-    }
-    QSV_CUDA(cudaMemsetAsync(w.meta + nchunks, 0, sizeof(int), s));
-    chunk_classify_kernel<kAmps><<<(unsigned)nchunks, kThreads, 0, s>>>(src, bins, w.aprefix, w.meta, w.inc);
-    QSV_LAUNCHED();
-    const u64 nsuper = (nchunks + 31) / 32;
-    super_classify_kernel<<<(unsigned)((nsuper * 32 + kThreads - 1) / kThreads), kThreads, 0, s>>>(
-        nchunks, w.meta, w.inc, w.smeta, w.sinc, w.pref);
-    QSV_LAUNCHED();
-    chunk_chain_kernel<kAmps><<<1, 32, 0, s>>>(src, bins, nchunks, w.meta, w.inc, w.smeta, w.sinc, w.chunk_end,
-                                               w.sstart, w.meta + nchunks);
-    QSV_LAUNCHED();
-    chunk_fill_kernel<<<(unsigned)((nchunks + kThreads - 1) / kThreads), kThreads, 0, s>>>(nchunks, w.smeta, w.sstart,
-                                                                                           w.pref, w.chunk_end);
-    QSV_LAUNCHED();
-    int err = 0;
-    QSV_CUDA(cudaMemcpyAsync(&err, w.meta + nchunks, sizeof(int), cudaMemcpyDeviceToHost, s));
-    QSV_CUDA(cudaStreamSynchronize(s));
-    if (err) {  // cannot happen by construction; keep the plain sequential kernel as the safety net
-      cdf_sequential_kernel<kAmps><<<1, 1024, 0, s>>>(src, bins, w.chunk_end);
-      QSV_LAUNCHED();
-    }
+    if (int rc = cdf_prepare<kAmps>(src, log2_bins, ws, nullptr, s)) return rc;
+    if (int rc = cdf_classify<kAmps>(src, log2_bins, 0.0, ws, s)) return rc;
+    if (int rc = cdf_chain<kAmps>(src, log2_bins, 0.0, ws, &total, s)) return rc;
   } else {
     chunk_sum_kernel<kAmps><<<(unsigned)nchunks, kThreads, 0, s>>>(src, bins, w.chunk_end);
     QSV_LAUNCHED();
@@ -593,20 +681,19 @@ static int sample_impl(const void* src, int log2_bins, const double* host_unifor
       seg_add_kernel<<<(unsigned)((nchunks + 255) / 256), 256, 0, s>>>(w.chunk_end, nchunks, w.seg1);
       QSV_LAUNCHED();
     }
+    QSV_CUDA(cudaMemcpyAsync(&total, w.chunk_end + (nchunks - 1), sizeof(double), cudaMemcpyDeviceToHost, s));
+    QSV_CUDA(cudaStreamSynchronize(s));
   }
-  double total = 0.0;
-  QSV_CUDA(cudaMemcpyAsync(&total, w.chunk_end + (nchunks - 1), sizeof(double), cudaMemcpyDeviceToHost, s));
-  QSV_CUDA(cudaStreamSynchronize(s));
   if (host_total) *host_total = total;
   // numpy's choice(): "probabilities do not sum to 1" when |sum - 1| > sqrt(eps)
   if (check_norm && !(fabs(total - 1.0) <= 1.4901161193847656e-08))
     return fail(QSV_ENORM, "probabilities do not sum to 1");
   if (!(total > 0.0)) return fail(QSV_ENORM, "probabilities sum to zero");
-  sample_kernel<kAmps><<<(shots + kThreads - 1) / kThreads, kThreads, 0, s>>>(src, bins, w.chunk_end, nchunks,
-                                                                              w.uniforms, shots, w.out);
-  QSV_LAUNCHED();
-  QSV_CUDA(cudaMemcpyAsync(host_out, w.out, (size_t)shots * sizeof(long long), cudaMemcpyDeviceToHost, s));
-  QSV_CUDA(cudaStreamSynchronize(s));
+  const int rc = exact ? cdf_search<kAmps, true>(src, log2_bins, 0.0, total, host_uniforms, shots, host_out, ws, s)
+                       : cdf_search<kAmps, false>(src, log2_bins, 0.0, total, host_uniforms, shots, host_out, ws, s);
+  if (rc) return rc;
+  for (int i = 0; i < shots; i++)
+    if (host_out[i] < 0) host_out[i] = (int64_t)bins;  // u >= 1: searchsorted returns len(cdf)
   return 0;
 }
 
@@ -677,7 +764,7 @@ int qsv_expval_pauli(const double* sv, int n, uint64_t z_mask, uint64_t x_mask, 
 static int marginal_log2_parts(int n, int m) {
   // enough CTAs to fill the machine: bins * parts >= ~4 CTAs per SM, parts <= 2^(n-m) / 256
   int lp = 0;
-  while (((1ull << m) << lp) < (u64)kNumSMs * 4 && (n - m - lp) > 10) lp++;
+  while (((1ull << m) << lp) < 592ull && (n - m - lp) > 10) lp++;  // fixed (not per device): it sizes the workspace
   return lp;
 }
 
@@ -728,6 +815,44 @@ int qsv_marginal(const double* sv, int n, const int32_t* measured_sorted, int m,
 size_t qsv_sample_workspace_bytes(int log2_bins, int shots) {
   if (log2_bins < 0 || log2_bins > 40 || shots < 0) return 0;
   return sample_ws_layout(log2_bins, shots, nullptr, nullptr);
+}
+
+int qsv_cdf_prepare(const double* src, int from_amplitudes, int log2_bins, void* ws, double* host_approx_total,
+                    void* stream) {
+  if (!src || !ws || !host_approx_total || log2_bins < 0 || log2_bins > 40)
+    return fail(QSV_EINVAL, "qsv_cdf_prepare: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  return from_amplitudes ? cdf_prepare<true>(src, log2_bins, ws, host_approx_total, s)
+                         : cdf_prepare<false>(src, log2_bins, ws, host_approx_total, s);
+}
+
+int qsv_cdf_classify(const double* src, int from_amplitudes, int log2_bins, double approx_offset, void* ws,
+                     void* stream) {
+  if (!src || !ws || log2_bins < 0 || log2_bins > 40 || !(approx_offset >= 0.0))
+    return fail(QSV_EINVAL, "qsv_cdf_classify: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  return from_amplitudes ? cdf_classify<true>(src, log2_bins, approx_offset, ws, s)
+                         : cdf_classify<false>(src, log2_bins, approx_offset, ws, s);
+}
+
+int qsv_cdf_chain(const double* src, int from_amplitudes, int log2_bins, double exact_start, void* ws,
+                  double* host_exact_end, void* stream) {
+  if (!src || !ws || !host_exact_end || log2_bins < 0 || log2_bins > 40 || !(exact_start >= 0.0))
+    return fail(QSV_EINVAL, "qsv_cdf_chain: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  return from_amplitudes ? cdf_chain<true>(src, log2_bins, exact_start, ws, host_exact_end, s)
+                         : cdf_chain<false>(src, log2_bins, exact_start, ws, host_exact_end, s);
+}
+
+int qsv_cdf_search(const double* src, int from_amplitudes, int log2_bins, double exact_start, double total,
+                   const double* host_uniforms, int shots, int64_t* host_out_idx, void* ws, void* stream) {
+  if (!src || !ws || !host_uniforms || !host_out_idx || log2_bins < 0 || log2_bins > 40 || shots < 1 ||
+      !(exact_start >= 0.0) || !(total > 0.0))
+    return fail(QSV_EINVAL, "qsv_cdf_search: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  return from_amplitudes
+             ? cdf_search<true, true>(src, log2_bins, exact_start, total, host_uniforms, shots, host_out_idx, ws, s)
+             : cdf_search<false, true>(src, log2_bins, exact_start, total, host_uniforms, shots, host_out_idx, ws, s);
 }
 
 int qsv_sample(const double* src, int from_amplitudes, int log2_bins, const double* host_uniforms, int shots,

@@ -667,24 +667,24 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
           const uint32_t z1b = (uint32_t)rec.z1 << 4;
           const uint32_t c3 = (uint32_t)rec.c3 << 4, c4 = (uint32_t)rec.c4 << 4, c5 = (uint32_t)rec.c5 << 4;
           if (rec.ngl == 6u) {
+            // software pipeline over the sub-cube's eight DMMA steps, operands requested two steps ahead
+            const uint32_t xo[8] = {0u, c3, c4, c3 + c4, c5, c5 + c3, c5 + c4, c5 + c3 + c4};
+            double xa[3], xb[3];
 #pragma unroll
-            for (int hb = 0; hb < 2; hb++) {
-              const uint32_t xh = hb ? c5 : 0u;
-              const uint32_t xo[4] = {xh, xh + c3, xh + c4, xh + c3 + c4};
-              double x0[4], x1[4];
+            for (int j = 0; j < 2; j++) {
+              xa[j] = *reinterpret_cast<const double*>(tb8 + (a_ld + xo[j]));
+              xb[j] = *reinterpret_cast<const double*>(tb8 + (a_ld + xo[j] + z1b));
+            }
 #pragma unroll
-              for (int it = 0; it < 4; it++) {
-                const uint32_t a = a_ld + xo[it];
-                x0[it] = *reinterpret_cast<const double*>(tb8 + a);
-                x1[it] = *reinterpret_cast<const double*>(tb8 + (a + z1b));
+            for (int j = 0; j < 8; j++) {
+              if (j + 2 < 8) {
+                xa[(j + 2) % 3] = *reinterpret_cast<const double*>(tb8 + (a_ld + xo[j + 2]));
+                xb[(j + 2) % 3] = *reinterpret_cast<const double*>(tb8 + (a_ld + xo[j + 2] + z1b));
               }
-#pragma unroll
-              for (int it = 0; it < 4; it++) {
-                double d0 = 0.0, d1 = 0.0;
-                dmma884(d0, d1, x0[it], b0);
-                dmma884(d0, d1, x1[it], b1);
-                *reinterpret_cast<double2*>(reinterpret_cast<char*>(tile) + (a_st + xo[it])) = make_double2(d0, d1);
-              }
+              double d0 = 0.0, d1 = 0.0;
+              dmma884(d0, d1, xa[j % 3], b0);
+              dmma884(d0, d1, xb[j % 3], b1);
+              *reinterpret_cast<double2*>(reinterpret_cast<char*>(tile) + (a_st + xo[j])) = make_double2(d0, d1);
             }
           } else {
             const uint32_t ng = 1u << rec.ngl;
@@ -721,28 +721,28 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
           const uint32_t z2b = (uint32_t)rec.c5 << 4;
           const uint32_t c3 = (uint32_t)rec.c3 << 4, c4 = (uint32_t)rec.c4 << 4;
           if (rec.ngl == 5u) {
+            // software pipeline over the sub-cube's four DMMA steps: the operands of step j + 1 are requested
+            // before the six DMMA of step j, so a warp waits for shared memory only once per op and keeps the FP64
+            // pipe and the shared-memory pipe busy at the same time
+            const uint32_t xo[4] = {0u, c3, c4, c3 + c4};
+            double2 u0n = *reinterpret_cast<const double2*>(ta + xo[0]);
+            double2 u1n = *reinterpret_cast<const double2*>(ta + (xo[0] + z2b));
 #pragma unroll
-            for (int hb = 0; hb < 2; hb++) {
-              const uint32_t xh = hb ? c4 : 0u;
-              const uint32_t xo[2] = {xh, xh + c3};
-              double2 u0[2], u1[2];
-#pragma unroll
-              for (int it = 0; it < 2; it++) {
-                u0[it] = *reinterpret_cast<const double2*>(ta + xo[it]);
-                u1[it] = *reinterpret_cast<const double2*>(ta + (xo[it] + z2b));
+            for (int j = 0; j < 4; j++) {
+              const double2 u0 = u0n, u1 = u1n;
+              if (j + 1 < 4) {
+                u0n = *reinterpret_cast<const double2*>(ta + xo[j + 1]);
+                u1n = *reinterpret_cast<const double2*>(ta + (xo[j + 1] + z2b));
               }
-#pragma unroll
-              for (int it = 0; it < 2; it++) {
-                double k0 = 0.0, k1 = 0.0, r0, r1, i0, i1;
-                dmma884(k0, k1, u0[it].x + u0[it].y, bq[0]);
-                dmma884(k0, k1, u1[it].x + u1[it].y, bq[1]);
-                dmma884_c(r0, r1, u0[it].y, bq[2], k0, k1);
-                dmma884_c(i0, i1, u0[it].x, bq[4], k0, k1);
-                dmma884(r0, r1, u1[it].y, bq[3]);
-                dmma884(i0, i1, u1[it].x, bq[5]);
-                *reinterpret_cast<double2*>(ta + xo[it]) = make_double2(r0, i0);
-                *reinterpret_cast<double2*>(ta + (xo[it] + z2b)) = make_double2(r1, i1);
-              }
+              double k0 = 0.0, k1 = 0.0, r0, r1, i0, i1;
+              dmma884(k0, k1, u0.x + u0.y, bq[0]);
+              dmma884(k0, k1, u1.x + u1.y, bq[1]);
+              dmma884_c(r0, r1, u0.y, bq[2], k0, k1);
+              dmma884_c(i0, i1, u0.x, bq[4], k0, k1);
+              dmma884(r0, r1, u1.y, bq[3]);
+              dmma884(i0, i1, u1.x, bq[5]);
+              *reinterpret_cast<double2*>(ta + xo[j]) = make_double2(r0, i0);
+              *reinterpret_cast<double2*>(ta + (xo[j] + z2b)) = make_double2(r1, i1);
             }
           } else {
             const uint32_t ng = 1u << rec.ngl;
@@ -1046,7 +1046,7 @@ chop_kernel(double2* __restrict__ sv, u64 n_amps, double thr) {
 
 static int grid_for(u64 n_amps) {
   u64 blocks = (n_amps + kThreads - 1) / kThreads;
-  const u64 cap = (u64)kNumSMs * 16;
+  const u64 cap = (u64)sm_count() * 16;
   return (int)std::max<u64>(1, std::min(blocks, cap));
 }
 
@@ -1208,19 +1208,6 @@ constexpr int kGroupThreads = 3 * 256 + 3 * 32;  // three groups of 8 compute wa
 constexpr size_t kMaxSmemPerBlock = 232448;  // 227 KiB (sm_100 opt-in limit, static + dynamic)
 
 static bool g_attr_set[64] = {false};
-static int g_sm_count[64] = {0};
-
-static int sm_count() {
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return kNumSMs;
-  if (!g_sm_count[dev]) {
-    int v = 0;
-    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = kNumSMs;
-    g_sm_count[dev] = v;
-  }
-  return g_sm_count[dev];
-}
-
 // Opt in to > 48 KiB of dynamic shared memory, once per device.
 static int ensure_attrs() {
   int dev = 0;
@@ -2010,6 +1997,24 @@ int qsv_apply_pass_tail(double* sv, int n, const int32_t* tile_qubits, int n_til
 }
 
 size_t qsv_tail_scratch_bytes(void) { return sizeof(double) * 8 * kMaxTail; }
+
+int qsv_alloc(void** dev_out, size_t bytes) {
+  if (!dev_out || bytes == 0) return fail(QSV_EINVAL, "qsv_alloc: bad arguments");
+  QSV_CUDA(cudaMalloc(dev_out, bytes));
+  return 0;
+}
+
+int qsv_free(void* dev_ptr) {
+  if (!dev_ptr) return 0;
+  QSV_CUDA(cudaFree(dev_ptr));
+  return 0;
+}
+
+int qsv_copy_d2d(void* dev_dst, const void* dev_src, size_t bytes, void* stream) {
+  if (!dev_dst || !dev_src) return fail(QSV_EINVAL, "qsv_copy_d2d: null pointer");
+  QSV_CUDA(cudaMemcpyAsync(dev_dst, dev_src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return 0;
+}
 
 int qsv_debug_set_flags(uint32_t flags) {
 #ifndef QSV_DEBUG_BUILD

@@ -67,6 +67,12 @@ class ShardedState:
     def _rank_bit(self, phys):
         return (self.rank >> (phys - self.n_local)) & 1
 
+    def _global_rank(self, group_rank):
+        """Rank inside ``self.group`` -> rank in the default (world) group."""
+        if self.group is None:
+            return group_rank
+        return self._dist.get_global_rank(self.group, group_rank)
+
     def _staging(self, amps):
         """Two send and two receive buffers of ``amps`` amplitudes (the exchange is double-buffered)."""
         torch = self._torch
@@ -107,10 +113,12 @@ class ShardedState:
         send, recv = self._staging(chunk)
         spans = [(begin, min(chunk, half - begin)) for begin in range(0, half, chunk)]
 
+        gpeer = self._global_rank(peer)  # P2POp takes GLOBAL ranks also when a group is given
+
         def exchange(i):
             cnt = spans[i][1]
-            ops = [dist.P2POp(dist.isend, send[i % 2][: 2 * cnt], peer, self.group),
-                   dist.P2POp(dist.irecv, recv[i % 2][: 2 * cnt], peer, self.group)]
+            ops = [dist.P2POp(dist.isend, send[i % 2][: 2 * cnt], gpeer, self.group),
+                   dist.P2POp(dist.irecv, recv[i % 2][: 2 * cnt], gpeer, self.group)]
             if self.rank > peer:
                 ops.reverse()
             return dist.batch_isend_irecv(ops)
@@ -174,8 +182,9 @@ class ShardedState:
             cnt = spans[i][1]
             ops = []
             for slot, lam in enumerate(lams):
-                ops.append(dist.P2POp(dist.isend, view(send, i, slot, cnt), peers[lam], self.group))
-                ops.append(dist.P2POp(dist.irecv, view(recv, i, slot, cnt), peers[lam], self.group))
+                gpeer = self._global_rank(peers[lam])  # P2POp takes GLOBAL ranks also when a group is given
+                ops.append(dist.P2POp(dist.isend, view(send, i, slot, cnt), gpeer, self.group))
+                ops.append(dist.P2POp(dist.irecv, view(recv, i, slot, cnt), gpeer, self.group))
             return dist.batch_isend_irecv(ops)
 
         def unpack(i):
@@ -400,39 +409,48 @@ class ShardedState:
         self.ensure_local(qubit)
         self.shard.collapse(self.pos[qubit], outcome, prob, is_reset)
 
-    def sample_all(self, uniforms):
-        """Blocked-order sampling of all n qubits in *physical* index order (rank-major), returned as
-        logical indices.  Every rank gets the full result."""
+    def sample_all(self, uniforms, check_norm=True):
+        """All n qubits, in the reference's bin order and with ITS running sums: numpy's ``choice`` is
+        ``cdf = p.cumsum(); cdf /= cdf[-1]; searchsorted(u, 'right')`` (qasm_simulator.py:213), one sequential
+        float64 sum over the 2^n bins.  With the identity layout the bins of rank r follow those of rank r - 1, so
+        the sum is CHAINED through the ranks: every rank classifies the chunks of its shard in parallel
+        (qsv_cdf_prepare / qsv_cdf_classify, steered by the all-gathered approximate totals), then rank r continues
+        the exact running sum where rank r - 1 stopped (qsv_cdf_chain: milliseconds, one double handed on), and
+        finally every rank looks the uniforms up in its own share of the CDF (qsv_cdf_search).  Seeded counts are
+        the reference's bit for bit, as on one GPU.  Returns (logical bin indices, total) on every rank."""
         torch = self._torch
         dist = self._dist
+        self.restore_identity_layout()
         uniforms = np.ascontiguousarray(uniforms, dtype=np.float64)
-        shots = uniforms.size
-        local_total = self.shard.norm2()
-        totals = torch.zeros(self.world, dtype=torch.float64, device=self.shard.comm_device())
-        totals[self.rank] = local_total
-        dist.all_reduce(totals, op=dist.ReduceOp.SUM, group=self.group)
-        totals = totals.cpu().numpy()
-        cdf = np.cumsum(totals)
-        total = float(cdf[-1])
-        owner = np.searchsorted(cdf / total, uniforms, side="right")
-        owner = np.minimum(owner, self.world - 1)
-        mine = np.nonzero(owner == self.rank)[0]
-        out = torch.zeros(shots, dtype=torch.int64, device=self.shard.comm_device())
-        if mine.size and local_total > 0.0:
-            before = cdf[self.rank] - totals[self.rank]
-            u_local = (uniforms[mine] * total - before) / totals[self.rank]
-            u_local = np.clip(u_local, 0.0, np.nextafter(1.0, 0.0))
-            idx, _ = self.shard.sample(list(range(self.n_local)), u_local, exact_order=False,
-                                       check_norm=False)
-            phys_idx = idx + (self.rank << self.n_local)
-            out[torch.as_tensor(mine, device=out.device)] = torch.as_tensor(phys_idx, device=out.device)
+        shots = int(uniforms.size)
+        dev = self.shard.comm_device()
+        approx = torch.zeros(self.world, dtype=torch.float64, device=dev)
+        approx[self.rank] = self.shard.cdf_prepare(shots)
+        dist.all_reduce(approx, op=dist.ReduceOp.SUM, group=self.group)
+        approx = approx.cpu().tolist()
+        self.shard.cdf_classify(float(sum(approx[: self.rank])), shots)
+        start, end = 0.0, 0.0
+        for r in range(self.world):  # the chain: rank r starts from the exact end of rank r - 1
+            handoff = torch.zeros(1, dtype=torch.float64, device=dev)
+            if r == self.rank:
+                start = end
+                handoff[0] = self.shard.cdf_chain(start, shots)
+            dist.broadcast(handoff, src=self._global_rank(r), group=self.group)
+            end = float(handoff.item())
+        total = end
+        if check_norm and not abs(total - 1.0) <= 1.4901161193847656e-08:
+            raise ValueError("probabilities do not sum to 1")  # numpy's choice()
+        if not total > 0.0:
+            raise ValueError("probabilities sum to zero")
+        idx = self.shard.cdf_search(start, total, uniforms)
+        mine = idx >= 0
+        phys = np.where(mine, idx + (self.rank << self.n_local), 0).astype(np.int64)
+        out = torch.as_tensor(np.stack([phys, mine.astype(np.int64)]), device=dev)
         dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self.group)
-        phys = out.cpu().numpy()
-        # physical index -> logical index
-        logical = np.zeros_like(phys)
-        for q in range(self.n):
-            logical |= ((phys >> self.pos[q]) & 1) << q
-        return logical, total
+        out = out.cpu().numpy()
+        if not np.all(out[1] == 1):  # every shot lies in exactly one shard's share of the CDF
+            raise _lib.QsvLibraryError("sharded sampler: a shot was claimed by %d shards" % int(out[1].max()))
+        return out[0], total
 
     # -- the interface simulator.py drives (same method set as engine.DeviceState), so that the BasicAer
     # -- mirror classes run SPMD on a sharded state: every rank executes the same run(qobj) ----------
@@ -467,14 +485,12 @@ class ShardedState:
         local = [(i, self.pos[q]) for i, q in enumerate(measured_sorted) if self.pos[q] < self.n_local]
         glob = [(i, self.pos[q]) for i, q in enumerate(measured_sorted) if self.pos[q] >= self.n_local]
         phys_sorted = sorted(p for _, p in local)
-        probs_local = self.shard.marginal(phys_sorted).to(dev)
-        bins = torch.arange(1 << len(phys_sorted), dtype=torch.int64, device=dev)
-        dest = torch.zeros_like(bins)
-        for i, p in local:
-            dest |= ((bins >> phys_sorted.index(p)) & 1) << i
-        dest += sum(self._rank_bit(p) << i for i, p in glob)
-        full = torch.zeros(1 << m, dtype=torch.float64, device=dev)
-        full[dest] = probs_local  # dest is injective: a plain scatter
+        probs_local = self.shard.marginal(phys_sorted)
+        dest_of = {p: i for i, p in local}
+        base = sum(self._rank_bit(p) << i for i, p in glob)
+        # bit j of the local bin index (physical bit phys_sorted[j]) goes to bit dest_of[...] of the full index;
+        # the rank's global measured bits select the block (qsv_scatter_bits)
+        full = self.shard.scatter_bits(probs_local, [dest_of[p] for p in phys_sorted], base, m).to(dev)
         self._dist.all_reduce(full, op=self._dist.ReduceOp.SUM, group=self.group)
         return full
 
@@ -482,13 +498,11 @@ class ShardedState:
         """engine.DeviceState.sample on the sharded state; every rank returns the same bin indices.
         Fewer than all qubits measured: the all-reduced marginal is sampled with the single-GPU sampler
         (numpy's cumsum order when ``exact_order``), on every rank alike.  All qubits measured (or a marginal
-        too large for one rank): blocked-order sampling of the full index, rank-major (``sample_all``) -- the
-        same distribution, and the same bins as the reference up to the rounding of the running sums."""
+        too large for one rank): ``sample_all`` -- the exact-order CDF chained through the ranks."""
         measured_sorted = list(measured_sorted)
         m = len(measured_sorted)
         if m == self.n or m > self.MAX_MARGINAL_QUBITS:
-            self.restore_identity_layout()
-            logical, total = self.sample_all(uniforms)
+            logical, total = self.sample_all(uniforms, check_norm=check_norm)
             if m == self.n:
                 return logical, total
             bins = np.zeros_like(logical)
@@ -629,7 +643,7 @@ def bench_main(args, metric, unit, measured_peaks, clock_sampler_cls):
     def step():
         st.init_basis0()
         st.apply_ops(ops)
-        return st.sample_all(uniforms)
+        return st.sample_all(uniforms)  # restores the identity layout, then the exact-order CDF across the ranks
 
     for _ in range(args.warmup):
         step()

@@ -279,6 +279,46 @@ class DeviceState:
                                            self.stream), "qsv_sample")
         return out, float(total.value)
 
+    # -- the exact-order sampler phase by phase, over ALL qubits of this state (dist.ShardedState.sample_all runs
+    # -- them across the shards: the running sum of shard r starts where shard r - 1 ended) ------------------
+    def _cdf_ws(self, shots):
+        ws_bytes = self.lib.qsv_sample_workspace_bytes(self.n, int(shots))
+        if self._sample_ws is None or self._sample_ws.numel() * 8 < ws_bytes:
+            self._sample_ws = self._torch.empty(ws_bytes // 8 + 8, dtype=self._torch.float64, device=self.device)
+        return ctypes.c_void_p(self._sample_ws.data_ptr())
+
+    def cdf_prepare(self, shots):
+        """Blocked chunk sums; returns the (approximate) sum of |psi|^2 over this state."""
+        out = ctypes.c_double(0.0)
+        with self._ctx():
+            _lib.check(self.lib.qsv_cdf_prepare(self.ptr, 1, self.n, self._cdf_ws(shots), ctypes.byref(out),
+                                                self.stream), "qsv_cdf_prepare")
+        return float(out.value)
+
+    def cdf_classify(self, approx_offset, shots):
+        with self._ctx():
+            _lib.check(self.lib.qsv_cdf_classify(self.ptr, 1, self.n, float(approx_offset), self._cdf_ws(shots),
+                                                 self.stream), "qsv_cdf_classify")
+
+    def cdf_chain(self, exact_start, shots):
+        """numpy-cumsum running sum over this state starting from ``exact_start``; returns its last value."""
+        out = ctypes.c_double(0.0)
+        with self._ctx():
+            _lib.check(self.lib.qsv_cdf_chain(self.ptr, 1, self.n, float(exact_start), self._cdf_ws(shots),
+                                              ctypes.byref(out), self.stream), "qsv_cdf_chain")
+        return float(out.value)
+
+    def cdf_search(self, exact_start, total, uniforms):
+        """Bin index per uniform, -1 / -2 for shots that fall before / after this state's share of the CDF."""
+        uniforms = np.ascontiguousarray(uniforms, dtype=np.float64)
+        out = np.empty(uniforms.size, dtype=np.int64)
+        with self._ctx():
+            _lib.check(self.lib.qsv_cdf_search(self.ptr, 1, self.n, float(exact_start), float(total),
+                                               ctypes.c_void_p(uniforms.ctypes.data), int(uniforms.size),
+                                               ctypes.c_void_p(out.ctypes.data), self._cdf_ws(uniforms.size),
+                                               self.stream), "qsv_cdf_search")
+        return out
+
     # -- readout ---------------------------------------------------------------------
     def chop(self, threshold):
         with self._ctx():
@@ -322,8 +362,25 @@ class DeviceState:
                                                 int(pattern), ctypes.c_void_p(buf.data_ptr()), int(begin), int(count),
                                                 self.stream), "qsv_unpack_bits")
 
+    def scatter_bits(self, src, dest_bits, base, log2_dst):
+        """Device tensor of 2^log2_dst doubles, zero except dst[base | deposit(s, dest_bits)] = src[s]
+        (qsv_scatter_bits; dist.ShardedState.marginal)."""
+        dst = self._torch.empty(1 << log2_dst, dtype=self._torch.float64, device=self.device)
+        with self._ctx():
+            _lib.check(self.lib.qsv_scatter_bits(ctypes.c_void_p(src.data_ptr()), len(dest_bits),
+                                                 _int32_array(dest_bits), int(base), ctypes.c_void_p(dst.data_ptr()),
+                                                 int(log2_dst), self.stream), "qsv_scatter_bits")
+        return dst
+
     def snapshot(self):
-        return self.state.clone()
+        """Device copy of the amplitudes (one qsv_copy_d2d; the buffer comes from the caching allocator)."""
+        snap = self._torch.empty_like(self.state)
+        with self._ctx():
+            _lib.check(self.lib.qsv_copy_d2d(ctypes.c_void_p(snap.data_ptr()), self.ptr, 16 << self.n, self.stream),
+                       "qsv_copy_d2d")
+        return snap
 
     def restore(self, snap):
-        self.state.copy_(snap)
+        with self._ctx():
+            _lib.check(self.lib.qsv_copy_d2d(self.ptr, ctypes.c_void_p(snap.data_ptr()), 16 << self.n, self.stream),
+                       "qsv_copy_d2d")

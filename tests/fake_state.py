@@ -151,6 +151,17 @@ class FakeState:
 
         return torch.from_numpy(np.ascontiguousarray(self._marginal_np(list(measured_sorted)), dtype=np.float64))
 
+    def scatter_bits(self, src, dest_bits, base, log2_dst):
+        import torch
+
+        s = np.arange(1 << len(dest_bits), dtype=np.int64)
+        dest = np.full_like(s, int(base))
+        for i, b in enumerate(dest_bits):
+            dest |= ((s >> i) & 1) << b
+        out = np.zeros(1 << log2_dst)
+        out[dest] = src.numpy()
+        return torch.from_numpy(out)
+
     def sample(self, measured_sorted, uniforms, exact_order=True, check_norm=True):
         return self._sample_np(self._marginal_np(measured_sorted), uniforms)
 
@@ -165,6 +176,26 @@ class FakeState:
         total = cdf[-1]
         cdf /= total
         return cdf.searchsorted(uniforms, side="right").astype(np.int64), float(total)
+
+    # the exact-order sampler phase by phase (engine.DeviceState.cdf_*): numpy itself, continued across shards
+    def cdf_prepare(self, shots):
+        self._p = np.abs(self.vec) ** 2
+        return float(self._p.sum())
+
+    def cdf_classify(self, approx_offset, shots):
+        pass
+
+    def cdf_chain(self, exact_start, shots):
+        # cumsum([start, p0, p1, ...]) is the one running sum numpy would compute over the concatenated shards
+        self._cdf = np.cumsum(np.concatenate(([exact_start], self._p)))[1:]
+        return float(self._cdf[-1])
+
+    def cdf_search(self, exact_start, total, uniforms):
+        uniforms = np.asarray(uniforms, dtype=np.float64)
+        idx = (self._cdf / total).searchsorted(uniforms, side="right").astype(np.int64)
+        idx[idx >= self._cdf.size] = -2
+        idx[exact_start / total > uniforms] = -1
+        return idx
 
     def chop(self, thr):
         self.vec[abs(self.vec) < thr] = 0.0

@@ -59,12 +59,28 @@ def _worker(rank, world, port, n, seed, out_dir):
         mask = ((idx >> q) & 1).astype(bool)
         assert abs(p0 - p[~mask].sum()) < 1e-12 and abs(p1 - p[mask].sum()) < 1e-12, (q, p0, p1)
     assert abs(st.norm2() - 1.0) < 1e-12
-    # sampling on the permuted layout: indices must be distributed like p (logical order)
+    # sampling from a permuted layout: sample_all restores the layout and chains numpy's running sum through the
+    # ranks -- the indices are exactly searchsorted(cumsum(|psi|^2) / total, u, 'right') over the WHOLE register
+    # (qasm_simulator.py:213), with psi the sharded state's own amplitudes
     u = np.random.RandomState(7).random_sample(4000)
     samples, total = st.sample_all(u)
-    assert abs(total - 1.0) < 1e-12
+    assert st.pos == list(range(n))
+    full_now = st.gather_statevector()
+    cdf = (np.abs(full_now) ** 2).cumsum()
+    assert total == cdf[-1]
+    assert np.array_equal(samples, (cdf / cdf[-1]).searchsorted(u, side="right"))
     hist = np.bincount(samples, minlength=2 ** n) / 4000.0
     assert np.abs(hist - p).max() < 0.05
+    st.apply_ops(ops[:6])  # leave the identity layout again for the checks below
+    for o in ops[:6]:
+        if o.kind in (_lib.GATE_DIAG1, _lib.GATE_DIAG2):
+            mat = np.diag(o.matrix)
+        elif o.kind == _lib.GATE_CX:
+            mat = orc.cx_gate_matrix()
+        else:
+            mat = o.matrix
+        ref = orc.apply_unitary(ref.reshape([2] * n), mat, list(o.qubits)).reshape(-1)
+    p = np.abs(ref) ** 2
     # Pauli expectation values on the permuted layout: X / Y on global qubits are swapped in, Z on a global
     # qubit is the sign of the rank bit (reference: quantum_info/states/statevector.py:377-408 via the oracle)
     prng = np.random.RandomState(100 + n)
@@ -118,9 +134,7 @@ SPMD_CASES = {
 }
 SPMD_UNITARY = ["random_2_unitary", "random_4_unitary", "unitary_five_circuits", "unitary_global_phase_x4",
                 "unitary_initial_unitary", "unitary_random", "multi_registers_unitary"]
-# all qubits measured: the sharded sampler walks the ranks' slabs in blocked order, so a uniform within ~1e-16
-# of a CDF step may land in the neighbouring bin -- counts are compared exactly here as well (none of these
-# fixtures has such a tie)
+# all qubits measured: the exact-order CDF is chained through the ranks (ShardedState.sample_all), counts identical
 SPMD_FULL_MEASURE = {2: ["qv_5_counts", "random_6_counts", "transpiled_lib_gates_l0_counts"],
                      4: ["qv_8_counts", "random_9_counts", "transpiled_qv_lib_10_counts"]}
 
@@ -268,3 +282,37 @@ def test_distributed_provider_with_reference_execute(tmp_path):
     port = _free_port()
     mp.spawn(_provider_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert os.path.exists(os.path.join(str(tmp_path), "provider_2.npy"))
+
+
+def _subgroup_worker(rank, world, port, out_dir):
+    for p in (ROOT, os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import golden_io
+    import helpers
+    from fake_state import FakeState
+    from qiskit_sdk_py_b200.dist import distributed_simulator
+
+    group = dist.new_group(ranks=[2, 3])  # every rank must call new_group
+    if rank in (2, 3):
+        def factory(backend):
+            return distributed_simulator(backend, shard_factory=lambda k: FakeState(k, tile_qubits=4), chunk_amps=8,
+                                         max_qubits=24, group=group)
+
+        for name in ["qv_5_counts", "random_6_state", "sampler_marginal_subset", "teleport", "random_4_unitary"]:
+            case = golden_io.load_case(name)
+            helpers.compare_result(helpers.run_case_with(factory, case), case, amp_tol=1e-12)
+        np.save(os.path.join(out_dir, "sub_%d.npy" % rank), np.array([1]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_state_on_a_strict_subgroup(tmp_path):
+    """exchanges address their peers by GLOBAL rank (torch's P2POp semantics) -- a state sharded over
+    ranks [2, 3] of a 4-rank job must not talk to ranks 0 / 1."""
+    port = _free_port()
+    mp.spawn(_subgroup_worker, args=(4, port, str(tmp_path)), nprocs=4, join=True)
+    assert os.path.exists(os.path.join(str(tmp_path), "sub_2.npy")) and os.path.exists(os.path.join(str(tmp_path), "sub_3.npy"))

@@ -477,3 +477,152 @@ def test_exact_cdf_is_bitwise_numpy_cumsum(kind):
     assert np.array_equal(chunk_end, cdf[1023::1024]), "chunk-end running sums differ from numpy's cumsum"
     expected = (cdf / cdf[-1]).searchsorted(u, side="right")
     assert np.array_equal(got, expected)
+
+
+def _cdf_call(name, *args):
+    _lib.check(getattr(_lib.load(), name)(*args), name)
+
+
+def _run_cdf_shards(src_host, from_amps, n_shards, uniforms):
+    """The four phases of the exact-order sampler (qsv_cdf_*) over `n_shards` consecutive pieces of one array, as
+    dist.ShardedState.sample_all drives them across ranks; returns (bin indices, total, all chunk ends)."""
+    import ctypes
+
+    import torch
+
+    lib = _lib.load()
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    size = src_host.size // n_shards
+    log2 = int(np.log2(size))
+    u = np.ascontiguousarray(uniforms, dtype=np.float64)
+    devs, wss, approx = [], [], []
+    for r in range(n_shards):
+        part = np.ascontiguousarray(src_host[r * size:(r + 1) * size])
+        dev = torch.as_tensor(part.view(np.float64), device="cuda")
+        ws = torch.zeros(lib.qsv_sample_workspace_bytes(log2, u.size) // 8 + 8, dtype=torch.float64, device="cuda")
+        tot = ctypes.c_double(0.0)
+        _cdf_call("qsv_cdf_prepare", ctypes.c_void_p(dev.data_ptr()), from_amps, log2, ctypes.c_void_p(ws.data_ptr()),
+                  ctypes.byref(tot), stream)
+        devs.append(dev), wss.append(ws), approx.append(tot.value)
+    starts, end = [], 0.0
+    for r in range(n_shards):
+        _cdf_call("qsv_cdf_classify", ctypes.c_void_p(devs[r].data_ptr()), from_amps, log2, float(sum(approx[:r])),
+                  ctypes.c_void_p(wss[r].data_ptr()), stream)
+        starts.append(end)
+        out = ctypes.c_double(0.0)
+        _cdf_call("qsv_cdf_chain", ctypes.c_void_p(devs[r].data_ptr()), from_amps, log2, end,
+                  ctypes.c_void_p(wss[r].data_ptr()), ctypes.byref(out), stream)
+        end = out.value
+    total = end
+    result = np.full(u.size, -5, dtype=np.int64)
+    claimed = np.zeros(u.size, dtype=np.int64)
+    for r in range(n_shards):
+        idx = np.empty(u.size, dtype=np.int64)
+        _cdf_call("qsv_cdf_search", ctypes.c_void_p(devs[r].data_ptr()), from_amps, log2, starts[r], total,
+                  ctypes.c_void_p(u.ctypes.data), u.size, ctypes.c_void_p(idx.ctypes.data),
+                  ctypes.c_void_p(wss[r].data_ptr()), stream)
+        mine = idx >= 0
+        result[mine] = idx[mine] + r * size
+        claimed += mine
+    nchunks = max(1, size // 1024)
+    chunk_end = np.concatenate([w[:nchunks].cpu().numpy() for w in wss])
+    assert np.all(claimed == 1)
+    return result, total, chunk_end
+
+
+@pytest.mark.parametrize("scale", [1.0, 1e-5])
+def test_exact_cdf_from_amplitudes_is_numpy_abs2(scale):
+    """All qubits measured: p_i = np.abs(psi_i) ** 2 as numpy rounds it (max * sqrt(fma(r, r, 1)) squared, NOT
+    re^2 + im^2 -- about a third of random inputs differ in the last bit) and the running sum is numpy's cumsum,
+    so the chunk ends and the sampled bins equal the reference's _add_sample_measure bit for bit."""
+    rng = np.random.RandomState(11)
+    nbins = 1 << 18
+    z = (rng.standard_normal(nbins) + 1j * rng.standard_normal(nbins)) * scale
+    z[rng.random_sample(nbins) < 0.01] = 0.0
+    z[5] = 3e-3 * scale          # purely real / purely imaginary amplitudes
+    z[6] = 2e-3j * scale
+    z /= np.linalg.norm(z)
+    p = np.abs(z) ** 2
+    naive = z.real * z.real + z.imag * z.imag
+    assert np.count_nonzero(p != naive) > nbins // 10, "the two roundings should differ often (else the test is void)"
+    cdf = p.cumsum()
+    u = np.random.RandomState(5).random_sample(3000)
+    got, total, chunk_end = _run_cdf_shards(z, 1, 1, u)
+    assert total == cdf[-1]
+    assert np.array_equal(chunk_end, cdf[1023::1024])
+    assert np.array_equal(got, (cdf / cdf[-1]).searchsorted(u, side="right"))
+    # and through the public sampler of a state
+    n = 18
+    st = make_state(n, z)
+    samples, tot = st.sample(list(range(n)), u, exact_order=True)
+    assert tot == cdf[-1] and np.array_equal(samples, got)
+
+
+@pytest.mark.parametrize("kind,n_shards", [("amps", 2), ("amps", 8), ("probs_wide", 4), ("probs_sparse", 4),
+                                           ("probs_empty_shard", 4)])
+def test_cdf_chained_across_shards_is_one_cumsum(kind, n_shards):
+    """qsv_cdf_prepare / classify / chain / search over consecutive shards, each continuing the previous shard's
+    exact running sum = numpy's cumsum over the whole array (what ShardedState.sample_all does across ranks)."""
+    rng = np.random.RandomState(len(kind) + n_shards)
+    nbins = 1 << 17
+    u = np.random.RandomState(6).random_sample(4000)
+    if kind == "amps":
+        z = rng.standard_normal(nbins) + 1j * rng.standard_normal(nbins)
+        z /= np.linalg.norm(z)
+        p, src, from_amps = np.abs(z) ** 2, z, 1
+    else:
+        if kind == "probs_wide":
+            p = np.exp(rng.uniform(-60, 0, nbins))
+        elif kind == "probs_sparse":
+            p = np.where(rng.random_sample(nbins) < 0.01, rng.random_sample(nbins), 0.0)
+        else:
+            p = rng.random_sample(nbins)
+            p[nbins // 4: nbins // 2] = 0.0  # the second of four shards holds no probability at all
+        p = p / p.sum()
+        src, from_amps = p, 0
+    cdf = p.cumsum()
+    got, total, chunk_end = _run_cdf_shards(src, from_amps, n_shards, u)
+    assert total == cdf[-1]
+    assert np.array_equal(chunk_end, cdf[1023::1024])
+    assert np.array_equal(got, (cdf / cdf[-1]).searchsorted(u, side="right"))
+
+
+def test_scatter_bits_and_device_memory_helpers():
+    """qsv_scatter_bits (a shard's marginal into the full marginal), qsv_alloc / qsv_copy_d2d / qsv_free."""
+    import ctypes
+
+    import torch
+
+    lib = _lib.load()
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    rng = np.random.RandomState(2)
+    src = rng.random_sample(1 << 5)
+    dest_bits, base, log2_dst = [6, 0, 3, 1, 4], (1 << 2) | (1 << 7), 8
+    dev_src = torch.as_tensor(src, device="cuda")
+    dev_dst = torch.full((1 << log2_dst,), 7.0, dtype=torch.float64, device="cuda")
+    arr = (ctypes.c_int32 * 5)(*dest_bits)
+    _lib.check(lib.qsv_scatter_bits(ctypes.c_void_p(dev_src.data_ptr()), 5, arr, base, ctypes.c_void_p(dev_dst.data_ptr()),
+                                    log2_dst, stream), "qsv_scatter_bits")
+    want = np.zeros(1 << log2_dst)
+    for s_idx in range(32):
+        t_idx = base
+        for i, b in enumerate(dest_bits):
+            t_idx |= ((s_idx >> i) & 1) << b
+        want[t_idx] = src[s_idx]
+    assert np.array_equal(dev_dst.cpu().numpy(), want)
+    assert lib.qsv_scatter_bits(ctypes.c_void_p(dev_src.data_ptr()), 5, (ctypes.c_int32 * 5)(6, 0, 3, 1, 2), base,
+                                ctypes.c_void_p(dev_dst.data_ptr()), log2_dst, stream) == _lib.QSV_EINVAL
+    ptr = ctypes.c_void_p()
+    _lib.check(lib.qsv_alloc(ctypes.byref(ptr), 32 * 8), "qsv_alloc")
+    _lib.check(lib.qsv_copy_d2d(ptr, ctypes.c_void_p(dev_src.data_ptr()), 32 * 8, stream), "qsv_copy_d2d")
+    back = torch.zeros(32, dtype=torch.float64, device="cuda")
+    _lib.check(lib.qsv_copy_d2d(ctypes.c_void_p(back.data_ptr()), ptr, 32 * 8, stream), "qsv_copy_d2d")
+    torch.cuda.synchronize()
+    assert np.array_equal(back.cpu().numpy(), src)
+    _lib.check(lib.qsv_free(ptr), "qsv_free")
+    st = make_state(12, rand_state(12, 3))
+    before = st.download()
+    snap = st.snapshot()
+    st.apply_ops([GateOp(_lib.GATE_DENSE1, [3], rand_unitary(1, rng))])
+    st.restore(snap)
+    assert np.array_equal(st.download(), before)
