@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the B200 statevector hot path.
 
-Metric (BASELINE.json): gate-pass HBM GB/s & circuit seconds on quantum-volume circuits.
+Metric (BASELINE.json): gate-pass HBM GB/s & circuit seconds on quantum-volume / QFT / random circuits.
 A *step* is one full run of the hot path on one synthetic circuit: initialise |0..0>, apply every
 gate of QuantumVolume(n, n, seed=1234) (n*floor(n/2) SU(4) `unitary` ops), draw 8192 shots.
 
@@ -12,16 +12,20 @@ gate of QuantumVolume(n, n, seed=1234) (n*floor(n/2) SU(4) `unitary` ops), draw 
              buffers: Qobj (gate matrices) in, counts out, planning/H2D/D2H inside the timed region
     roofline: the dominant kernel is tile_pass_kernel (one launch = one pass = 32*2^n algorithmic
              bytes); achieved = passes*32*2^n / time of the pass section (CUDA events, live)
-    cpu_baseline: the numpy oracle port of the reference (one core: np.einsum is single threaded)
-             on a bounded sample of the same circuit family at the reference's 24-qubit cap
+    cpu_baseline: the reference's own QasmSimulatorPy.run (np.einsum per gate, one core) on a bounded
+             sample of the same circuit family at the reference's 24-qubit cap
+    qft / random: the other two circuit families of BASELINE's metric, with per-pass rooflines
 
 N = 1 workload: 33-qubit QV (BASELINE config 4, 128 GiB state) -- the largest single-GPU config.
 N > 1: weak scaling, 33 local qubits per GPU (34/35/36 qubits on 2/4/8 GPUs, BASELINE config 5),
-one process per GPU, state sharded by the high-order qubits, qubit-swap exchanges over NCCL.
+one process per GPU, state sharded by the high-order qubits, qubit-swap exchanges over NCCL; before the
+timed region the golden fixtures run through the sharded simulators as a parity gate (`check.parity`).
 
-`--impl reference` times the reference's CPU algorithm (oracle port) on a bounded sample.
+`--impl reference` times the reference's own CPU implementation (QasmSimulatorPy.run from the copy under
+baseline/_ref; the numpy oracle port if that cannot be imported) on a bounded sample per step.
 """
 import argparse
+import copy
 import json
 import os
 import statistics
@@ -42,9 +46,10 @@ SHOTS = 8192
 QV_SEED = 1234
 SIM_SEED = 42
 REF_QUBITS = 24          # reference cap (qasm_simulator.py:64)
-REF_GATES_PER_STEP = 6   # bounded sample per reference step (~0.4 s per gate at n=24)
+REF_GATES_PER_STEP = 24  # bounded CPU sample per step: every 12th SU(4) of QuantumVolume(24) (~0.3-0.9 s per gate)
+RANDOM_DEPTH = 20
 FP64_DMMA_PEAK_TFLOPS = 37.0      # measured: tools/fp64_peak.cu on B200 (DMMA.8x8x4), profiles/r1_fp64_peak_dfma_vs_dmma.txt
-TRAFFIC_BYTES_PER_AMP = 31.78     # measured DRAM bytes per amplitude per pass (ncu, n=28; writes still in L2 at kernel end are not counted)
+NCU_TRAFFIC_FILE = os.path.join("profiles", "r2_tile_pass_ncu_dram.json")  # written by tools/ncu_summary.py from an ncu CSV
 
 
 def measured_peaks():
@@ -53,6 +58,21 @@ def measured_peaks():
         with open(path) as fh:
             return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def measured_traffic(n):
+    """DRAM bytes per launch of the pass kernel from the committed ncu capture (dram__bytes_read.sum +
+    dram__bytes_write.sum of one `ncu --set full` launch), scaled by 2^(n - n_capture) when the sizes differ."""
+    path = os.path.join(ROOT, NCU_TRAFFIC_FILE)
+    if not os.path.exists(path):
+        return None, "no ncu capture committed (%s missing)" % NCU_TRAFFIC_FILE
+    with open(path) as fh:
+        rec = json.load(fh)
+    per_launch = float(rec["dram_bytes_read"]) + float(rec["dram_bytes_write"])
+    scale = 2.0 ** (n - int(rec["n_qubits"]))
+    return per_launch * scale, "%s: dram__bytes_read %.4g + dram__bytes_write %.4g per launch at n=%d (%s)%s" % (
+        NCU_TRAFFIC_FILE, rec["dram_bytes_read"], rec["dram_bytes_write"], rec["n_qubits"], rec.get("source", "ncu --set full"),
+        "" if scale == 1.0 else ", scaled by 2^%d" % (n - int(rec["n_qubits"])))
 
 
 class ClockSampler:
@@ -115,78 +135,117 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
+def workload_config(n, depth, tile, world=1, n_local=None):
+    """Description of the workload -- the same dict in the B200 arm and in the reference arm (host-only: the
+    planner runs without a GPU)."""
+    from qiskit_sdk_py_b200 import circuits, lower, planner
+
+    ins = [i for i in circuits.quantum_volume_instructions(n, depth, QV_SEED) if i["name"] == "unitary"]
+    cfg = {
+        "workload": "QuantumVolume(%d, depth %d, seed %d): %d SU(4) gates + %d-shot sampling, complex128 statevector "
+                    "(%.1f GiB)%s -- BASELINE config %d" % (
+                        n, depth, QV_SEED, len(ins), SHOTS, 16 * 2 ** n / 2 ** 30,
+                        " on one B200" if world == 1 else " sharded over %d B200 (%d local qubits, %.1f GiB per GPU)" % (
+                            world, n_local, 16 * 2 ** n_local / 2 ** 30), 4 if world == 1 else 5),
+        "n_qubits": n, "depth": depth, "gates": len(ins), "shots": SHOTS, "tile_qubits": tile,
+        "l2": "state (%.1f GiB per GPU) is far larger than the 126 MB L2; no flush needed" % (
+            16 * 2 ** (n_local or n) / 2 ** 30),
+        "sampler": "exact-order (numpy cumsum order, bit-exact seeded counts)",
+    }
+    if world == 1:
+        ops = [lower.lower_gate(i["name"], i["qubits"], i.get("params")) for i in ins]
+        passes = planner.plan_passes(ops, n, tile)
+        cfg["passes"] = len(passes)
+        cfg["gates_per_pass"] = len(ins) / len(passes)
+    else:
+        cfg["local_qubits"] = n_local
+        cfg["parallelism"] = ("state sharded by the %d high-order qubits; qubit swaps = fused all-to-all exchanges over "
+                              "NCCL send/recv" % int(round(np.log2(world))))
+    return cfg
+
+
+# ---- the reference's CPU implementation on a bounded sample ----------------------------------------
+def cpu_sample_qobj(n=REF_QUBITS, n_gates=REF_GATES_PER_STEP):
+    """`n_gates` SU(4) gates spread evenly over QuantumVolume(n, n, seed) (every k-th gate of the circuit, so the
+    sample sees the same mix of qubit pairs -- einsum's speed depends on which axes a gate touches), no measurement."""
+    from qiskit_sdk_py_b200 import circuits
+
+    ins = [i for i in circuits.quantum_volume_instructions(n, n, QV_SEED) if i["name"] == "unitary"]
+    stride = max(1, len(ins) // n_gates)
+    pick = ins[::stride][:n_gates]
+    exp = circuits.make_experiment("qv_sample_%d" % n, n, pick, memory_slots=0)
+    return circuits.make_qobj([exp], shots=1, seed_simulator=SIM_SEED), len(pick), stride
+
+
+def reference_runner():
+    """(kind, run(qobj_dict) -> result) -- the reference's own QasmSimulatorPy when its package can be imported
+    (baseline/_ref on the GPU box, /root/reference in the build container), else the numpy oracle port."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "oracle", "ref_env"))
+        import warnings
+
+        import ref_import
+
+        ref_import.import_reference()
+        warnings.simplefilter("ignore")
+        from qiskit import BasicAer
+        from qiskit.qobj import QasmQobj
+
+        backend = BasicAer.get_backend("qasm_simulator")
+
+        def run(qobj_dict):
+            return backend.run(QasmQobj.from_dict(copy.deepcopy(qobj_dict))).result()
+
+        return "reference", run, "QasmSimulatorPy.run(qobj) of the unmodified reference (%s)" % ref_import.REFERENCE_ROOT
+    except Exception as exc:  # the reference package is not importable here: the port restates the same numpy calls
+        from oracle import basicaer_oracle as orc
+
+        sim = orc.OracleQasmSimulator()
+        return "port", (lambda qobj_dict: sim.run(copy.deepcopy(qobj_dict))), "oracle port (reference import failed: %s)" % exc
+
+
+def cpu_reference_leg(steps, warmup, n=REF_QUBITS, n_gates=REF_GATES_PER_STEP):
+    kind, run, how = reference_runner()
+    qobj, picked, stride = cpu_sample_qobj(n, n_gates)
+    warm_qobj, _, _ = cpu_sample_qobj(n, 2)
+    for _ in range(max(1, warmup) if warmup else 0):
+        run(warm_qobj)  # page-in / allocator warm-up on a 2-gate sample (a full sample step costs ~10 s)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        run(qobj)
+        times.append(time.perf_counter() - t0)
+    dt = sum(times)
+    value = steps * picked * 32.0 * 2 ** n / dt / 1e9
+    return {
+        "value": value, "unit": UNIT, "cores": 1, "kind": kind, "host_cpus": os.cpu_count(), "seconds": dt,
+        "ms_per_step": dt / steps * 1e3,
+        "sample": "%d SU(4) gates per step = every %dth gate of QuantumVolume(%d, depth %d, seed %d) (the reference caps "
+                  "at 24 qubits), shots=1, through %s; np.einsum is single-threaded" % (picked, stride, n, n, QV_SEED, how),
+    }
+
+
 def reference_arm(args):
-    """The reference's own CPU algorithm (numpy oracle port; np.einsum, one thread) on a bounded
-    sample: REF_GATES_PER_STEP SU(4) gates of the same QV family at the reference's 24-qubit cap."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import basicaer_oracle as orc
-    from qiskit_sdk_py_b200 import circuits
+    from qiskit_sdk_py_b200 import planner
 
-    n = args.ref_qubits
-    ins = circuits.quantum_volume_instructions(n, 2, QV_SEED)
-    gates = [i for i in ins if i["name"] == "unitary"][: args.ref_gates]
-    state = np.zeros(2 ** n, dtype=complex)
-    state[0] = 1.0
-    state = state.reshape([2] * n)
-
-    def step(st):
-        for g in gates:
-            st = orc.apply_unitary(st, g["params"][0], g["qubits"])
-        return st
-
-    for _ in range(args.warmup):
-        state = step(state)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        state = step(state)
-    dt = time.perf_counter() - t0
-    bytes_per_gate = 32.0 * 2 ** n
-    value = args.steps * len(gates) * bytes_per_gate / dt / 1e9
-    sample = "%d SU(4) gates of QuantumVolume(%d, seed=%d) per step (reference cap is 24 qubits)" % (
-        len(gates), n, QV_SEED)
+    world = max(1, args.gpus)
+    n = args.qubits + int(round(np.log2(world)))
+    cfg = workload_config(n, args.depth or n, args.tile or planner.DEFAULT_TILE_QUBITS, world, args.qubits)
+    leg = cpu_reference_leg(args.steps, args.warmup, args.ref_qubits, args.ref_gates)
     line = {
         "impl": "reference",
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "metric": METRIC, "value": leg["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": leg["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "QuantumVolume gate passes, complex128 statevector, CPU reference algorithm "
-                               "(np.einsum per gate, qasm_simulator.py:145-161)", "n_qubits": n,
-                   "gates_per_step": len(gates)},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
-                         "host_cpus": os.cpu_count()},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": cfg,
+        "cpu_baseline": {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample", "host_cpus", "seconds")},
+        "e2e": {"value": leg["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
-
-
-def cpu_baseline_leg(seconds_budget=20.0):
-    """Oracle port on this box's host cores (one: np.einsum is single-threaded), bounded sample."""
-    from oracle import basicaer_oracle as orc
-    from qiskit_sdk_py_b200 import circuits
-
-    n = REF_QUBITS
-    ins = [i for i in circuits.quantum_volume_instructions(n, 4, QV_SEED) if i["name"] == "unitary"]
-    state = np.zeros(2 ** n, dtype=complex)
-    state[0] = 1.0
-    state = state.reshape([2] * n)
-    state = orc.apply_unitary(state, ins[0]["params"][0], ins[0]["qubits"])  # warm-up / page-in
-    done = 0
-    t0 = time.perf_counter()
-    for g in ins[1:]:
-        state = orc.apply_unitary(state, g["params"][0], g["qubits"])
-        done += 1
-        if time.perf_counter() - t0 > seconds_budget:
-            break
-    dt = time.perf_counter() - t0
-    return {
-        "value": done * 32.0 * 2 ** n / dt / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
-        "host_cpus": os.cpu_count(), "seconds": dt,
-        "sample": "%d SU(4) gate passes of QuantumVolume(%d, seed=%d) (reference cap 24 qubits), "
-                  "np.einsum per gate as qasm_simulator.py:145-161" % (done, n, QV_SEED),
-    }
 
 
 # ------------------------------------------------------------------------------------------------
@@ -196,6 +255,44 @@ def pick_qubits(requested, torch, reserve=3 << 30):
     while n > 20 and (16 << n) + reserve > free:
         n -= 1
     return n
+
+
+def timed_passes(st, passes, torch, n):
+    """Run planned passes one by one with CUDA events; returns per-pass ms."""
+    stream = torch.cuda.current_stream()
+    events = []
+    for p in passes:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        st.apply_pass(p.tile_qubits, p.ops, tail=p.tail or None)
+        e1.record(stream)
+        events.append((e0, e1))
+    torch.cuda.synchronize()
+    return [a.elapsed_time(b) for a, b in events]
+
+
+def family_block(name, instructions, n, tile, st, torch, peak):
+    """Per-pass roofline of another circuit family (QFT, random basis-gate circuit) on the resident state."""
+    from qiskit_sdk_py_b200 import lower, planner
+
+    ops = [o for o in (lower.lower_gate(i["name"], i["qubits"], i.get("params")) for i in instructions) if o is not None]
+    merged = planner.merge_ops(ops)
+    passes = planner.plan_passes(merged, n, tile, tails=True)
+    st.init_basis0()
+    timed_passes(st, passes, torch, n)  # warm-up
+    ms = timed_passes(st, passes, torch, n)
+    per_pass_gbs = [32.0 * 2 ** n / (t * 1e-3) / 1e9 for t in ms]
+    return {
+        "workload": name, "instructions": len(ops), "merged_ops": len(merged), "passes": len(passes),
+        "tail_gates": sum(len(p.tail) for p in passes), "pass_section_ms": sum(ms),
+        "reference_equivalent_GBps": len(ops) * 32.0 * 2 ** n / (sum(ms) * 1e-3) / 1e9,
+        "roofline": {"bound": "hbm", "kernel": "tile_pass_kernel", "unit": "GB/s", "peak": peak,
+                     "achieved": len(passes) * 32.0 * 2 ** n / (sum(ms) * 1e-3) / 1e9,
+                     "frac": len(passes) * 32.0 * 2 ** n / (sum(ms) * 1e-3) / 1e9 / peak,
+                     "per_pass_ms": [round(t, 3) for t in ms],
+                     "per_pass_frac": [round(g / peak, 3) for g in per_pass_gbs],
+                     "worst_pass_frac": min(per_pass_gbs) / peak},
+    }
 
 
 def main():
@@ -211,6 +308,8 @@ def main():
     ap.add_argument("--ref-gates", type=int, default=REF_GATES_PER_STEP)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-families", action="store_true", help="skip the QFT / random-circuit blocks")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the golden parity gate")
     args = ap.parse_args()
 
     # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on
@@ -230,17 +329,17 @@ def main():
     from qiskit_sdk_py_b200.engine import DeviceState
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     if world > 1:
         from qiskit_sdk_py_b200 import dist as qdist
 
-        return qdist.bench_main(args, METRIC, UNIT, measured_peaks, ClockSampler)
+        return qdist.bench_main(args, sys.modules[__name__])
 
     n = pick_qubits(args.qubits, torch)
     depth = args.depth or n
     tile = args.tile or planner.DEFAULT_TILE_QUBITS
+    cfg = workload_config(n, depth, tile)
     qobj = circuits.quantum_volume(n, depth, QV_SEED, shots=SHOTS, seed_simulator=SIM_SEED)
     instructions = qobj["experiments"][0]["instructions"]
     gate_ins = [i for i in instructions if i["name"] == "unitary"]
@@ -253,7 +352,6 @@ def main():
     st = DeviceState(n, tile_qubits=tile)
     uniforms = np.random.RandomState(SIM_SEED).random_sample(SHOTS)
     measured = list(range(n))
-    exact = True  # numpy cumsum order at every size (parallel exact scan)
     stream = torch.cuda.current_stream()
 
     def device_step(ev=None):
@@ -264,8 +362,7 @@ def main():
             st.apply_pass(p.tile_qubits, p.ops)
         if ev:
             ev[1].record(stream)
-        samples, total = st.sample(measured, uniforms, exact_order=exact)
-        return samples, total
+        return st.sample(measured, uniforms, exact_order=True)
 
     for _ in range(args.warmup):
         device_step()
@@ -292,6 +389,7 @@ def main():
     achieved = bytes_per_gate_pass / (per_launch_ms * 1e-3) / 1e9
     assert abs(total - 1.0) < 1e-9, total
     counts_top = int(np.bincount(samples % 4096).max())
+    traffic, traffic_src = measured_traffic(n)
 
     # FP64 work of the pass launches.  `nominal`: 32 flop per amplitude per SU(4) gate (a 4x4 complex matrix on
     # groups of 4 amplitudes).  `executed`: what the kernel issues after gate fusion -- a lone 2-qubit op is 2
@@ -313,12 +411,23 @@ def main():
         "frac_at_measured_clock": (flops_executed / (pass_ms * 1e-3) / (148 * 128 * clock_info["sm_mhz"] * 1e6)
                                    if clock_info.get("sm_mhz") else None),
         "kernel_ops": {"fused_3qubit_blocks": n_blocks, "2qubit_ops": n_single,
-                       "group_variant_passes": sum(i["threads"] == 768 for i in infos)},
+                       "group_variant_passes": sum(i["threads"] == 864 for i in infos)},
         "peak_source": "measured on B200 with tools/fp64_peak.cu (profiles/r1_fp64_peak_dfma_vs_dmma.txt)",
         "flops": "executed: 32 flop/amplitude per lone 2-qubit op (2 DMMA.8x8x4 per 32 amplitudes), 49 per fused "
                  "3-qubit block in the 3-multiplication form (6 DMMA + 2 DADD per 64 amplitudes); nominal: 32 per "
                  "SU(4) gate",
     }
+
+    # ---- the other circuit families of BASELINE's metric, per-pass rooflines on the same resident state ----
+    qft = rnd = None
+    if not args.no_families:
+        qft_ins = [i for i in circuits.qft(n, state_seed=3)["experiments"][0]["instructions"]
+                   if i["name"] not in ("measure", "barrier")]
+        qft = family_block("QFT(%d) with final swaps on a product state, basis gates u1/u2/u3/cx" % n, qft_ins, n, tile, st,
+                           torch, peak)
+        rnd_ins = circuits.random_basis_instructions(n, RANDOM_DEPTH, 7)
+        rnd = family_block("random basis-gate circuit (u1/u2/u3/rz/sx/x/cx + 2-qubit unitaries), %d qubits, depth %d, seed 7"
+                           % (n, RANDOM_DEPTH), rnd_ins, n, tile, st, torch, peak)
 
     # ---- end-to-end leg through the plugin-facing call, host buffers in and out ------------------
     e2e = None
@@ -326,8 +435,6 @@ def main():
         del st
         torch.cuda.empty_cache()
         sim = simulator.QasmSimulatorB200(tile_qubits=tile, max_qubits=max(n, 33))
-        import copy
-
         sim.run(copy.deepcopy(qobj))  # warm-up (allocation, attribute set-up)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -342,48 +449,35 @@ def main():
         e2e = {"value": n_gates * bytes_per_gate_pass / e2e_s / 1e9, "unit": UNIT,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "circuit_s": e2e_s,
                "api": "QasmSimulatorB200.run(qobj dict) -> counts"}
-
-    # ---- second workload family of BASELINE's metric (informational, outside the timed headline): QFT on the
-    # same register, in the simulator basis, through the same plugin-facing call ---------------------
-    qft = None
-    if not args.no_e2e:
-        qft_qobj = circuits.qft(n, state_seed=3, shots=SHOTS, measure_final=True, seed_simulator=SIM_SEED)
-        n_ins = sum(1 for i in qft_qobj["experiments"][0]["instructions"] if i["name"] not in ("measure", "barrier"))
-        sim.run(copy.deepcopy(qft_qobj))
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        sim.run(copy.deepcopy(qft_qobj))
-        torch.cuda.synchronize()
-        qft_s = time.perf_counter() - t0
-        qft = {"workload": "QFT(%d) with final swaps on a product state, basis gates u1/u2/u3/cx, %d-shot sampling" % (n, SHOTS),
-               "instructions": n_ins, "passes": sim.last_stats.get("passes"), "circuit_s": qft_s,
-               "reference_equivalent_GBps": n_ins * bytes_per_gate_pass / qft_s / 1e9,
-               "note": "the reference makes one einsum pass per instruction; peephole merging, diagonal tables and "
-                       "diagonal tails bring the circuit down to `passes` passes over HBM"}
+        if qft is not None:  # the QFT family end to end through the same call
+            qft_qobj = circuits.qft(n, state_seed=3, shots=SHOTS, measure_final=True, seed_simulator=SIM_SEED)
+            sim.run(copy.deepcopy(qft_qobj))
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            sim.run(copy.deepcopy(qft_qobj))
+            torch.cuda.synchronize()
+            qft["e2e_circuit_s"] = time.perf_counter() - t0
+            rnd_qobj = circuits.random_circuit(n, RANDOM_DEPTH, 7, shots=SHOTS, seed_simulator=SIM_SEED)
+            sim.run(copy.deepcopy(rnd_qobj))
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            sim.run(copy.deepcopy(rnd_qobj))
+            torch.cuda.synchronize()
+            rnd["e2e_circuit_s"] = time.perf_counter() - t0
 
     cpu = None
     if not args.no_cpu_baseline:
-        cpu = cpu_baseline_leg()
+        cpu = cpu_reference_leg(1, 1, args.ref_qubits, args.ref_gates)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {
-            "workload": "QuantumVolume(%d, depth %d, seed %d): %d SU(4) gates + %d-shot sampling, complex128 "
-                        "statevector (%.1f GiB) on one B200 -- BASELINE config 4" % (
-                            n, depth, QV_SEED, n_gates, SHOTS, 16 * 2 ** n / 2 ** 30),
-            "n_qubits": n, "depth": depth, "gates": n_gates, "shots": SHOTS, "tile_qubits": tile,
-            "passes": len(passes), "gates_per_pass": n_gates / len(passes),
-            "circuit_s": step_ms * 1e-3,
-            "l2": "state (%.1f GiB) is far larger than the 126 MB L2; no flush needed" % (16 * 2 ** n / 2 ** 30),
-            "sampler": "exact-order" if exact else "blocked-parallel",
-        },
+        "config": cfg,
+        "circuit_s": step_ms * 1e-3,
         "roofline": {
             "bound": "hbm", "kernel": "tile_pass_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak, "traffic": TRAFFIC_BYTES_PER_AMP * 2 ** n, "peak_source": peak_src,
-            "traffic_source": "ncu --set full at n=28: dram__bytes_read 4.295 GB + write 4.236 GB per launch = "
-                              "31.8 B/amplitude (profiles/r1_tile_pass_kernel_ncu_full_summary.txt), scaled to 2^n",
+            "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "traffic_source": traffic_src,
             "algorithmic_bytes_per_launch": bytes_per_gate_pass, "launch_ms": per_launch_ms,
             "launches_per_step": len(passes), "pass_section_ms": pass_ms,
             # the fused pass is FP64-bound, not HBM-bound: the same launches against the measured DMMA peak
@@ -392,6 +486,7 @@ def main():
         "cpu_baseline": cpu,
         "e2e": e2e,
         "qft": qft,
+        "random_circuit": rnd,
         "gpu_launches": int(launches),
         "clocks": clock_info,
         "check": {"sample_total_prob": total, "max_bin_mod4096": counts_top},

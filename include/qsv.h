@@ -123,6 +123,13 @@ size_t qsv_tail_scratch_bytes(void);
 int qsv_pass_info(int n_qubits, const int32_t* tile_qubits, int n_tile, const qsv_gate_t* gates,
                   int n_gates, const int32_t* dest_qubits, int32_t* info);
 
+/* Host-only, like qsv_pass_info: the kernel ops of the lowered pass in execution order, four ints per op --
+ * kind (QSV_GATE_*; 6 = fused 3-qubit block), stage, physical qubits q0 | q1 << 8 of the op's two lane bits,
+ * flags (dense ops: bit 0 = its 128-bit shared-memory accesses are bank-conflict free, bit 1 = its 64-bit loads
+ * are).  Returns the number of ops written (<= max_ops) or a negative error.  Planning / profiling aid. */
+int qsv_pass_ops(int n_qubits, const int32_t* tile_qubits, int n_tile, const qsv_gate_t* gates, int n_gates,
+                 const int32_t* dest_qubits, int32_t* ops_out, int max_ops);
+
 /* psi <- (G on qubits) psi for a dense k-qubit matrix, k >= 1.  Replaces one _add_unitary call
  * (qasm_simulator.py:145-161; `unitary` instruction :543-546).  k <= 2 goes through qsv_apply_pass;
  * 3 <= k <= QSV_MAX_DENSE_K uses the staged dense kernel, which needs `dev_mat_scratch`, a device

@@ -1,8 +1,9 @@
 """Import the UNMODIFIED reference (Qiskit Terra 0.18, /root/reference) in this container.
 
 TEST INFRASTRUCTURE ONLY.  Used by tests/golden/make_golden.py (to generate the committed
-golden fixtures) and by the CPU-side adapter tests that are skipped when /root/reference is
-absent (it is absent on the GPU box).  Nothing in the product package imports this file.
+golden fixtures), by the adapter tests (CPU: numpy test double; GPU box: the real CUDA backends next to
+BasicAer in one process, from the baseline/_ref copy) and by bench.py's reference arm / cpu_baseline leg, which
+time the reference's own QasmSimulatorPy.  Nothing in the product package imports this file.
 
 The reference needs a few third-party modules that are not installed here and cannot be
 installed (no network): retworkx (-> retworkx_shim.py), ply (-> qasm2_reader.py), fastjsonschema, python-constraint, plus three Cython
@@ -16,7 +17,22 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("QISKIT_REFERENCE_ROOT", "/root/reference")
+_REPO_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def _default_root():
+    """/root/reference in the build container; on the GPU box (where that tree does not exist) the git-ignored copy
+    of the reference package that __graft_entry__.build() leaves under baseline/_ref/ and that ships with the
+    working tree."""
+    env = os.environ.get("QISKIT_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/qiskit"):
+        return "/root/reference"
+    return os.path.join(_REPO_ROOT, "baseline", "_ref")
+
+
+REFERENCE_ROOT = _default_root()
 
 
 def reference_available():

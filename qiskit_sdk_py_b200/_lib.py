@@ -69,6 +69,7 @@ SIGNATURES = {
                                      ctypes.POINTER(QsvGate), _c_int, _c_void_p, _c_void_p]),
     "qsv_tail_scratch_bytes": (_c_size_t, []),
     "qsv_pass_info": (_c_int, [_c_int, _p_int32, _c_int, ctypes.POINTER(QsvGate), _c_int, _p_int32, _p_int32]),
+    "qsv_pass_ops": (_c_int, [_c_int, _p_int32, _c_int, ctypes.POINTER(QsvGate), _c_int, _p_int32, _p_int32, _c_int]),
     "qsv_apply_matrix": (_c_int, [_c_void_p, _c_int, _p_int32, _c_int, _c_void_p, _c_void_p, _c_void_p]),
     "qsv_reduce_workspace_bytes": (_c_size_t, []),
     "qsv_prob_qubit": (_c_int, [_c_void_p, _c_int, _c_int, _c_void_p, _p_double, _c_void_p]),

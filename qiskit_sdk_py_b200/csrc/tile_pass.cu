@@ -80,15 +80,19 @@ static uint32_t debug_flags() {
 
 #ifdef QSV_PROFILE
 // per (CTA, group, role) phase totals in clocks; role 0 = compute warp 0, 1 = compute warp 7, 2 = producer
-constexpr int kProfSlots = 8;
+constexpr int kProfSlots = 20;  // 0-3 phases; 4 stage-barrier waits; 5 + o: op o of the pass (o < 15)
 __device__ unsigned long long g_prof[160 * 3 * 3 * kProfSlots];
 #define PROF_DECL unsigned long long prof_acc[kProfSlots] = {0}; long long prof_t0 = clock64();
 #define PROF_MARK(slot) do { const long long t1_ = clock64(); prof_acc[slot] += (unsigned long long)(t1_ - prof_t0); prof_t0 = t1_; } while (0)
+#define PROF_OP_BEGIN long long prof_t2 = clock64();
+#define PROF_OP_MARK(slot) do { const long long t3_ = clock64(); prof_acc[(slot) < kProfSlots ? (slot) : kProfSlots - 1] += (unsigned long long)(t3_ - prof_t2); prof_t2 = t3_; } while (0)
 #define PROF_FLUSH(role) do { if ((threadIdx.x & 31u) == 0 && blockIdx.x < 160) \
     for (int q_ = 0; q_ < kProfSlots; q_++) g_prof[((blockIdx.x * 3 + grp) * 3 + (role)) * kProfSlots + q_] = prof_acc[q_]; } while (0)
 #else
 #define PROF_DECL
 #define PROF_MARK(slot) do { } while (0)
+#define PROF_OP_BEGIN
+#define PROF_OP_MARK(slot) do { } while (0)
 #define PROF_FLUSH(role) do { } while (0)
 #endif
 
@@ -643,8 +647,10 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
     }
 
     int o = 0;
+    PROF_OP_BEGIN
     for (int sidx = 0; sidx < nstages; sidx++) {
       if (sidx > 0) gsync();  // stage boundary: warps re-partition the tile
+      PROF_OP_MARK(4);
       const uint32_t n_inner = d.stages[sidx].n_inner, n_outer = d.stages[sidx].n_outer;
       const int o_end = o + d.stages[sidx].n_ops;
       const bool warp_on = wid < (1u << n_outer);  // small tiles: fewer sub-cubes than warps
@@ -839,6 +845,7 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
         // kDB with debug flag 128: request the next tile only now, after the first op of this tile
         if constexpr (kDB)
           if (!next_issued) issue_next();
+        PROF_OP_MARK(5 + o);
       }
     }
     if constexpr (kDB)
@@ -1244,6 +1251,7 @@ static int ensure_attrs() {
 struct PassPlan {
   size_t smem;
   int threads, n_in, n_fused3;
+  uint8_t op_flags[kMaxOps];  // dense ops: bit 0 = 128-bit accesses conflict-free, bit 1 = 64-bit loads conflict-free
   bool groups;  // three double-buffered warp groups per CTA (tile_pass_kernel<768, 1, 3>)
 };
 
@@ -1262,6 +1270,7 @@ static int lower_pass(PassDesc& d, PassPlan& plan, int n, const int32_t* tile_qu
   if (n - n_tile > 31) return fail(QSV_ERANGE, "qsv_apply_pass: grid too large");
 
   memset(&d, 0, sizeof(d));
+  memset(plan.op_flags, 0, sizeof(plan.op_flags));
   const int b = n_tile;
   d.n = n;
   d.b = b;
@@ -1653,6 +1662,8 @@ static int lower_pass(PassDesc& d, PassPlan& plan, int n, const int32_t* tile_qu
         if (fb[i] != f0 && fb[i] != f1) fo[nfo++] = fb[i];
       op.ngl = (uint8_t)nf;
       for (int j = 0; j < 6; j++) op.col[j] = j < nf ? sw1(fo[j]) : 0;
+      plan.op_flags[k] = (uint8_t)((f0 >= 0 && independent3(bvec(f0), v0, v1) ? 1 : 0) |
+                                   (f0 >= 0 && f1 >= 0 && independent3(bvec(f0), bvec(f1), v0) ? 2 : 0));
     }
 
     // ---- runs of consecutive diagonal gates -> lookup tables (QFT-like circuits are mostly such runs) ----
@@ -2054,6 +2065,24 @@ int qsv_pass_info(int n, const int32_t* tile_qubits, int n_tile, const qsv_gate_
   info[6] = (int32_t)d.pb_st;
   info[7] = plan.n_in;
   return 0;
+}
+
+int qsv_pass_ops(int n, const int32_t* tile_qubits, int n_tile, const qsv_gate_t* gates, int n_gates,
+                 const int32_t* dest_qubits, int32_t* ops_out, int max_ops) {
+  if (!tile_qubits || !ops_out || (n_gates > 0 && !gates)) return fail(QSV_EINVAL, "qsv_pass_ops: null pointer");
+  static thread_local PassDesc d;
+  PassPlan plan;
+  if (int rc = lower_pass(d, plan, n, tile_qubits, n_tile, gates, n_gates, dest_qubits)) return rc;
+  int o = 0;
+  for (int sidx = 0; sidx < d.nstages; sidx++)
+    for (int k = 0; k < d.stages[sidx].n_ops && o < max_ops; k++, o++) {
+      const PassOp& op = d.ops[o];
+      ops_out[4 * o] = op.kind;
+      ops_out[4 * o + 1] = sidx;
+      ops_out[4 * o + 2] = d.tb[op.t0] | (d.tb[op.t1] << 8);
+      ops_out[4 * o + 3] = plan.op_flags[o];
+    }
+  return o;
 }
 
 int qsv_apply_pass_remap(double* sv, int n, const int32_t* tile_qubits, int n_tile, const qsv_gate_t* gates,

@@ -26,6 +26,7 @@ import numpy as np
 
 from . import _lib
 from .lower import GateOp
+from .planner import DEFAULT_TILE_QUBITS as DEFAULT_TILE
 
 DEFAULT_CHUNK_AMPS = 1 << 26  # 1 GiB staging buffers
 
@@ -59,6 +60,7 @@ class ShardedState:
         self.swaps = 0
         self.fused_exchanges = 0
         self.swap_bytes = 0
+        self._xch_events = []   # (start, end) CUDA events around every exchange (device shards only)
 
     # -- helpers -----------------------------------------------------------------------
     def _logical_at(self, phys):
@@ -101,10 +103,37 @@ class ShardedState:
         self.apply_ops([GateOp(_lib.GATE_DENSE1, [n_half + j], fan) for j in range(n_half)] +
                        [GateOp(_lib.GATE_CX, [n_half + j, j], None) for j in range(n_half)])
 
+    # -- exchange timing (bench.py: exchange vs pass time per step) -------------------------------
+    def _xch_begin(self):
+        if getattr(self.shard, "device", None) is None:
+            return None
+        ev = self._torch.cuda.Event(enable_timing=True)
+        ev.record()
+        return ev
+
+    def _xch_end(self, begin):
+        if begin is not None:
+            ev = self._torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self._xch_events.append((begin, ev))
+
+    @property
+    def exchange_ms(self):
+        """Marker for exchange_time_ms: exchanges recorded so far."""
+        return len(self._xch_events)
+
+    def exchange_time_ms(self, since=0):
+        """Device time (ms) of the exchanges recorded after marker ``since`` (synchronises)."""
+        if not self._xch_events[since:]:
+            return 0.0
+        self._torch.cuda.synchronize()
+        return float(sum(a.elapsed_time(b) for a, b in self._xch_events[since:]))
+
     # -- the exchange step -------------------------------------------------------------
     def swap_global_local(self, phys_global, phys_local):
         """Swap physical bits (global j, local L): exchange the half with bit L != my bit j."""
         dist = self._dist
+        t_begin = self._xch_begin()
         j = phys_global - self.n_local
         beta = (self.rank >> j) & 1
         peer = self.rank ^ (1 << j)
@@ -137,6 +166,7 @@ class ShardedState:
             self.shard.unpack_half(phys_local, 1 - beta, recv[i % 2], begin, cnt)
             if i + 2 < len(spans):
                 self.shard.pack_half(phys_local, 1 - beta, send[i % 2], spans[i + 2][0], spans[i + 2][1])
+        self._xch_end(t_begin)
         qa, qb = self._logical_at(phys_global), self._logical_at(phys_local)
         self.pos[qa], self.pos[qb] = phys_local, phys_global
         self.swaps += 1
@@ -150,6 +180,7 @@ class ShardedState:
         if len(pairs) == 1:
             return self.swap_global_local(*pairs[0])
         dist = self._dist
+        t_begin = self._xch_begin()
         k = len(pairs)
         gbits = [pg - self.n_local for pg, _ in pairs]
         lbits = [pl for _, pl in pairs]
@@ -205,6 +236,7 @@ class ShardedState:
             unpack(i)
             if i + 2 < len(spans):
                 pack(i + 2)
+        self._xch_end(t_begin)
         for pg, pl in pairs:
             qa, qb = self._logical_at(pg), self._logical_at(pl)
             self.pos[qa], self.pos[qb] = pl, pg
@@ -605,8 +637,60 @@ def distributed_simulator(backend="qasm_simulator", shard_factory=None, group=No
     return cls(state_factory=state_factory, seed_sync=seed_sync, **kwargs)
 
 
-def bench_main(args, metric, unit, measured_peaks, clock_sampler_cls):
-    """bench.py leg for N > 1 GPUs: weak scaling, args.qubits local qubits per GPU."""
+# Golden fixtures (outputs of the unmodified reference, tests/golden/) run through the sharded simulators before the
+# timed region of bench.py --gpus N: seeded counts / memory identical, amplitudes <= 1e-10.  A case is used when its
+# register leaves every rank at least two local qubits.
+PARITY_CASES = ["qv_20_counts", "qv_24_counts", "qft_20", "qv_18_state", "midcircuit_8", "sv_midcircuit_10",
+                "transpiled_init_reset_cond_counts", "sampler_marginal_subset", "random_14_counts", "random_6_unitary",
+                "random_4_unitary", "unitary_random"]
+
+
+def parity_gate(factory_kwargs, world, cases=None, device="cuda"):
+    """Run PARITY_CASES through distributed_simulator on every rank; returns (summary string, details)."""
+    import sys
+    import time
+
+    import torch
+    import torch.distributed as dist
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    tests_dir = os.path.join(root, "tests")
+    if tests_dir not in sys.path:
+        sys.path.insert(0, tests_dir)
+    import golden_io  # fixtures + comparison helpers are test infrastructure (no oracle code involved)
+    import helpers
+
+    g = int(round(math.log2(world)))
+    ran, failed, details = 0, [], {}
+    for name in (cases or PARITY_CASES):
+        case = golden_io.load_case(name)
+        n = case["qobj"]["config"]["n_qubits"]
+        n_state = 2 * n if case["backend"] == "unitary_simulator" else n
+        if n_state - g < 2:
+            continue
+        t0 = time.perf_counter()
+        err = ""
+        try:
+            result = helpers.run_case_with(lambda backend: distributed_simulator(backend, **factory_kwargs), case)
+            helpers.compare_result(result, case, amp_tol=1e-10)
+        except AssertionError as exc:
+            err = "mismatch %s" % (str(exc)[:120],)
+        flag = torch.tensor([1 if err else 0], device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)  # a mismatch on ANY rank fails the case
+        ran += 1
+        details[name] = {"backend": case["backend"], "n_qubits": n, "ok": int(flag.item()) == 0,
+                         "s": round(time.perf_counter() - t0, 3)}
+        if int(flag.item()):
+            failed.append(name + (": " + err if err else ""))
+    summary = "golden %d/%d identical" % (ran - len(failed), ran)
+    if failed:
+        summary += " FAILED: " + "; ".join(failed)
+    return summary, details
+
+
+def bench_main(args, bench):
+    """bench.py leg for N > 1 GPUs: weak scaling, args.qubits local qubits per GPU.  ``bench`` is the bench.py module
+    (metric names, clock sampler, peaks, workload description)."""
     import json
 
     import torch
@@ -632,12 +716,20 @@ def bench_main(args, metric, unit, measured_peaks, clock_sampler_cls):
     n = n_local + g
     depth = args.depth or n
     tile = args.tile or None
-    shots, qv_seed, sim_seed = 8192, 1234, 42
+    shots, qv_seed, sim_seed = bench.SHOTS, bench.QV_SEED, bench.SIM_SEED
+    factory = (lambda k: DeviceState(k, tile_qubits=tile)) if tile else DeviceState
+    chunk_amps = min(chunk, 1 << (n_local - 1))
+
+    # ---- parity gate: golden fixtures through the sharded simulators (every rank, before anything is timed) ----
+    parity, parity_details = ("skipped (--no-parity)", {})
+    if not args.no_parity:
+        parity, parity_details = parity_gate({"shard_factory": factory, "chunk_amps": 1 << 22, "max_qubits": 40}, world)
+        torch.cuda.empty_cache()
+
     ins = [i for i in circuits.quantum_volume_instructions(n, depth, qv_seed) if i["name"] == "unitary"]
     ops = [lower.lower_gate(i["name"], i["qubits"], i.get("params")) for i in ins]
     n_gates = len(ops)
-    factory = (lambda k: DeviceState(k, tile_qubits=tile)) if tile else DeviceState
-    st = ShardedState(n, factory, chunk_amps=min(chunk, 1 << (n_local - 1)))
+    st = ShardedState(n, factory, chunk_amps=chunk_amps)
     uniforms = np.random.RandomState(sim_seed).random_sample(shots)
 
     def step():
@@ -645,33 +737,67 @@ def bench_main(args, metric, unit, measured_peaks, clock_sampler_cls):
         st.apply_ops(ops)
         return st.sample_all(uniforms)  # restores the identity layout, then the exact-order CDF across the ranks
 
+    def timed(fn, reps):
+        """Device time of `reps` calls of fn, max over ranks (CUDA events, barrier + synchronize on both sides)."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0.record()
+        out = None
+        for _ in range(reps):
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()) / reps, out
+
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
     dist.barrier()
-    clocks = clock_sampler_cls(local_rank)
+    clocks = bench.ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
     launches0 = _lib.launch_count()
-    swaps0, bytes0 = st.swaps, st.swap_bytes
+    swaps0, bytes0, fused0 = st.swaps, st.swap_bytes, st.fused_exchanges
     passes0 = st.shard.passes_launched
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    dist.barrier()
-    e0.record()
-    for _ in range(args.steps):
-        samples, total = step()
-    e1.record()
-    torch.cuda.synchronize()
-    dist.barrier()
-    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
-    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    step_ms = float(ms.item()) / args.steps
+    xch0 = st.exchange_ms
+    step_ms, (samples, total) = timed(step, args.steps)
     launches = torch.tensor([_lib.launch_count() - launches0], device="cuda", dtype=torch.int64)
     dist.all_reduce(launches, op=dist.ReduceOp.SUM)
     passes_dev = (st.shard.passes_launched - passes0) / args.steps
     swaps_dev = (st.swaps - swaps0) / args.steps
+    fused_dev = (st.fused_exchanges - fused0) / args.steps
     swap_gb_dev = (st.swap_bytes - bytes0) / args.steps / 1e9
+    exchange_ms = st.exchange_time_ms(xch0) / args.steps
+    clock_info = clocks.stop() if rank == 0 else None
+
+    # ---- the other circuit families of BASELINE's metric on the sharded state (one warm-up, one timed run each) ----
+    families = {}
+    if not args.no_families:
+        qft_ins = [i for i in circuits.qft(n, state_seed=3)["experiments"][0]["instructions"]
+                   if i["name"] not in ("measure", "barrier")]
+        rnd_ins = circuits.random_basis_instructions(n, bench.RANDOM_DEPTH, 7)
+        for key, label, fins in (("qft", "QFT(%d) with final swaps on a product state, basis gates" % n, qft_ins),
+                                 ("random_circuit", "random basis-gate circuit, %d qubits, depth %d, seed 7"
+                                  % (n, bench.RANDOM_DEPTH), rnd_ins)):
+            fops = [o for o in (lower.lower_gate(i["name"], i["qubits"], i.get("params")) for i in fins) if o is not None]
+
+            def run_family():
+                st.init_basis0()
+                st.apply_ops(fops)
+                st.restore_identity_layout()
+                return st.norm2()
+
+            run_family()
+            p0, s0, b0 = st.shard.passes_launched, st.swaps, st.swap_bytes
+            fam_ms, nrm = timed(run_family, 1)
+            families[key] = {"workload": label, "instructions": len(fops), "circuit_s": fam_ms * 1e-3,
+                             "local_passes": st.shard.passes_launched - p0, "qubit_swaps": st.swaps - s0,
+                             "swap_GB_per_gpu": (st.swap_bytes - b0) / 1e9, "norm2": nrm,
+                             "reference_equivalent_GBps": len(fops) * 32.0 * 2 ** n / (fam_ms * 1e-3) / 1e9}
 
     # ---- end-to-end leg: the same circuit through the plugin-facing call on every rank (SPMD), host Qobj in
     # (gate matrices + shots), counts out; wall clock around run(), max over ranks -----------------------------
@@ -684,8 +810,7 @@ def bench_main(args, metric, unit, measured_peaks, clock_sampler_cls):
         torch.cuda.empty_cache()
         try:
             qobj = circuits.quantum_volume(n, depth, qv_seed, shots=shots, seed_simulator=sim_seed)
-            sim = distributed_simulator("qasm_simulator", shard_factory=factory,
-                                        chunk_amps=min(chunk, 1 << (n_local - 1)), max_qubits=n)
+            sim = distributed_simulator("qasm_simulator", shard_factory=factory, chunk_amps=chunk_amps, max_qubits=n)
             sim.run(copy.deepcopy(qobj))  # warm-up (allocation of the shard and the staging buffers)
             torch.cuda.synchronize()
             dist.barrier()
@@ -699,7 +824,7 @@ def bench_main(args, metric, unit, measured_peaks, clock_sampler_cls):
             counts = res["results"][0]["data"]["counts"]
             assert sum(counts.values()) == shots
             e2e_s = float(e2e_ms.item()) * 1e-3
-            e2e = {"value": n_gates * 32.0 * 2 ** n / e2e_s / 1e9, "unit": unit,
+            e2e = {"value": n_gates * 32.0 * 2 ** n / e2e_s / 1e9, "unit": bench.UNIT,
                    "h2d_bytes_per_step": int(world * (n_gates * 256 + shots * 8)),
                    "d2h_bytes_per_step": int(world * (shots * 8 + 8)), "circuit_s": e2e_s,
                    "api": "dist.distributed_simulator('qasm_simulator').run(qobj dict) -> counts, on every rank "
@@ -710,37 +835,37 @@ def bench_main(args, metric, unit, measured_peaks, clock_sampler_cls):
             # a deterministic host-side failure is the same on every rank: report it instead of losing the line
             e2e_error = "%s: %s" % (type(exc).__name__, exc)
     if rank == 0:
-        clock_info = clocks.stop()
         bytes_per_gate_pass = 32.0 * 2 ** n
         value = n_gates * bytes_per_gate_pass / (step_ms * 1e-3) / 1e9
-        passes, swaps, swap_gb = passes_dev, swaps_dev, swap_gb_dev
-        peak, peak_src = measured_peaks()
+        peak, peak_src = bench.measured_peaks()
+        cfg = bench.workload_config(n, depth, args.tile or DEFAULT_TILE, world, n_local)
         line = {
-            "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
+            "metric": bench.METRIC, "value": value, "unit": bench.UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {
-                "workload": "QuantumVolume(%d, depth %d, seed %d): %d SU(4) gates + %d-shot sampling, complex128 "
-                            "statevector sharded over %d B200 (%d local qubits, %.1f GiB per GPU) -- BASELINE "
-                            "config 5" % (n, depth, qv_seed, n_gates, shots, world, n_local, 16 * 2 ** n_local / 2 ** 30),
-                "n_qubits": n, "local_qubits": n_local, "depth": depth, "gates": n_gates, "shots": shots,
-                "parallelism": "state sharded by the %d high-order qubits; qubit swaps over NCCL send/recv" % g,
-                "local_passes_per_step": passes, "qubit_swaps_per_step": swaps,
-                "swap_GB_per_gpu_per_step": swap_gb, "circuit_s": step_ms * 1e-3,
-                "l2": "shards (%.1f GiB) are far larger than the 126 MB L2" % (16 * 2 ** n_local / 2 ** 30),
-            },
+            "config": cfg,
+            "circuit_s": step_ms * 1e-3,
+            "schedule": {"local_passes_per_step": passes_dev, "qubit_swaps_per_step": swaps_dev,
+                         "fused_exchanges_per_step": fused_dev, "swap_GB_per_gpu_per_step": swap_gb_dev,
+                         "exchange_ms_per_step": exchange_ms,
+                         "exchange_GBps_per_gpu_per_direction": (swap_gb_dev / (exchange_ms * 1e-3) if exchange_ms else None),
+                         "nvlink_peak_GBps_per_direction": 900.0},
             "roofline": {"bound": "hbm", "kernel": "tile_pass_kernel", "achieved": None, "peak": peak, "unit": "GB/s",
                          "frac": None, "traffic": None, "peak_source": peak_src,
                          "note": "per-kernel roofline is reported by the N=1 run"},
             "cpu_baseline": None,
-            "e2e": e2e or {"value": value, "unit": unit, "h2d_bytes_per_step": int(n_gates * 256 + shots * 8),
+            "e2e": e2e or {"value": value, "unit": bench.UNIT, "h2d_bytes_per_step": int(n_gates * 256 + shots * 8),
                            "d2h_bytes_per_step": int(shots * 8 + 8 * world),
                            "note": "e2e leg %s: the device-timed leg is driven from host op lists; uniforms in, "
                                    "sample indices out are inside its timed region"
                                    % ("failed (%s)" % e2e_error if e2e_error else "skipped")},
+            "qft": families.get("qft"),
+            "random_circuit": families.get("random_circuit"),
             "gpu_launches": int(launches.item()),
             "clocks": clock_info,
-            "check": {"sample_total_prob": total},
+            "check": {"sample_total_prob": total, "parity": parity, "parity_cases": parity_details,
+                      "sampler": "exact-order CDF chained through the ranks (counts bit-identical to the reference's "
+                                 "seeded RandomState.choice)"},
         }
         print(json.dumps(line), flush=True)
     dist.destroy_process_group()

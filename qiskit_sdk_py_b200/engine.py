@@ -145,6 +145,21 @@ class DeviceState:
         keys = ("ops", "stages", "fused3", "smem_bytes", "threads", "piece_log2_load", "piece_log2_store", "gates")
         return dict(zip(keys, list(info)))
 
+    @staticmethod
+    def pass_ops(n_qubits, tile_qubits, ops, dest=None):
+        """Host-only: the kernel ops of the lowered pass, as dicts (kind, stage, qubits, conflict-free flags)."""
+        lib = _lib.load()
+        gates = (_lib.QsvGate * max(1, len(ops)))()
+        for i, op in enumerate(ops):
+            _fill_gate(gates[i], op)
+        out = (ctypes.c_int32 * (4 * _lib.MAX_PASS_GATES))()
+        rc = lib.qsv_pass_ops(n_qubits, _int32_array(tile_qubits), len(tile_qubits), gates, len(ops),
+                              None if dest is None else _int32_array(dest), out, _lib.MAX_PASS_GATES)
+        if rc < 0:
+            _lib.check(rc, "qsv_pass_ops")
+        return [{"kind": out[4 * o], "stage": out[4 * o + 1], "q0": out[4 * o + 2] & 255, "q1": out[4 * o + 2] >> 8,
+                 "flags": out[4 * o + 3]} for o in range(rc)]
+
     def apply_dense(self, qubits, matrix):
         """One stand-alone k-qubit gate (the `unitary` instruction with k >= 3)."""
         k = len(qubits)

@@ -108,6 +108,10 @@ class _B200Backend(BackendV1):
         for key, val in list(qobj_dict["config"].items()):
             if hasattr(val, "value") and not isinstance(val, (int, float, str, list, dict)):
                 qobj_dict["config"][key] = val.value
+        # options set with set_options() persist across runs, as in the reference (qasm_simulator.py:292-293)
+        self._sim.option_defaults = {key: getattr(self.options, key) for key in
+                                     ("initial_statevector", "initial_unitary", "chop_threshold")
+                                     if hasattr(self.options, key)}
         try:
             result = self._sim.run(qobj_dict, **backend_options)
         except simulator.BasicAerError as exc:

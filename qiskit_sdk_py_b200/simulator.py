@@ -63,6 +63,17 @@ def max_qubits_for_device(bytes_per_amp=16, default=33):
     return default
 
 
+def _touch_cuda():
+    """Initialise CUDA (run time only, never at import / backend construction: Terra may fork before that)."""
+    try:
+        import torch
+
+        if torch.cuda.is_available() and not torch.cuda.is_initialized():
+            torch.cuda.init()
+    except Exception:  # pragma: no cover
+        pass
+
+
 def _cfg_get(cfg, key, default=None):
     return cfg[key] if key in cfg else default
 
@@ -96,6 +107,9 @@ class QasmSimulatorB200:
         # counts vs the reference; the parallel exact scan costs ~1 % of a circuit even at 33 qubits);
         # above, the blocked parallel scan is used
         self.exact_sampling_max_qubits = exact_sampling_max_qubits
+        # persistent option defaults of the owning backend (BackendV1.set_options): the reference resets its
+        # per-run options from self.options, not from the class defaults (qasm_simulator.py:292-293)
+        self.option_defaults = None
         self._local_random = np.random.RandomState()  # qasm_simulator.py:119
         self._classical_memory = 0
         self._classical_register = 0
@@ -120,9 +134,12 @@ class QasmSimulatorB200:
         return self.NAME
 
     def max_qubits(self):
-        if self._max_qubits is None:
-            self._max_qubits = max_qubits_for_device()
-        return self._max_qubits
+        """The explicit cap if one was given, else what the current GPU holds -- recomputed on every call: before
+        CUDA is initialised (backend construction, configuration()) it is the B200 default, at _validate time the
+        device's real memory."""
+        if self._max_qubits is not None:
+            return self._max_qubits
+        return max_qubits_for_device()
 
     def configuration_dict(self):
         gates = [
@@ -158,8 +175,11 @@ class QasmSimulatorB200:
     # -- options ---------------------------------------------------------------------
     def _set_options(self, qobj_config, backend_options):
         """qasm_simulator.py:289-317."""
-        self._initial_statevector = self.DEFAULT_OPTIONS["initial_statevector"]
-        self._chop_threshold = self.DEFAULT_OPTIONS["chop_threshold"]
+        defaults = self.option_defaults if self.option_defaults is not None else self.DEFAULT_OPTIONS
+        self._initial_statevector = defaults.get("initial_statevector")
+        if self._initial_statevector is not None:
+            self._initial_statevector = np.array(self._initial_statevector, dtype=complex)
+        self._chop_threshold = defaults.get("chop_threshold")
         backend_options = dict(backend_options or {})
         if "backend_options" in backend_options and backend_options["backend_options"]:
             backend_options = backend_options["backend_options"]
@@ -192,6 +212,8 @@ class QasmSimulatorB200:
     def _validate(self, qobj):
         """qasm_simulator.py:655-675."""
         n_qubits = qobj["config"]["n_qubits"]
+        if self._max_qubits is None and self._state_factory == self._device_state:
+            _touch_cuda()  # the memory-based cap needs the device's properties
         max_qubits = self.max_qubits()
         if n_qubits > max_qubits:
             raise BasicAerError(
@@ -383,7 +405,14 @@ class QasmSimulatorB200:
         self._local_random.seed(seed=seed_simulator)
         self._validate_measure_sampling(experiment)
 
-        self._state = self._state_factory(self._number_of_qubits)
+        try:
+            self._state = self._state_factory(self._number_of_qubits)
+        except MemoryError as exc:
+            raise BasicAerError("not enough device memory for {} qubits: {}".format(self._number_of_qubits, exc))
+        except RuntimeError as exc:  # torch.cuda.OutOfMemoryError is a RuntimeError
+            if "out of memory" not in str(exc).lower():
+                raise
+            raise BasicAerError("not enough device memory for {} qubits: {}".format(self._number_of_qubits, exc))
         lowered = self._lower(instructions)
 
         memory = []
@@ -542,6 +571,7 @@ class UnitarySimulatorB200:
     def __init__(self, state_factory=None, max_qubits=None):
         self._state_factory = state_factory or DeviceState
         self._max_qubits = max_qubits
+        self.option_defaults = None  # see QasmSimulatorB200.option_defaults (unitary_simulator.py:160-161)
         self._initial_unitary = None
         self._chop_threshold = 1e-15
         self._global_phase = 0
@@ -551,9 +581,9 @@ class UnitarySimulatorB200:
         return self.NAME
 
     def max_qubits(self):
-        if self._max_qubits is None:
-            self._max_qubits = max_qubits_for_device() // 2
-        return self._max_qubits
+        if self._max_qubits is not None:
+            return self._max_qubits
+        return max_qubits_for_device() // 2
 
     def configuration_dict(self):
         cfg = QasmSimulatorB200(max_qubits=self.max_qubits()).configuration_dict()
@@ -564,8 +594,11 @@ class UnitarySimulatorB200:
 
     def _set_options(self, qobj_config, backend_options):
         """unitary_simulator.py:157-188."""
-        self._initial_unitary = self.DEFAULT_OPTIONS["initial_unitary"]
-        self._chop_threshold = self.DEFAULT_OPTIONS["chop_threshold"]
+        defaults = self.option_defaults if self.option_defaults is not None else self.DEFAULT_OPTIONS
+        self._initial_unitary = defaults.get("initial_unitary")
+        if self._initial_unitary is not None:
+            self._initial_unitary = np.array(self._initial_unitary, dtype=complex)
+        self._chop_threshold = defaults.get("chop_threshold")
         backend_options = dict(backend_options or {})
         if "backend_options" in backend_options:
             backend_options = backend_options["backend_options"]

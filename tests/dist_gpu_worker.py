@@ -60,6 +60,11 @@ def main():
         assert np.all(np.abs(hist[top] - p[top]) < 5 * np.sqrt(p[top] / 20000.0) + 1e-3)
         swaps = st.swaps
         full = st.gather_statevector()
+        # the sharded sampler is the reference's: searchsorted(cumsum(|psi|^2) / total, u, 'right') over the whole
+        # register, running sum chained through the ranks (qasm_simulator.py:213) -- bit for bit
+        cdf = (np.abs(full) ** 2).cumsum()
+        assert total == cdf[-1]
+        assert np.array_equal(samples, (cdf / cdf[-1]).searchsorted(u, side="right"))
         err = float(np.max(np.abs(full - ref)))
         assert err < 1e-12, err
         if rank == 0:
@@ -73,12 +78,19 @@ def main():
              "sampler_marginal_subset", "sampler_partial_qubit", "sv_global_phase", "sv_reset_midcircuit", "teleport",
              "transpiled_init_reset_cond_counts", "qv_8_state", "random_12_state", "qft_12_counts", "qv_11_counts",
              "unitary_random", "unitary_global_phase_x4", "random_6_unitary", "unitary_initial_unitary"]
+    names += ["midcircuit_8", "sv_midcircuit_10", "qv_16_counts", "random_14_counts"]
+    g = int(np.log2(world))
+    done = 0
     for name in names:
         case = golden_io.load_case(name)
+        nq = case["qobj"]["config"]["n_qubits"] * (2 if case["backend"] == "unitary_simulator" else 1)
+        if nq - g < 2:
+            continue
+        done += 1
         result = helpers.run_case_with(lambda backend: distributed_simulator(backend, chunk_amps=1 << 9), case)
         helpers.compare_result(result, case, amp_tol=1e-10)
     if rank == 0:
-        print("spmd ok: %d golden cases through distributed_simulator on %d ranks" % (len(names), world), flush=True)
+        print("spmd ok: %d golden cases through distributed_simulator on %d ranks" % (done, world), flush=True)
     dist.destroy_process_group()
 
 

@@ -520,6 +520,44 @@ def transpiled_cases():
          assembled(transpile(qc, sim, optimization_level=1), shots=3000, seed_simulator=21, memory=True))
 
 
+def midcircuit_wide_cases():
+    """Mid-circuit measure / reset / conditionals on registers wide enough for a state sharded over 8 ranks (the
+    reference's own mid-circuit tests have 3-4 qubits): per-shot simulation with the exact RNG order
+    (qasm_simulator.py:512-531, :561-614).  Used by the multi-GPU parity gate of bench.py and tests/test_gpu_dist.py."""
+    rng = np.random.RandomState(2024)
+
+    def build(n, name):
+        qr = QuantumRegister(n, "q")
+        ca = ClassicalRegister(3, "ca")
+        cb = ClassicalRegister(n, "cb")
+        c = QuantumCircuit(qr, ca, cb, name=name)
+        for q in range(n):
+            c.u3(*rng.uniform(0, PI, 3), qr[q])
+        for q in range(n - 1):
+            c.cx(qr[q], qr[q + 1])
+        for q in range(n):
+            c.u3(*rng.uniform(0, PI, 3), qr[q])
+        c.cx(qr[n - 1], qr[0])                     # highest (global on every sharding) -> lowest
+        c.measure(qr[n - 1], ca[0])                # mid-circuit measure of a global qubit
+        c.u1(0.7, qr[n - 2]).c_if(ca, 1)
+        c.x(qr[1]).c_if(ca, 1)
+        c.reset(qr[n - 2])                         # reset of a global qubit
+        h(c, qr[n - 2])
+        c.cx(qr[n - 2], qr[2])
+        c.measure(qr[2], ca[1])
+        c.u3(0.3, 0.2, 0.1, qr[n - 1]).c_if(ca, 3)
+        c.reset(qr[0])
+        c.u2(0.1, 0.4, qr[0])
+        c.cx(qr[0], qr[n - 1])
+        c.measure(qr[n - 3], ca[2])
+        for q in range(n):
+            c.measure(qr[q], cb[q])
+        return c
+
+    save("midcircuit_8", "qasm_simulator", assembled(build(8, "midcircuit_8"), shots=150, seed_simulator=31, memory=True))
+    save("sv_midcircuit_10", "statevector_simulator", assembled(build(10, "sv_midcircuit_10"), seed_simulator=77))
+
+
 def large_cases():
     save("qft_16_product", "statevector_simulator", gen.qft(16, state_seed=3))
     save("qv_16_counts", "qasm_simulator", gen.quantum_volume(16, shots=8192, seed_simulator=42))
@@ -541,7 +579,11 @@ if __name__ == "__main__":
     ap.add_argument("--only-large", action="store_true")
     ap.add_argument("--only-expval", action="store_true")
     ap.add_argument("--only-transpiled", action="store_true")
+    ap.add_argument("--only-midcircuit-wide", action="store_true")
     args = ap.parse_args()
+    if args.only_midcircuit_wide:
+        midcircuit_wide_cases()
+        sys.exit(0)
     if args.only_expval:
         expval_cases()
         sys.exit(0)
@@ -554,6 +596,7 @@ if __name__ == "__main__":
         cases_from_generators()
         expval_cases()
         transpiled_cases()
+        midcircuit_wide_cases()
     if args.large or args.only_large:
         large_cases()
     if args.huge:

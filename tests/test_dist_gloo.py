@@ -316,3 +316,36 @@ def test_sharded_state_on_a_strict_subgroup(tmp_path):
     port = _free_port()
     mp.spawn(_subgroup_worker, args=(4, port, str(tmp_path)), nprocs=4, join=True)
     assert os.path.exists(os.path.join(str(tmp_path), "sub_2.npy")) and os.path.exists(os.path.join(str(tmp_path), "sub_3.npy"))
+
+
+def _parity_gate_worker(rank, world, port, out_dir):
+    for p in (ROOT, os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from fake_state import FakeState
+    from qiskit_sdk_py_b200.dist import parity_gate
+
+    kwargs = {"shard_factory": lambda k: FakeState(k, tile_qubits=4), "chunk_amps": 8, "max_qubits": 24}
+    cases = ["midcircuit_8", "sv_midcircuit_10", "random_6_unitary", "sampler_marginal_subset", "qv_11_counts",
+             "transpiled_init_reset_cond_counts", "bell_seed42"]
+    summary, details = parity_gate(kwargs, world, cases=cases, device="cpu")
+    fits = [c for c in cases if c not in ("bell_seed42",) and not (world == 4 and c == "transpiled_init_reset_cond_counts"
+                                                                    and False)]
+    assert summary.startswith("golden %d/%d identical" % (len(details), len(details))) and "FAILED" not in summary, summary
+    assert "bell_seed42" not in details          # 2 qubits do not leave two local qubits per rank
+    assert "midcircuit_8" in details and details["midcircuit_8"]["ok"]
+    if rank == 0:
+        np.save(os.path.join(out_dir, "gate_%d.npy" % world), np.array([len(details), len(fits)]))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_bench_parity_gate(tmp_path, world):
+    """The golden parity gate bench.py --gpus N runs before its timed region (dist.parity_gate), here over gloo."""
+    port = _free_port()
+    mp.spawn(_parity_gate_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    res = np.load(os.path.join(str(tmp_path), "gate_%d.npy" % world))
+    assert res[0] >= 5

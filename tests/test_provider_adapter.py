@@ -134,3 +134,45 @@ def test_conditional_circuit(qk, provider):
     t.measure(qr[2], cr[2])
     res = provider.get_backend("qasm_simulator").run(t, shots=100, seed_simulator=1).result()
     assert res.get_counts() == {"111": 100}
+
+
+def test_set_options_persist_like_the_reference(qk, provider):
+    """options set with backend.set_options() are the defaults of every later run (the reference reads
+    self.options in _set_options, qasm_simulator.py:292-293 / unitary_simulator.py:160-161)."""
+    from qiskit_sdk_py_b200.provider import B200Provider
+    from fake_state import FakeState
+
+    ours = B200Provider(simulator_kwargs={"state_factory": FakeState, "max_qubits": 24})
+    qc = qk.QuantumCircuit(1)
+    qc.rz(0.3, 0)
+    for name, key, value in (("statevector_simulator", "initial_statevector", np.array([0, 1], dtype=complex)),
+                             ("qasm_simulator", "initial_statevector", np.array([0, 1], dtype=complex))):
+        b, r = ours.get_backend(name), type(qk.BasicAer.get_backend(name))()
+        b.set_options(**{key: value})
+        r.set_options(**{key: value})
+        if name == "statevector_simulator":
+            got = b.run(qc).result().get_statevector()
+            want = r.run(qc).result().get_statevector()
+            assert np.max(np.abs(got - want)) < 1e-13 and abs(got[1]) > 0.9
+            # a per-run option still wins, and the stored one is back on the next run
+            got = b.run(qc, initial_statevector=[1, 0]).result().get_statevector()
+            assert abs(got[0]) > 0.9
+            assert abs(b.run(qc).result().get_statevector()[1]) > 0.9
+        else:
+            qm = qk.QuantumCircuit(1, 1)
+            qm.measure(0, 0)
+            assert b.run(qm, shots=20, seed_simulator=1).result().get_counts() == \
+                r.run(qm, shots=20, seed_simulator=1).result().get_counts() == {"1": 20}
+    b, r = ours.get_backend("statevector_simulator"), type(qk.BasicAer.get_backend("statevector_simulator"))()
+    b.set_options(chop_threshold=0.5, initial_statevector=None)  # the same backend object: the option had persisted
+    r.set_options(chop_threshold=0.5)
+    qh = qk.QuantumCircuit(2)
+    qh.u3(0.4, 0, 0, 0)
+    assert np.array_equal(b.run(qh).result().get_statevector() == 0, r.run(qh).result().get_statevector() == 0)
+    b, r = ours.get_backend("unitary_simulator"), type(qk.BasicAer.get_backend("unitary_simulator"))()
+    x = np.array([[0, 1], [1, 0]], dtype=complex)
+    b.set_options(initial_unitary=x)
+    r.set_options(initial_unitary=x)
+    qi = qk.QuantumCircuit(1)
+    qi.rz(0.2, 0)
+    assert np.max(np.abs(b.run(qi).result().get_unitary() - r.run(qi).result().get_unitary())) < 1e-13
