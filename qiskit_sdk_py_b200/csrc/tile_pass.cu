@@ -121,8 +121,9 @@ struct __align__(4) PassStage {
   uint16_t ocol[4];       // cj[obit[j]]
 };
 
-constexpr int kMaxRuns = 4;      // diagonal runs of a pass that get a lookup table (4 KiB of shared memory each)
+constexpr int kMaxRuns = 8;      // diagonal runs of a pass that get a lookup table (2^nbits complex of shared memory each)
 constexpr int kRunBits = 8;      // ... over at most 8 tile bits
+constexpr int kMaxRunEntries = 512;  // all tables of a pass together: 8 KiB of shared memory
 
 // A run of consecutive diagonal gates of one stage, folded on the host into ONE table over the tile bits the
 // run touches: element li is multiplied by tab[x(li)], x = the run's bits of li gathered.  x is a sum of a
@@ -130,6 +131,7 @@ constexpr int kRunBits = 8;      // ... over at most 8 tile bits
 struct DiagRun {
   uint8_t first_op, n_ops, nbits, pad;
   uint16_t moff;                      // table (2^nbits complex) in PassDesc::mats
+  uint16_t toff;                      // ... and its offset (complex entries) in the shared-memory table area
   uint16_t xw[kWarps], xl[32], xit[8];
 };
 
@@ -156,6 +158,7 @@ struct PassDesc {
   int32_t n, b, nops, nstages;
   int32_t nfrag;        // B-fragment units (64 doubles) of all ops: 1 per 2-qubit gate, 4 per fused block
   int32_t nruns;        // tabulated diagonal runs
+  int32_t run_entries;  // their tables together (complex entries)
   uint32_t n_tiles;
   uint32_t flags;       // QSV_DEBUG_FLAGS (profiling experiments)
   uint32_t pb_ld;       // log2(amplitudes per bulk-load piece): contiguous low tile bits, at most 4 (256 B)
@@ -338,8 +341,8 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
   uint32_t (*st_it)[8] = reinterpret_cast<uint32_t (*)[8]>(st_lane + nst_all);           // [nstages][8]
   // tabulated diagonal runs: [nruns][256] complex (16-byte aligned), then [nruns][56] index parts
   const uintptr_t run_base = (reinterpret_cast<uintptr_t>(st_it + nst_all) + 15u) & ~(uintptr_t)15u;
-  double2 (*runtab)[1 << kRunBits] = reinterpret_cast<double2 (*)[1 << kRunBits]>(run_base);
-  uint16_t (*runix)[56] = reinterpret_cast<uint16_t (*)[56]>(runtab + d.nruns);
+  double2* runtab = reinterpret_cast<double2*>(run_base);  // the runs' tables back to back (DiagRun::toff)
+  uint16_t (*runix)[56] = reinterpret_cast<uint16_t (*)[56]>(runtab + d.run_entries);
   __shared__ double2 tail_f_all[kG][16][2];    // per tile: factor pair of every tile bit; [b] = scalar
   __shared__ double2 tail_tab_all[kG][2][64];  // per tile: the two tables of the diagonal tail
   double2 (*tail_f)[2] = tail_f_all[grp];
@@ -436,7 +439,7 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
   for (int idx = ctid; idx < d.nruns * (1 << kRunBits); idx += cthreads) {
     const int r = idx >> kRunBits, x = idx & ((1 << kRunBits) - 1);
     const DiagRun& run = d.runs[r];
-    if (x < (1 << run.nbits)) runtab[r][x] = make_double2(d.mats[run.moff + 2 * x], d.mats[run.moff + 2 * x + 1]);
+    if (x < (1 << run.nbits)) runtab[run.toff + x] = make_double2(d.mats[run.moff + 2 * x], d.mats[run.moff + 2 * x + 1]);
     if (x < 56) runix[r][x] = x < kWarps ? run.xw[x] : x < kWarps + 32 ? run.xl[x - kWarps] : run.xit[x - kWarps - 32];
   }
   for (int idx = ctid; d.tail.n && idx < 112; idx += cthreads) {
@@ -784,7 +787,7 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
           if (is_diag && rec.ngl) {
             // tabulated run: one table lookup and one complex multiply per element for the whole run
             const int r = rec.ngl - 1;
-            const double2* tab = runtab[r];
+            const double2* tab = runtab + d.runs[r].toff;
             const uint32_t x0 = (uint32_t)runix[r][wid] + (uint32_t)runix[r][kWarps + lane];
             for (uint32_t it = 0; it < 8u; it++) {
               if ((lane | (it << 5)) >= n_el) break;
@@ -1299,7 +1302,7 @@ static int lower_pass(PassDesc& d, PassPlan& plan, int n, const int32_t* tile_qu
     uint64_t adj[64] = {0};
     int deg[64] = {0};
     for (int i = 0; i < n_gates; i++) {
-      if (gates[i].kind != QSV_GATE_DENSE2) continue;
+      if (gates[i].kind != QSV_GATE_DENSE2 && gates[i].kind != QSV_GATE_CX) continue;
       const int a = gates[i].q0, c = gates[i].q1;
       if (a < 0 || a >= n || c < 0 || c >= n || a == c) continue;  // reported below
       if (!((adj[a] >> c) & 1ull)) { adj[a] |= 1ull << c; adj[c] |= 1ull << a; deg[a]++; deg[c]++; }
@@ -1393,6 +1396,7 @@ static int lower_pass(PassDesc& d, PassPlan& plan, int n, const int32_t* tile_qu
       return fail(QSV_EINVAL, "qsv_apply_pass: gate qubit q0 is not a tile qubit");
     if (nq == 2 && (gsrc.q1 < 0 || gsrc.q1 >= n || local_of[gsrc.q1] < 0 || gsrc.q1 == gsrc.q0))
       return fail(QSV_EINVAL, "qsv_apply_pass: gate qubit q1 is not a tile qubit / equals q0");
+    if (gsrc.kind == QSV_GATE_CX && b >= 2) ndbl = 32;  // runs as a dense permutation on the tensor path (see below)
     if (moff + ndbl > kMaxIn) return fail(QSV_ERANGE, "qsv_apply_pass: matrix payload too large");
     op.kind = gsrc.kind;
     op.t0 = local_of[gsrc.q0];
@@ -1406,7 +1410,14 @@ static int lower_pass(PassDesc& d, PassPlan& plan, int n, const int32_t* tile_qu
       case QSV_GATE_CX: op.need = 1u << op.t1; break;  // target; the control may be any tile bit
       default: op.need = 0; break;                      // diagonal gates need no particular partition
     }
-    if (gsrc.kind == QSV_GATE_DENSE1 && b >= 2) {
+    if (gsrc.kind == QSV_GATE_CX && b >= 2) {
+      // A lone CX as an element-wise conditional swap diverges (half of the lanes idle) and cost more than a dense
+      // gate; as the 0/1 permutation matrix of basicaertools.py:70-72 it takes the DMMA path -- every product is
+      // exact, so the result is the same bits -- and it fuses into 3-qubit blocks like any other gate.
+      op_as_dense(QSV_GATE_CX, nullptr, mats_in + moff);
+      op.kind = QSV_GATE_DENSE2;
+      op.need = op.touch;
+    } else if (gsrc.kind == QSV_GATE_DENSE1 && b >= 2) {
       memset(mats_in + moff, 0, sizeof(double) * 32);  // widened once the partner bit is known
       memcpy(mats_in + moff, gsrc.m, sizeof(double) * 8);
     } else {
@@ -1678,7 +1689,7 @@ static int lower_pass(PassDesc& d, PassPlan& plan, int n, const int32_t* tile_qu
       while (k2 < k_end && is_diag(k2) && popc(bits | sops[k2].touch) <= kRunBits) bits |= sops[k2++].touch;
       const int n_run = k2 - k, nb = popc(bits);
       // a table costs about as much as two gates of the plain path
-      if (n_run >= 3 && d.nruns < kMaxRuns && moff + (2 << nb) <= kMaxMat) {
+      if (n_run >= 2 && d.nruns < kMaxRuns && moff + (2 << nb) <= kMaxMat && d.run_entries + (1 << nb) <= kMaxRunEntries) {
         DiagRun& run = d.runs[d.nruns];
         int ub[kRunBits], nu = 0;
         for (int j = 0; j < b; j++)
@@ -1692,6 +1703,8 @@ static int lower_pass(PassDesc& d, PassPlan& plan, int n, const int32_t* tile_qu
         run.n_ops = (uint8_t)n_run;
         run.nbits = (uint8_t)nb;
         run.moff = (uint16_t)moff;
+        run.toff = (uint16_t)d.run_entries;
+        d.run_entries += 1 << nb;
         for (uint32_t x = 0; x < (1u << nb); x++) {
           uint32_t li = 0;
           for (int j = 0; j < nu; j++) li |= ((x >> j) & 1u) << ub[j];
@@ -1844,7 +1857,7 @@ static int lower_pass(PassDesc& d, PassPlan& plan, int n, const int32_t* tile_qu
   for (int j = 4; j < b; j++) tile_slots += pad_of_bit(j);
   const size_t smem = tile_slots * sizeof(double2) + (size_t)nfrag * 64 * sizeof(double) +
                       (size_t)n_gates * (sizeof(OpRec) + 32 * 4) + (size_t)n_stages * ((kWarps + 32 + 8) * 4) + 16 +
-                      (size_t)d.nruns * ((sizeof(double2) << kRunBits) + 56 * sizeof(uint16_t));
+                      (size_t)d.run_entries * sizeof(double2) + (size_t)d.nruns * 56 * sizeof(uint16_t);
   d.n_tiles = 1u << (n - b);
   // one warp per 2^8 amplitudes: 512 threads for b = 12, 256 for b = 11, ...; at least one warp
   plan.smem = smem;

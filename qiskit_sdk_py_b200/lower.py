@@ -25,8 +25,9 @@ class GateOp:
 
     @property
     def payload_doubles(self):
-        return {_lib.GATE_DENSE1: 8, _lib.GATE_DENSE2: 32, _lib.GATE_DIAG1: 4, _lib.GATE_DIAG2: 8,
-                _lib.GATE_CX: 0}.get(self.kind, 0)
+        # doubles of matrix payload inside a pass (a cx runs as its 4x4 permutation matrix on the tensor path)
+        return {_lib.GATE_DENSE1: 32, _lib.GATE_DENSE2: 32, _lib.GATE_DIAG1: 4, _lib.GATE_DIAG2: 8,
+                _lib.GATE_CX: 32}.get(self.kind, 0)
 
     def __repr__(self):
         return "GateOp(%r, %r)" % (self.kind, self.qubits)

@@ -120,12 +120,77 @@ def merge_ops(ops):
     return merged
 
 
+_DIAG_KINDS = (_lib.GATE_DIAG1, _lib.GATE_DIAG2)
+
+
+def schedule_pass_ops(ops):
+    """Reorder the gates of ONE pass (all inside the tile) for the kernel's lowering, which fuses a dense 2-qubit
+    gate with the gates that FOLLOW it inside (at most) three qubits into one 3-qubit block and folds CONSECUTIVE
+    diagonal gates into one table sweep.  List scheduling over the dependency DAG of the pass -- two gates depend on
+    each other iff they share a qubit and are not both diagonal (diagonal gates commute with each other):
+
+      * while a non-diagonal gate is ready, take the first one (program order) and let it pull in, one after the
+        other, every ready gate the block can absorb (a gate inside the block's qubits, or a 2-qubit gate that
+        extends a 2-qubit block to three qubits);
+      * when only diagonal gates are ready (the next dense gates wait for them), take ALL of them at once.
+
+    A QFT pass (Hadamard-merged dense gates separated by controlled-phase fans) goes from 6 dense ops + 5 diagonal
+    runs to 3 blocks + 2 runs; streams without diagonal gates keep the blocks that program order gives, or better.
+    The returned order is a topological order of that DAG, hence the same unitary."""
+    n = len(ops)
+    if n < 3:
+        return list(ops)
+    qsets = [frozenset(op.qubits) for op in ops]
+    diag = [op.kind in _DIAG_KINDS for op in ops]
+    succs = [[] for _ in range(n)]
+    indeg = [0] * n
+    for j in range(n):
+        for i in range(j):
+            if (qsets[i] & qsets[j]) and not (diag[i] and diag[j]):
+                succs[i].append(j)
+                indeg[j] += 1
+    ready = set(i for i in range(n) if indeg[i] == 0)
+    out = []
+
+    def emit(i):
+        ready.discard(i)
+        out.append(ops[i])
+        for j in succs[i]:
+            indeg[j] -= 1
+            if indeg[j] == 0:
+                ready.add(j)
+
+    while ready:
+        dense_ready = [i for i in sorted(ready) if not diag[i]]
+        if not dense_ready:
+            for i in sorted(ready):
+                emit(i)
+            continue
+        seed = dense_ready[0]
+        emit(seed)
+        if ops[seed].kind != _lib.GATE_DENSE2:
+            continue
+        block = set(ops[seed].qubits)
+        while True:
+            pick = None
+            for j in sorted(ready):
+                if qsets[j] <= block or (len(block) == 2 and len(qsets[j]) == 2 and len(block | qsets[j]) == 3):
+                    pick = j
+                    break
+            if pick is None:
+                break
+            block |= qsets[pick]
+            emit(pick)
+    assert len(out) == n
+    return out
+
+
 def _relabel(op, layout):
     return GateOp(op.kind, [layout[q] for q in op.qubits], op.matrix)
 
 
 def plan_passes(ops, n_qubits, tile_qubits=DEFAULT_TILE_QUBITS, max_gates=_lib.MAX_PASS_GATES,
-                max_payload=_lib.MAX_PASS_MATRIX_DOUBLES, layout=None, remap=False, tails=False):
+                max_payload=_lib.MAX_PASS_MATRIX_DOUBLES, layout=None, remap=False, tails=False, schedule=True):
     """Group ``ops`` (GateOps on LOGICAL qubits, <= 2 qubits each) into passes.
 
     Frontier-greedy over the gate dependency DAG: a gate is *ready* when it is the first pending gate
@@ -243,6 +308,8 @@ def plan_passes(ops, n_qubits, tile_qubits=DEFAULT_TILE_QUBITS, max_gates=_lib.M
                 new_pos[qi], new_pos[qe] = layout[qe], layout[qi]
             if incoming:
                 dest = [new_pos[q] for q in tile_log]
+        if schedule:
+            chosen = schedule_pass_ops(chosen)
         passes.append(Pass(tile_phys, [_relabel(op, layout) for op in chosen], dest,
                            [_relabel(op, layout) for op in tail]))
         if dest is not None:

@@ -217,3 +217,66 @@ def test_merge_ops_turns_controlled_phase_into_one_diagonal_op():
     # untouched ops are passed through as the same objects
     lone = [lower.lower_gate("u3", [0], [0.1, 0.2, 0.3]), lower.lower_gate("cx", [1, 2], None)]
     assert merge_ops(lone)[0] is lone[0] and merge_ops(lone)[1] is lone[1]
+
+
+def test_schedule_pass_ops_preserves_the_unitary():
+    """planner.schedule_pass_ops only commutes gates on disjoint qubits or pairs of diagonal gates: the reordered
+    list is a permutation of the input and gives the same state (oracle einsum, qasm_simulator.py:145-161)."""
+    from oracle import basicaer_oracle as orc
+    from qiskit_sdk_py_b200 import _lib, planner
+    from qiskit_sdk_py_b200.lower import GateOp
+
+    rng = np.random.RandomState(12)
+
+    def ru(k):
+        q, r = np.linalg.qr(rng.standard_normal((2 ** k, 2 ** k)) + 1j * rng.standard_normal((2 ** k, 2 ** k)))
+        return q * (np.diag(r) / np.abs(np.diag(r)))
+
+    n = 7
+    for trial in range(30):
+        ops = []
+        for _ in range(int(rng.randint(3, 30))):
+            a, b = (int(x) for x in rng.choice(n, 2, replace=False))
+            pick = rng.randint(6)
+            if pick <= 1:
+                ops.append(GateOp(_lib.GATE_DENSE2, [a, b], ru(2)))
+            elif pick == 2:
+                ops.append(GateOp(_lib.GATE_DIAG2, [a, b], np.exp(1j * rng.uniform(0, 6, 4))))
+            elif pick == 3:
+                ops.append(GateOp(_lib.GATE_DIAG1, [a], np.exp(1j * rng.uniform(0, 6, 2))))
+            elif pick == 4:
+                ops.append(GateOp(_lib.GATE_DENSE1, [a], ru(1)))
+            else:
+                ops.append(GateOp(_lib.GATE_CX, [a, b], None))
+        out = planner.schedule_pass_ops(ops)
+        assert sorted(map(id, out)) == sorted(map(id, ops))
+        vec = rng.standard_normal(2 ** n) + 1j * rng.standard_normal(2 ** n)
+
+        def run(seq):
+            st = vec.reshape([2] * n)
+            for op in seq:
+                mat = np.diag(op.matrix) if op.kind in (_lib.GATE_DIAG1, _lib.GATE_DIAG2) else \
+                    orc.cx_gate_matrix() if op.kind == _lib.GATE_CX else op.matrix
+                st = orc.apply_unitary(st, mat, list(op.qubits))
+            return st.reshape(-1)
+
+        assert np.max(np.abs(run(out) - run(ops))) < 1e-12
+
+
+def test_schedule_turns_qft_fans_into_blocks_and_long_runs():
+    """QFT-33 through merge_ops + plan_passes: with the in-pass scheduler the Hadamard-merged dense gates pair up into
+    3-qubit blocks and the controlled-phase fans between them collapse into a few long diagonal runs."""
+    from qiskit_sdk_py_b200 import circuits, lower, planner
+    from qiskit_sdk_py_b200.engine import DeviceState
+
+    n = 33
+    ins = circuits.qft(n)["experiments"][0]["instructions"]
+    ops = [o for o in (lower.lower_gate(i["name"], i["qubits"], i.get("params")) for i in ins) if o is not None]
+    merged = planner.merge_ops(ops)
+    count = {}
+    for sched in (False, True):
+        passes = planner.plan_passes(merged, n, tails=True, schedule=sched)
+        kinds = [o["kind"] for p in passes for o in DeviceState.pass_ops(n, p.tile_qubits, p.ops)]
+        count[sched] = (len(passes), kinds.count(6), kinds.count(2))
+    assert count[True][0] == count[False][0] == 13
+    assert count[True][1] >= 2 * count[False][1] and count[True][2] <= count[False][2] // 2
