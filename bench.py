@@ -159,8 +159,9 @@ def workload_config(n, depth, tile, world=1, n_local=None):
         cfg["gates_per_pass"] = len(ins) / len(passes)
     else:
         cfg["local_qubits"] = n_local
-        cfg["parallelism"] = ("state sharded by the %d high-order qubits; qubit swaps = fused all-to-all exchanges over "
-                              "NCCL send/recv" % int(round(np.log2(world))))
+        cfg["parallelism"] = ("state sharded by the %d high-order qubits; qubit swaps = one in-place all-to-all kernel per "
+                              "rank over NVLink peer memory (CUDA IPC), NCCL only for barriers and scalar reductions"
+                              % int(round(np.log2(world))))
     return cfg
 
 

@@ -227,6 +227,23 @@ int qsv_pack_bits(const double* sv, int n_local, const int32_t* local_qubits, in
 int qsv_unpack_bits(double* sv, int n_local, const int32_t* local_qubits, int k, uint32_t pattern,
                     const double* dev_buf, size_t chunk_begin, size_t chunk_amps, void* stream);
 
+/* Qubit swap over NVLink peer memory, in place and without staging: the k global qubits whose
+ * values on this rank read `my_pattern` trade places with the local qubits local_qubits[0..k).  peer_sv[lam] is the
+ * shard of the rank whose k global bits read lam, mapped into this process with qsv_ipc_import (entry my_pattern is
+ * ignored).  ONE kernel per rank: for every peer it swaps, element by element, half of the pair's sub-block (the
+ * partner does the other half) -- remote load / remote store over NVLink, so every moved amplitude crosses the
+ * link once per direction and touches HBM once per side.  The caller must bracket the call with a stream-ordered
+ * barrier among the participating ranks.  max_ctas > 0 limits the grid (to leave SMs to a concurrent pass). */
+int qsv_swap_bits_p2p(double* sv, int n_local, const int32_t* local_qubits, int k, uint32_t my_pattern,
+                      double* const* peer_sv, int max_ctas, void* stream);
+
+/* CUDA IPC plumbing for the above (one process per GPU): export = 64-byte handle of the allocation that holds
+ * dev_ptr + dev_ptr's offset inside it; import maps a peer's allocation and returns the peer pointer; release
+ * unmaps it (before the owner frees the memory). */
+int qsv_ipc_export(const void* dev_ptr, void* handle_out, uint64_t* offset_out);
+int qsv_ipc_import(const void* handle, uint64_t offset, void** peer_ptr_out);
+int qsv_ipc_release(void* peer_ptr, uint64_t offset);
+
 /* dev_dst (2^log2_dst doubles) = 0 everywhere except dev_dst[base | sum_i bit_i(s) << dest_bit[i]] = dev_src[s]
  * for s in [0, 2^m): a shard's marginal over its local measured qubits lands in the bins of the full marginal that
  * its rank bits (base) select; the ranks' arrays are then all-reduced (qasm_simulator.py:202-209 across shards). */

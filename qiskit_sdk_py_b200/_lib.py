@@ -95,6 +95,11 @@ SIGNATURES = {
     "qsv_unpack_bits": (_c_int, [_c_void_p, _c_int, _p_int32, _c_int, ctypes.c_uint32, _c_void_p, _c_size_t,
                                  _c_size_t, _c_void_p]),
     "qsv_norm2": (_c_int, [_c_void_p, _c_int, _c_void_p, _p_double, _c_void_p]),
+    "qsv_swap_bits_p2p": (_c_int, [_c_void_p, _c_int, _p_int32, _c_int, ctypes.c_uint32, ctypes.POINTER(_c_void_p), _c_int,
+                                  _c_void_p]),
+    "qsv_ipc_export": (_c_int, [_c_void_p, _c_void_p, ctypes.POINTER(ctypes.c_uint64)]),
+    "qsv_ipc_import": (_c_int, [_c_void_p, ctypes.c_uint64, ctypes.POINTER(_c_void_p)]),
+    "qsv_ipc_release": (_c_int, [_c_void_p, ctypes.c_uint64]),
     "qsv_scatter_bits": (_c_int, [_c_void_p, _c_int, _p_int32, ctypes.c_uint64, _c_void_p, _c_int, _c_void_p]),
     "qsv_alloc": (_c_int, [ctypes.POINTER(_c_void_p), _c_size_t]),
     "qsv_free": (_c_int, [_c_void_p]),

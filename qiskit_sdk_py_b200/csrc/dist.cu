@@ -5,6 +5,9 @@
 // gather / scatter that half to and from a contiguous staging buffer; the transport itself is NCCL
 // send/recv issued by the Python host through torch.distributed.  (The reference has no multi-device
 // path at all: qasm_simulator.py keeps one numpy array in host memory.)
+#include <cuda.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace qsv {
@@ -79,6 +82,75 @@ scatter_bits_kernel(const double* __restrict__ src, const __grid_constant__ Scat
   }
 }
 
+// ---- qubit swap over NVLink peer memory, in place, no staging and no NCCL on the data path -----------------
+// Swapping k global qubits with the k local qubits `bits` is an all-to-all among the 2^k ranks that differ only
+// in those global bits: rank beta's sub-block [local bits = lam] trades places with rank lam's sub-block [local
+// bits = beta].  The peers' shards are mapped into this process (CUDA IPC, qsv_ipc_import), so ONE kernel per
+// rank does the whole exchange: for every peer lam it walks HALF of the pair's sub-block (the rank with the
+// smaller pattern takes the lower half of the compressed index range, its partner the upper half) and swaps
+// element by element -- remote load + local load, remote store + local store, 16 bytes each, coalesced in runs
+// of 2^(lowest swapped bit) amplitudes.  Every amplitude that has to move crosses NVLink exactly once in each
+// direction and HBM sees exactly one read and one write per moved amplitude on each side (the staged NCCL path
+// read and wrote every moved amplitude three times).  The caller brackets the kernel with a stream-ordered
+// barrier among the ranks (all passes before it are complete on every rank; all swaps are complete before the
+// next pass).
+struct P2PDesc {
+  int32_t k, n_local;
+  int32_t bits[8];        // ascending local bit positions
+  uint32_t beta;          // this rank's pattern of the k global bits
+  uint32_t perm[8];       // bit i of a pattern <-> position bits[perm[i]] ... (patterns are given in the caller's order)
+  double2* peer[256];     // peer[lam]: base of the shard of the rank whose global bits read lam (beta: unused)
+};
+
+__device__ __forceinline__ u64 p2p_deposit(const P2PDesc& d, uint32_t pattern) {
+  u64 v = 0;
+  for (int i = 0; i < d.k; i++) v |= (u64)((pattern >> i) & 1u) << d.bits[d.perm[i]];
+  return v;
+}
+
+__global__ void __launch_bounds__(1024)
+swap_p2p_kernel(double2* __restrict__ mine, const __grid_constant__ P2PDesc d) {
+  const u64 sub = 1ull << (d.n_local - d.k);  // amplitudes per sub-block
+  const u64 half = sub >> 1;
+  const u64 dep_beta = p2p_deposit(d, d.beta);
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  const u64 t0 = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  for (uint32_t lam = 0; lam < (1u << d.k); lam++) {
+    if (lam == d.beta) continue;
+    double2* __restrict__ theirs = d.peer[lam];
+    const u64 dep_lam = p2p_deposit(d, lam);
+    const u64 begin = d.beta < lam ? 0 : half;
+    constexpr int kU = 4;  // independent remote loads in flight per thread
+    for (u64 h0 = t0; h0 < half; h0 += stride * kU) {
+      double2 a[kU], b[kU];
+      u64 im[kU], ip[kU];
+#pragma unroll
+      for (int u = 0; u < kU; u++) {
+        const u64 h = h0 + (u64)u * stride;
+        u64 x = begin + (h < half ? h : 0);
+        for (int i = 0; i < d.k; i++) {
+          const int p = d.bits[i];
+          x = ((x >> p) << (p + 1)) | (x & ((1ull << p) - 1ull));
+        }
+        im[u] = x | dep_lam;   // my sub-block that leaves
+        ip[u] = x | dep_beta;  // the partner's sub-block that comes here
+        if (h < half) {
+          b[u] = __ldcv(theirs + ip[u]);
+          a[u] = mine[im[u]];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kU; u++) {
+        const u64 h = h0 + (u64)u * stride;
+        if (h < half) {
+          mine[im[u]] = b[u];
+          theirs[ip[u]] = a[u];
+        }
+      }
+    }
+  }
+}
+
 static int make_sub(int n_local, const int32_t* local_qubits, int k, uint32_t pattern, SubDesc* d) {
   if (k < 1 || k > 8 || k >= n_local || !local_qubits) return -1;
   int order[8];
@@ -129,6 +201,80 @@ int qsv_unpack_half(double* sv, int n_local, int L, int bitv, const double* dev_
   if (count == 0) return 0;
   unpack_half_kernel<<<grid_for(count), kThreads, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<double2*>(sv), L, (u64)bitv, reinterpret_cast<const double2*>(dev_buf), begin, count);
+  QSV_LAUNCHED();
+  return 0;
+}
+
+int qsv_ipc_export(const void* dev_ptr, void* handle_out, uint64_t* offset_out) {
+  if (!dev_ptr || !handle_out || !offset_out) return fail(QSV_EINVAL, "qsv_ipc_export: null pointer");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  // the handle names the whole allocation: find its base (the caller's pointer may sit inside a pooled block)
+  cudaPointerAttributes attr;
+  QSV_CUDA(cudaPointerGetAttributes(&attr, dev_ptr));
+  if (attr.type != cudaMemoryTypeDevice) return fail(QSV_EINVAL, "qsv_ipc_export: not a device pointer");
+  void* base = nullptr;
+  size_t size = 0;
+  // driver entry point fetched at run time: the library must load (host-only entry points, CPU tests) on machines
+  // without libcuda
+  typedef CUresult (*get_range_t)(CUdeviceptr*, size_t*, CUdeviceptr);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  QSV_CUDA(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qres));
+  if (!fn || qres != cudaDriverEntryPointSuccess) return fail(QSV_EINVAL, "qsv_ipc_export: cuMemGetAddressRange unavailable");
+  if (reinterpret_cast<get_range_t>(fn)(reinterpret_cast<CUdeviceptr*>(&base), &size, (CUdeviceptr)(uintptr_t)dev_ptr) !=
+      CUDA_SUCCESS)
+    return fail(QSV_EINVAL, "qsv_ipc_export: cuMemGetAddressRange failed");
+  QSV_CUDA(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(handle_out), base));
+  *offset_out = (uint64_t)((const char*)dev_ptr - (const char*)base);
+  return 0;
+}
+
+int qsv_ipc_import(const void* handle, uint64_t offset, void** peer_ptr_out) {
+  if (!handle || !peer_ptr_out) return fail(QSV_EINVAL, "qsv_ipc_import: null pointer");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  void* base = nullptr;
+  QSV_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+  *peer_ptr_out = (char*)base + offset;
+  return 0;
+}
+
+int qsv_ipc_release(void* peer_ptr, uint64_t offset) {
+  if (!peer_ptr) return 0;
+  QSV_CUDA(cudaIpcCloseMemHandle((char*)peer_ptr - offset));
+  return 0;
+}
+
+int qsv_swap_bits_p2p(double* sv, int n_local, const int32_t* local_qubits, int k, uint32_t my_pattern,
+                      double* const* peer_sv, int max_ctas, void* stream) {
+  if (!sv || !local_qubits || !peer_sv || k < 1 || k > 8 || k >= n_local || my_pattern >= (1u << k))
+    return fail(QSV_EINVAL, "qsv_swap_bits_p2p: bad arguments");
+  P2PDesc d;
+  memset(&d, 0, sizeof(d));
+  d.k = k;
+  d.n_local = n_local;
+  d.beta = my_pattern;
+  int order[8];
+  for (int i = 0; i < k; i++) order[i] = i;
+  for (int i = 0; i < k; i++)
+    for (int j = i + 1; j < k; j++)
+      if (local_qubits[order[j]] < local_qubits[order[i]]) { int t = order[i]; order[i] = order[j]; order[j] = t; }
+  for (int i = 0; i < k; i++) {
+    const int q = local_qubits[order[i]];
+    if (q < 0 || q >= n_local || (i > 0 && q == d.bits[i - 1])) return fail(QSV_EINVAL, "qsv_swap_bits_p2p: bad local qubits");
+    d.bits[i] = q;
+    d.perm[order[i]] = (uint32_t)i;  // pattern bit order[i] sits at the i-th smallest position
+  }
+  for (uint32_t lam = 0; lam < (1u << k); lam++) {
+    if (lam != my_pattern && !peer_sv[lam]) return fail(QSV_EINVAL, "qsv_swap_bits_p2p: null peer pointer");
+    d.peer[lam] = reinterpret_cast<double2*>(peer_sv[lam]);
+  }
+  const u64 half = (1ull << (n_local - k)) >> 1;
+  if (half == 0) return fail(QSV_ERANGE, "qsv_swap_bits_p2p: sub-block too small");
+  int ctas = max_ctas > 0 ? max_ctas : 2 * sm_count();
+  const u64 need = (half + 1023) / 1024;
+  if ((u64)ctas > need) ctas = (int)need;
+  swap_p2p_kernel<<<ctas, 1024, 0, (cudaStream_t)stream>>>(reinterpret_cast<double2*>(sv), d);
   QSV_LAUNCHED();
   return 0;
 }

@@ -28,7 +28,8 @@ from . import _lib
 from .lower import GateOp
 from .planner import DEFAULT_TILE_QUBITS as DEFAULT_TILE
 
-DEFAULT_CHUNK_AMPS = 1 << 26  # 1 GiB staging buffers
+DEFAULT_CHUNK_AMPS = 1 << 26  # 1 GiB staging buffers (torch.distributed transport of the CPU tests)
+_IPC_OPEN = {}                 # CUDA IPC handle -> [mapped base pointer, references]
 
 
 class ShardedState:
@@ -36,7 +37,7 @@ class ShardedState:
     double with the same interface) holding this rank's 2^(n - log2(world)) amplitudes."""
 
     def __init__(self, n_qubits, shard_factory, rank=None, world=None, chunk_amps=DEFAULT_CHUNK_AMPS,
-                 group=None):
+                 group=None, p2p=True):
         import torch
         import torch.distributed as dist
 
@@ -61,6 +62,12 @@ class ShardedState:
         self.fused_exchanges = 0
         self.swap_bytes = 0
         self._xch_events = []   # (start, end) CUDA events around every exchange (device shards only)
+        # NVLink peer memory: shards that can export a CUDA IPC handle (engine.DeviceState) are mapped into every
+        # rank of the group once, and the exchanges run as ONE in-place swap kernel per rank (qsv_swap_bits_p2p);
+        # the numpy test double of the CPU tests has no such handle and goes through torch.distributed send/recv
+        self._peers = None      # group rank -> (peer pointer, offset)
+        if p2p and hasattr(self.shard, "ipc_export"):
+            self._map_peers()
 
     # -- helpers -----------------------------------------------------------------------
     def _logical_at(self, phys):
@@ -103,6 +110,82 @@ class ShardedState:
         self.apply_ops([GateOp(_lib.GATE_DENSE1, [n_half + j], fan) for j in range(n_half)] +
                        [GateOp(_lib.GATE_CX, [n_half + j, j], None) for j in range(n_half)])
 
+    # -- NVLink peer mapping -------------------------------------------------------------------------
+    def _map_peers(self):
+        handle, offset = self.shard.ipc_export()
+        everyone = [None] * self.world
+        self._dist.all_gather_object(everyone, (handle, offset), group=self.group)
+        self._peers = {}
+        for r, (h, off) in enumerate(everyone):
+            if r == self.rank:
+                continue
+            # an allocation can be opened only once per process: successive states of a peer usually live in the same
+            # cached block, so the mapping is shared and reference-counted
+            entry = _IPC_OPEN.get(h)
+            if entry is None:
+                entry = _IPC_OPEN[h] = [self.shard.ipc_import(h, 0), 0]
+            entry[1] += 1
+            self._peers[r] = (entry[0] + off, h)
+
+    def _unmap_peers(self):
+        peers, self._peers = self._peers, None
+        for _ptr, h in (peers or {}).values():
+            entry = _IPC_OPEN.get(h)
+            if entry is None:
+                continue
+            entry[1] -= 1
+            if entry[1] <= 0:
+                del _IPC_OPEN[h]
+                self.shard.ipc_release(entry[0], 0)
+
+    def close(self):
+        """Unmap the peers' shards (collective: every rank calls it before any rank frees its shard)."""
+        if self._peers:
+            self._torch.cuda.synchronize()
+            self._unmap_peers()
+            self._dist.barrier(group=self.group)
+
+    def __del__(self):
+        try:
+            self._unmap_peers()
+        except Exception:  # interpreter shutdown
+            pass
+
+    def _stream_barrier(self):
+        """Stream-ordered barrier among the ranks: everything enqueued before it has completed on EVERY rank before
+        anything enqueued after it starts (a one-element all-reduce on the compute stream)."""
+        t = self._torch.zeros(1, dtype=self._torch.float32, device=self.shard.comm_device())
+        self._dist.all_reduce(t, group=self.group)
+
+    def _swap_p2p(self, pairs):
+        """The exchange as one in-place NVLink kernel per rank (see qsv_swap_bits_p2p)."""
+        t_begin = self._xch_begin()
+        k = len(pairs)
+        gbits = [pg - self.n_local for pg, _ in pairs]
+        lbits = [pl for _, pl in pairs]
+        beta = 0
+        for i, j in enumerate(gbits):
+            beta |= ((self.rank >> j) & 1) << i
+        ptrs = [None] * (1 << k)
+        for lam in range(1 << k):
+            if lam == beta:
+                continue
+            r = self.rank
+            for i, j in enumerate(gbits):
+                r = (r & ~(1 << j)) | (((lam >> i) & 1) << j)
+            ptrs[lam] = self._peers[r][0]
+        self._stream_barrier()
+        self.shard.swap_bits_p2p(lbits, beta, ptrs)
+        self._stream_barrier()
+        self._xch_end(t_begin)
+        for pg, pl in pairs:
+            qa, qb = self._logical_at(pg), self._logical_at(pl)
+            self.pos[qa], self.pos[qb] = pl, pg
+        self.swaps += k
+        if k > 1:
+            self.fused_exchanges += 1
+        self.swap_bytes += 16 * (1 << (self.n_local - k)) * ((1 << k) - 1)
+
     # -- exchange timing (bench.py: exchange vs pass time per step) -------------------------------
     def _xch_begin(self):
         if getattr(self.shard, "device", None) is None:
@@ -132,6 +215,8 @@ class ShardedState:
     # -- the exchange step -------------------------------------------------------------
     def swap_global_local(self, phys_global, phys_local):
         """Swap physical bits (global j, local L): exchange the half with bit L != my bit j."""
+        if self._peers is not None:
+            return self._swap_p2p([(phys_global, phys_local)])
         dist = self._dist
         t_begin = self._xch_begin()
         j = phys_global - self.n_local
@@ -177,6 +262,8 @@ class ShardedState:
         those global bits: ``pairs`` = [(phys_global, phys_local), ...].  Each rank keeps 1/2^k of its shard
         and exchanges the other sub-blocks, (1 - 2^-k) of the shard in total -- against k/2 of the shard for
         k successive pairwise swaps."""
+        if self._peers is not None:
+            return self._swap_p2p(pairs)
         if len(pairs) == 1:
             return self.swap_global_local(*pairs[0])
         dist = self._dist
@@ -806,6 +893,7 @@ def bench_main(args, bench):
         import copy
         import time
 
+        st.close()  # unmap the peers' shards before anybody frees one
         del st
         torch.cuda.empty_cache()
         try:

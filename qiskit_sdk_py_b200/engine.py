@@ -377,6 +377,35 @@ class DeviceState:
                                                 int(pattern), ctypes.c_void_p(buf.data_ptr()), int(begin), int(count),
                                                 self.stream), "qsv_unpack_bits")
 
+    # -- NVLink peer memory (dist.ShardedState): CUDA IPC handle of this state, peers' states, the in-place swap ----
+    def ipc_export(self):
+        """(64-byte handle, offset) that lets another process on this node map this state's amplitudes."""
+        handle = ctypes.create_string_buffer(64)
+        offset = ctypes.c_uint64(0)
+        with self._ctx():
+            _lib.check(self.lib.qsv_ipc_export(self.ptr, handle, ctypes.byref(offset)), "qsv_ipc_export")
+        return bytes(handle.raw), int(offset.value)
+
+    def ipc_import(self, handle, offset):
+        """Map a peer's state (from its ipc_export) into this process; returns the peer pointer (int)."""
+        out = ctypes.c_void_p()
+        with self._ctx():
+            _lib.check(self.lib.qsv_ipc_import(ctypes.c_char_p(handle), int(offset), ctypes.byref(out)), "qsv_ipc_import")
+        return int(out.value)
+
+    def ipc_release(self, peer_ptr, offset):
+        with self._ctx():
+            _lib.check(self.lib.qsv_ipc_release(ctypes.c_void_p(peer_ptr), int(offset)), "qsv_ipc_release")
+
+    def swap_bits_p2p(self, local_qubits, my_pattern, peer_ptrs, max_ctas=0):
+        """In-place exchange of this state's sub-blocks with the peers' over NVLink (qsv_swap_bits_p2p);
+        ``peer_ptrs[lam]`` = mapped state of the rank whose swapped global bits read ``lam`` (None for my own)."""
+        arr = (ctypes.c_void_p * len(peer_ptrs))(*[ctypes.c_void_p(p) if p else None for p in peer_ptrs])
+        with self._ctx():
+            _lib.check(self.lib.qsv_swap_bits_p2p(self.ptr, self.n, _int32_array(local_qubits), len(local_qubits),
+                                                  int(my_pattern), arr, int(max_ctas), self.stream),
+                       "qsv_swap_bits_p2p")
+
     def scatter_bits(self, src, dest_bits, base, log2_dst):
         """Device tensor of 2^log2_dst doubles, zero except dst[base | deposit(s, dest_bits)] = src[s]
         (qsv_scatter_bits; dist.ShardedState.marginal)."""
