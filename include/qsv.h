@@ -131,9 +131,11 @@ int qsv_pass_ops(int n_qubits, const int32_t* tile_qubits, int n_tile, const qsv
                  const int32_t* dest_qubits, int32_t* ops_out, int max_ops);
 
 /* psi <- (G on qubits) psi for a dense k-qubit matrix, k >= 1.  Replaces one _add_unitary call
- * (qasm_simulator.py:145-161; `unitary` instruction :543-546).  k <= 2 goes through qsv_apply_pass;
- * 3 <= k <= QSV_MAX_DENSE_K uses the staged dense kernel, which needs `dev_mat_scratch`, a device
- * buffer of at least 2*4^k doubles (the matrix is copied there). */
+ * (qasm_simulator.py:145-161; `unitary` instruction :543-546).  k <= 2 goes through qsv_apply_pass; k = 3 is one
+ * fused 3-qubit block of the pass kernel; 4 <= k <= 7 (states of at least 11 qubits) is a complex GEMM over the
+ * tile's groups on the FP64 tensor path (DMMA, 3-multiplication form); larger k and smaller states use a scalar
+ * staged kernel.  k >= 4 needs `dev_mat_scratch`, a device buffer of at least 4*4^k doubles (the matrix, re-arranged
+ * into tensor-core fragments, is copied there). */
 int qsv_apply_matrix(double* sv, int n_qubits, const int32_t* qubits, int k, const double* host_matrix,
                      double* dev_mat_scratch, void* stream);
 

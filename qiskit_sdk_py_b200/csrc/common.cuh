@@ -60,4 +60,10 @@ __device__ __forceinline__ void cfma(double2& acc, double2 a, double2 b) {
   acc.y = fma(a.y, b.x, acc.y);
 }
 
+// dense_k.cu: k-qubit dense gate (4 <= k <= 7, n >= 11) as a complex GEMM on the FP64 tensor path;
+// dev_scratch holds dense_k_scratch_doubles(k) doubles
+int launch_dense_k_dmma(double* sv, int n, const int32_t* qubits, int k, const double* host_matrix, double* dev_scratch,
+                        cudaStream_t s);
+size_t dense_k_scratch_doubles(int k);
+
 }  // namespace qsv

@@ -1263,7 +1263,8 @@ struct PassPlan {
 // every index table of the kernel into `d`.
 static int lower_pass(PassDesc& d, PassPlan& plan, int n, const int32_t* tile_qubits, int n_tile,
                       const qsv_gate_t* gates, int n_gates, const int32_t* dest_qubits,
-                      const qsv_gate_t* tail = nullptr, int n_tail = 0, double* tail_ent = nullptr) {
+                      const qsv_gate_t* tail = nullptr, int n_tail = 0, double* tail_ent = nullptr,
+                      const double* block8 = nullptr, const int32_t* block_qubits = nullptr) {
   if (n_tail < 0 || n_tail > kMaxTail) return fail(QSV_ERANGE, "qsv_apply_pass_tail: too many tail gates");
   if (n_tail > 0 && (!tail || !tail_ent)) return fail(QSV_EINVAL, "qsv_apply_pass_tail: null pointer");
   if (n < 1 || n > 40) return fail(QSV_EINVAL, "qsv_apply_pass: bad state / n_qubits");
@@ -1435,6 +1436,51 @@ static int lower_pass(PassDesc& d, PassPlan& plan, int n, const int32_t* tile_qu
     const bool fuse_on = !(d.flags & 8u) && b >= 3;
     bool used[kMaxOps] = {false};
     int n_out = 0, mo = 0;
+    // a finished 3-qubit block (`cur`: 8x8 complex, index bit k <-> tile bit ub[k]) -> kernel op + matrix in role order
+    auto emit_block = [&](const double* cur, const int* ub, uint32_t cur_touch, HostOp& out) {
+      // roles of the three bits: (t0, t1) should differ in bank class (see the slot layout)
+      int role[3] = {0, 1, 2};
+      bool found = false;
+      for (int a = 0; a < 3 && !found; a++)
+        for (int c = 0; c < 3 && !found; c++)
+          if (a != c && differ(bank_class(ub[a]), bank_class(ub[c]))) {
+            role[0] = a; role[1] = c; role[2] = 3 - a - c;
+            found = true;
+          }
+      double* m8 = mats + mo;
+      for (int r = 0; r < 8; r++)
+        for (int c = 0; c < 8; c++) {
+          int ro = 0, co = 0;  // index in the ub order
+          for (int k = 0; k < 3; k++) {
+            ro |= ((r >> k) & 1) << role[k];
+            co |= ((c >> k) & 1) << role[k];
+          }
+          m8[2 * (8 * r + c)] = cur[2 * (8 * ro + co)];
+          m8[2 * (8 * r + c) + 1] = cur[2 * (8 * ro + co) + 1];
+        }
+      out.kind = kGateDense3;
+      out.t0 = ub[role[0]];
+      out.t1 = ub[role[1]];
+      out.t2 = ub[role[2]];
+      out.touch = cur_touch;
+      out.need = cur_touch;
+      out.moff = mo;
+      out.foff = 0;
+      mo += 128;
+    };
+    if (block8) {  // a 3-qubit `unitary` given as such (qsv_apply_matrix, k = 3): it is the pass's first op
+      int ub[3];
+      uint32_t touch = 0;
+      for (int k = 0; k < 3; k++) {
+        if (block_qubits[k] < 0 || block_qubits[k] >= n || local_of[block_qubits[k]] < 0 ||
+            ((touch >> local_of[block_qubits[k]]) & 1u))
+          return fail(QSV_EINVAL, "qsv_apply_matrix: bad qubit list");
+        ub[k] = local_of[block_qubits[k]];
+        touch |= 1u << ub[k];
+      }
+      if (b < 3) return fail(QSV_ERANGE, "qsv_apply_matrix: a 3-qubit gate needs a tile of 3 qubits");
+      emit_block(block8, ub, touch, hops[n_out++]);
+    }
     for (int i = 0; i < n_in; i++) {
       if (used[i]) continue;
       used[i] = true;
@@ -1508,33 +1554,7 @@ static int lower_pass(PassDesc& d, PassPlan& plan, int n, const int32_t* tile_qu
         mo += 32;
         continue;
       }
-      // roles of the three bits: (t0, t1) should differ in bank class (see the slot layout)
-      int role[3] = {0, 1, 2};
-      bool found = false;
-      for (int a = 0; a < 3 && !found; a++)
-        for (int c = 0; c < 3 && !found; c++)
-          if (a != c && differ(bank_class(ub[a]), bank_class(ub[c]))) {
-            role[0] = a; role[1] = c; role[2] = 3 - a - c;
-            found = true;
-          }
-      double* m8 = mats + mo;
-      for (int r = 0; r < 8; r++)
-        for (int c = 0; c < 8; c++) {
-          int ro = 0, co = 0;  // index in the ub order
-          for (int k = 0; k < 3; k++) {
-            ro |= ((r >> k) & 1) << role[k];
-            co |= ((c >> k) & 1) << role[k];
-          }
-          m8[2 * (8 * r + c)] = cur[2 * (8 * ro + co)];
-          m8[2 * (8 * r + c) + 1] = cur[2 * (8 * ro + co) + 1];
-        }
-      out.kind = kGateDense3;
-      out.t0 = ub[role[0]];
-      out.t1 = ub[role[1]];
-      out.t2 = ub[role[2]];
-      out.touch = cur_touch;
-      out.need = cur_touch;
-      mo += 128;
+      emit_block(cur, ub, cur_touch, out);
     }
     n_gates = n_out;
     moff = mo;
@@ -1882,13 +1902,15 @@ static int lower_pass(PassDesc& d, PassPlan& plan, int n, const int32_t* tile_qu
 
 static int launch_pass(double* sv, int n, const int32_t* tile_qubits, int n_tile, const qsv_gate_t* gates,
                        int n_gates, cudaStream_t stream, const int32_t* dest_qubits = nullptr,
-                       const qsv_gate_t* tail = nullptr, int n_tail = 0, void* dev_scratch = nullptr) {
+                       const qsv_gate_t* tail = nullptr, int n_tail = 0, void* dev_scratch = nullptr,
+                       const double* block8 = nullptr, const int32_t* block_qubits = nullptr) {
   if (!sv) return fail(QSV_EINVAL, "qsv_apply_pass: bad state / n_qubits");
   if (n_tail > 0 && !dev_scratch) return fail(QSV_EINVAL, "qsv_apply_pass_tail: null device scratch");
   static thread_local PassDesc d;
   static thread_local double tail_ent[kMaxTail * 8];
   PassPlan plan;
-  if (int rc = lower_pass(d, plan, n, tile_qubits, n_tile, gates, n_gates, dest_qubits, tail, n_tail, tail_ent))
+  if (int rc = lower_pass(d, plan, n, tile_qubits, n_tile, gates, n_gates, dest_qubits, tail, n_tail, tail_ent, block8,
+                          block_qubits))
     return rc;
   if (int rc = ensure_attrs()) return rc;
   if (n_tail > 0)  // small pageable copy: staged by the driver before the call returns, ordered on the stream
@@ -2122,7 +2144,17 @@ int qsv_apply_matrix(double* sv, int n, const int32_t* qubits, int k, const doub
     return launch_pass(sv, n, tile, nt, &g, 1, s);
   }
   if (k > QSV_MAX_DENSE_K) return fail(QSV_ERANGE, "qsv_apply_matrix: k > 12 is not supported");
-  if (!dev_mat_scratch) return fail(QSV_EINVAL, "qsv_apply_matrix: k >= 3 needs dev_mat_scratch");
+  if (k == 3) {
+    // one fused 3-qubit block of the pass kernel (8x8 complex in the 3-multiplication DMMA form): the path that
+    // pairs of 2-qubit gates take, here with the caller's matrix
+    const int nt = default_tile(n, qubits, k, std::min(n, 11), tile);
+    if (nt < 0) return fail(QSV_EINVAL, "qsv_apply_matrix: bad qubit list");
+    return launch_pass(sv, n, tile, nt, nullptr, 0, s, nullptr, nullptr, 0, nullptr, host_matrix, qubits);
+  }
+  if (!dev_mat_scratch) return fail(QSV_EINVAL, "qsv_apply_matrix: k >= 4 needs dev_mat_scratch");
+  if (k <= 7 && n >= 11)  // complex GEMM over the tile's groups on the FP64 tensor path (dense_k.cu)
+    return launch_dense_k_dmma(sv, n, qubits, k, host_matrix, dev_mat_scratch, s);
+  // states smaller than one tile, and k >= 8 (the 2^k x 2^k matrix no longer fits beside the tile): scalar kernel
   const int want = std::min(n, std::min(12, std::max(k + 3, 10)));
   const int nt = default_tile(n, qubits, k, std::max(want, k), tile);
   if (nt < 0) return fail(QSV_EINVAL, "qsv_apply_matrix: bad qubit list");

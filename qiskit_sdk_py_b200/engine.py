@@ -167,15 +167,15 @@ class DeviceState:
         if k > _lib.MAX_DENSE_K:
             raise _lib.QsvLibraryError("unitary on %d qubits: more than %d qubits is not supported"
                                        % (k, _lib.MAX_DENSE_K))
-        need = 2 * 4 ** k
-        if k >= 3 and (self._mat_scratch is None or self._mat_scratch.numel() < need):
+        need = 4 * 4 ** k
+        if k >= 4 and (self._mat_scratch is None or self._mat_scratch.numel() < need):
             self._mat_scratch = self._torch.empty(need, dtype=self._torch.float64, device=self.device)
-        scratch = ctypes.c_void_p(self._mat_scratch.data_ptr()) if k >= 3 else ctypes.c_void_p(0)
+        scratch = ctypes.c_void_p(self._mat_scratch.data_ptr()) if k >= 4 else ctypes.c_void_p(0)
         with self._ctx():
             _lib.check(self.lib.qsv_apply_matrix(self.ptr, self.n, _int32_array(qubits), k,
                                                  ctypes.c_void_p(mat.ctypes.data), scratch, self.stream),
                        "qsv_apply_matrix")
-            if k >= 3:
+            if k >= 4:
                 self.synchronize()  # the pageable host matrix was staged by the async copy; be safe
         self.passes_launched += 1
         self.gates_applied += 1

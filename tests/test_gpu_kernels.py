@@ -288,9 +288,11 @@ def test_qft_through_planner_tails(n):
     assert np.max(np.abs(st.download() - ref)) < 1e-11
 
 
-@pytest.mark.parametrize("n,k", [(3, 3), (5, 3), (9, 4), (12, 5), (13, 6), (14, 7), (9, 9), (15, 3)])
+@pytest.mark.parametrize("n,k", [(3, 3), (5, 3), (9, 4), (12, 5), (13, 6), (14, 7), (9, 9), (15, 3), (11, 4), (16, 4),
+                                 (20, 5), (18, 6), (17, 7), (22, 3), (12, 8)])
 def test_dense_k(n, k):
-    """k-qubit `unitary` instructions, k >= 3 (qasm_simulator.py:543-546)."""
+    """k-qubit `unitary` instructions, k >= 3 (qasm_simulator.py:543-546): k = 3 is one fused block of the pass
+    kernel, 4 <= k <= 7 at n >= 11 the DMMA complex-GEMM kernel (dense_k.cu), the rest the scalar staged kernel."""
     rng = np.random.RandomState(n * 31 + k)
     vec = rand_state(n, n + k)
     st = make_state(n, vec)
@@ -626,3 +628,18 @@ def test_scatter_bits_and_device_memory_helpers():
     st.apply_ops([GateOp(_lib.GATE_DENSE1, [3], rand_unitary(1, rng))])
     st.restore(snap)
     assert np.array_equal(st.download(), before)
+
+
+def test_dense_k_low_and_high_qubits():
+    """The DMMA dense-k kernel with gate qubits among the lowest bits (they are tile bits either way), among the
+    highest, and in descending order (matrix index bit j <-> qubits[j])."""
+    n = 19
+    rng = np.random.RandomState(77)
+    vec = rand_state(n, 5)
+    st = make_state(n, vec)
+    ref = vec.copy()
+    for qubits in ([0, 1, 2, 3], [18, 17, 16, 15, 14], [3, 18, 0, 9, 1, 12], [5, 4, 3, 2, 1, 0, 6], [2, 10, 18]):
+        mat = rand_unitary(len(qubits), rng)
+        st.apply_ops([lower.matrix_op(mat, qubits)])
+        ref = orc.apply_unitary(ref.reshape([2] * n), mat, qubits).reshape(-1)
+    assert np.max(np.abs(st.download() - ref)) < TOL
