@@ -96,11 +96,14 @@ class QasmSimulatorB200:
     }  # qasm_simulator.py:133-143
 
     def __init__(self, state_factory=None, max_qubits=None, exact_sampling_max_qubits=40,
-                 tile_qubits=None, seed_sync=None):
+                 tile_qubits=None, seed_sync=None, statevector_on_device=False):
         self._state_factory = state_factory or self._device_state
         # multi-process (sharded) runs: every rank executes the same run(qobj); a seed the backend draws itself
         # (qasm_simulator.py:499-502) must then be the same on all ranks -- seed_sync(seed) -> rank 0's seed
         self._seed_sync = seed_sync
+        # statevector simulator: leave the final state in HBM and return a statevector.DeviceStatevector handle in
+        # data["statevector"] (expectation values / probabilities / sampling without the 2^n-amplitude D2H copy)
+        self._statevector_on_device = bool(statevector_on_device)
         self._max_qubits = max_qubits
         self._tile_qubits = tile_qubits
         # up to this many sampled qubits the CDF is accumulated in numpy's cumsum order (bit-exact
@@ -318,6 +321,10 @@ class QasmSimulatorB200:
     def _get_statevector(self):
         """qasm_simulator.py:330-334: chop on the device, then one D2H copy owned by the Result."""
         self._state.chop(self._chop_threshold)
+        if self._statevector_on_device:
+            from .statevector import DeviceStatevector
+
+            return DeviceStatevector(self._state)
         return self._state.download()
 
     # -- run -------------------------------------------------------------------------

@@ -643,3 +643,34 @@ def test_dense_k_low_and_high_qubits():
         st.apply_ops([lower.matrix_op(mat, qubits)])
         ref = orc.apply_unitary(ref.reshape([2] * n), mat, qubits).reshape(-1)
     assert np.max(np.abs(st.download() - ref)) < TOL
+
+
+def test_device_statevector_handle():
+    """the statevector simulator leaves the final state on the device and hands out a
+    Statevector-like handle; expectation values / probabilities / sampling run there (qsv_expval_pauli, qsv_marginal,
+    exact-order sampler), checked against the oracle on the downloaded amplitudes."""
+    import copy
+
+    from qiskit_sdk_py_b200 import circuits, simulator
+    from qiskit_sdk_py_b200.statevector import DeviceStatevector
+
+    n = 12
+    qobj = circuits.random_circuit(n, 8, 4, measure_final=False, shots=1)
+    res = simulator.StatevectorSimulatorB200(statevector_on_device=True).run(copy.deepcopy(qobj))
+    sv = res["results"][0]["data"]["statevector"]
+    assert isinstance(sv, DeviceStatevector) and sv.num_qubits == n
+    ref = orc.OracleQasmSimulator(show_final_state=True).run(copy.deepcopy(qobj))["results"][0]["data"]["statevector"]
+    assert np.max(np.abs(sv.to_numpy() - ref)) < TOL
+    rng = np.random.RandomState(0)
+    for label in ["Z" * n, "X" + "I" * (n - 1)] + ["".join(rng.choice(list("IXYZ"), n)) for _ in range(6)]:
+        assert abs(sv.expectation_value(label) - orc.expval_pauli(ref, label)) < 1e-12
+    p = np.abs(ref) ** 2
+    got = sv.probabilities([7, 2, 9])
+    want = np.zeros(8)
+    for i in range(1 << n):
+        want[((i >> 7) & 1) | (((i >> 2) & 1) << 1) | (((i >> 9) & 1) << 2)] += p[i]
+    assert np.max(np.abs(got - want)) < 1e-12
+    own = np.abs(sv.to_numpy()) ** 2
+    cdf = own.cumsum()
+    exp = (cdf / cdf[-1]).searchsorted(np.random.RandomState(9).random_sample(300), side="right")
+    assert sv.sample_memory(300, seed=9) == [format(int(s), "0%db" % n) for s in exp]

@@ -280,3 +280,42 @@ def test_schedule_turns_qft_fans_into_blocks_and_long_runs():
         count[sched] = (len(passes), kinds.count(6), kinds.count(2))
     assert count[True][0] == count[False][0] == 13
     assert count[True][1] >= 2 * count[False][1] and count[True][2] <= count[False][2] // 2
+
+
+def test_device_statevector_handle_against_oracle():
+    """statevector.DeviceStatevector (here over the numpy test double): expectation values incl. qargs, linear
+    combinations and signed labels, probabilities in the caller's qubit order, seeded sampling -- against the oracle's
+    restatement of Statevector._expectation_value_pauli (statevector.py:377-408) and plain numpy."""
+    from fake_state import FakeState
+    from oracle import basicaer_oracle as orc
+    from qiskit_sdk_py_b200 import circuits
+    from qiskit_sdk_py_b200.statevector import DeviceStatevector
+
+    n = 6
+    ins = circuits.random_basis_instructions(n, 6, 5)
+    sv = DeviceStatevector.from_instructions(n, ins, state_factory=lambda k: FakeState(k, tile_qubits=4))
+    vec = sv.to_numpy()
+    assert sv.num_qubits == n and sv.dim == 64 and abs(sv.norm() - 1.0) < 1e-12
+    for label in ("ZIIXYZ", "XXXXXX", "IIIIIZ", "YIZIXI"):
+        assert abs(sv.expectation_value(label) - orc.expval_pauli(vec, label)) < 1e-12
+    assert abs(sv.expectation_value("-iZIIXYZ") + 1j * orc.expval_pauli(vec, "ZIIXYZ")) < 1e-12
+    # qargs: "XZ" on qubits [1, 4] = X on qubit 4, Z on qubit 1
+    assert abs(sv.expectation_value("XZ", qargs=[1, 4]) - orc.expval_pauli(vec, "IXIIZI")) < 1e-12
+    combo = [("ZIIIII", 0.5), ("IXIIII", -1.5j)]
+    want = 0.5 * orc.expval_pauli(vec, "ZIIIII") - 1.5j * orc.expval_pauli(vec, "IXIIII")
+    assert abs(sv.expectation_value(combo) - want) < 1e-12
+    p = np.abs(vec) ** 2
+    idx = np.arange(64)
+    got = sv.probabilities([4, 1])
+    want = np.zeros(4)
+    for i in range(64):
+        want[((i >> 4) & 1) | (((i >> 1) & 1) << 1)] += p[i]
+    assert np.max(np.abs(got - want)) < 1e-13
+    assert np.max(np.abs(sv.probabilities() - p)) < 1e-13
+    mem = sv.sample_memory(200, seed=3)
+    cdf = p.cumsum()
+    exp = (cdf / cdf[-1]).searchsorted(np.random.RandomState(3).random_sample(200), side="right")
+    assert mem == [format(int(s), "06b") for s in exp]
+    assert sum(sv.sample_counts(500, qargs=[0, 5], seed=1).values()) == 500
+    sv.evolve([circuits.u3(0.3, 0.2, 0.1, 2)])
+    assert abs(sv.norm() - 1.0) < 1e-12
