@@ -273,9 +273,9 @@ uint64_t qsv_launch_count(void);
 int qsv_debug_set_flags(uint32_t flags);
 
 /* Profiling aid (tools/ only; no reference counterpart): per-phase clock totals of the last warp-group pass,
- * [CTA][group][role][8] uint64 -- role 0/1 = compute warps 0 and 7 (0 wait for the tile, 1 gates, 2 loop
- * overhead), role 2 = the group's TMA producer warp (0 wait for the gates, 1 issue stores, 2 wait for the
- * stores to read the buffer, 3 issue loads).  Only the debug library (libqsv_dbg.so, -DQSV_PROFILE) records
+ * [CTA][group][role 0..8][20] uint64 -- roles 0..7 = the group's compute warps (0 wait for the tile, 1 gates, 2 loop
+ * overhead, 4 stage barriers, 5 + o = kernel op o), role 8 = the group's TMA producer warp (0 wait for the gates,
+ * 1 issue stores, 2 wait for the stores to read the buffer, 3 issue loads).  Only the debug library (libqsv_dbg.so, -DQSV_PROFILE) records
  * them; the production library returns QSV_ERANGE. */
 int qsv_debug_profile(uint64_t* host_out, size_t n_words);
 

@@ -108,6 +108,7 @@ __device__ __forceinline__ u64 p2p_deposit(const P2PDesc& d, uint32_t pattern) {
   return v;
 }
 
+template <int kU>  // independent remote loads in flight per thread
 __global__ void __launch_bounds__(1024)
 swap_p2p_kernel(double2* __restrict__ mine, const __grid_constant__ P2PDesc d) {
   const u64 sub = 1ull << (d.n_local - d.k);  // amplitudes per sub-block
@@ -117,10 +118,10 @@ swap_p2p_kernel(double2* __restrict__ mine, const __grid_constant__ P2PDesc d) {
   const u64 t0 = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   for (uint32_t lam = 0; lam < (1u << d.k); lam++) {
     if (lam == d.beta) continue;
+    if (!d.peer[lam]) continue;  // a partial exchange: only the peers given
     double2* __restrict__ theirs = d.peer[lam];
     const u64 dep_lam = p2p_deposit(d, lam);
     const u64 begin = d.beta < lam ? 0 : half;
-    constexpr int kU = 4;  // independent remote loads in flight per thread
     for (u64 h0 = t0; h0 < half; h0 += stride * kU) {
       double2 a[kU], b[kU];
       u64 im[kU], ip[kU];
@@ -150,6 +151,8 @@ swap_p2p_kernel(double2* __restrict__ mine, const __grid_constant__ P2PDesc d) {
     }
   }
 }
+
+int g_p2p_unroll = 4;  // tools/p2p_swap_probe.py sweeps it through qsv_debug_set_flags (bits 12-13)
 
 static int make_sub(int n_local, const int32_t* local_qubits, int k, uint32_t pattern, SubDesc* d) {
   if (k < 1 || k > 8 || k >= n_local || !local_qubits) return -1;
@@ -265,16 +268,19 @@ int qsv_swap_bits_p2p(double* sv, int n_local, const int32_t* local_qubits, int 
     d.bits[i] = q;
     d.perm[order[i]] = (uint32_t)i;  // pattern bit order[i] sits at the i-th smallest position
   }
-  for (uint32_t lam = 0; lam < (1u << k); lam++) {
-    if (lam != my_pattern && !peer_sv[lam]) return fail(QSV_EINVAL, "qsv_swap_bits_p2p: null peer pointer");
-    d.peer[lam] = reinterpret_cast<double2*>(peer_sv[lam]);
-  }
+  for (uint32_t lam = 0; lam < (1u << k); lam++)  // a null entry = that pair is not exchanged by this call
+    d.peer[lam] = lam == my_pattern ? nullptr : reinterpret_cast<double2*>(peer_sv[lam]);
   const u64 half = (1ull << (n_local - k)) >> 1;
   if (half == 0) return fail(QSV_ERANGE, "qsv_swap_bits_p2p: sub-block too small");
   int ctas = max_ctas > 0 ? max_ctas : 2 * sm_count();
   const u64 need = (half + 1023) / 1024;
   if ((u64)ctas > need) ctas = (int)need;
-  swap_p2p_kernel<<<ctas, 1024, 0, (cudaStream_t)stream>>>(reinterpret_cast<double2*>(sv), d);
+  switch (g_p2p_unroll) {
+    case 1: swap_p2p_kernel<1><<<ctas, 1024, 0, (cudaStream_t)stream>>>(reinterpret_cast<double2*>(sv), d); break;
+    case 2: swap_p2p_kernel<2><<<ctas, 1024, 0, (cudaStream_t)stream>>>(reinterpret_cast<double2*>(sv), d); break;
+    case 8: swap_p2p_kernel<8><<<ctas, 1024, 0, (cudaStream_t)stream>>>(reinterpret_cast<double2*>(sv), d); break;
+    default: swap_p2p_kernel<4><<<ctas, 1024, 0, (cudaStream_t)stream>>>(reinterpret_cast<double2*>(sv), d); break;
+  }
   QSV_LAUNCHED();
   return 0;
 }

@@ -79,15 +79,16 @@ static uint32_t debug_flags() {
 }
 
 #ifdef QSV_PROFILE
-// per (CTA, group, role) phase totals in clocks; role 0 = compute warp 0, 1 = compute warp 7, 2 = producer
+// per (CTA, group, role) phase totals in clocks; roles 0..7 = the group's compute warps, 8 = its producer warp
 constexpr int kProfSlots = 20;  // 0-3 phases; 4 stage-barrier waits; 5 + o: op o of the pass (o < 15)
-__device__ unsigned long long g_prof[160 * 3 * 3 * kProfSlots];
+constexpr int kProfRoles = 9;
+__device__ unsigned long long g_prof[160 * 3 * kProfRoles * kProfSlots];
 #define PROF_DECL unsigned long long prof_acc[kProfSlots] = {0}; long long prof_t0 = clock64();
 #define PROF_MARK(slot) do { const long long t1_ = clock64(); prof_acc[slot] += (unsigned long long)(t1_ - prof_t0); prof_t0 = t1_; } while (0)
 #define PROF_OP_BEGIN long long prof_t2 = clock64();
 #define PROF_OP_MARK(slot) do { const long long t3_ = clock64(); prof_acc[(slot) < kProfSlots ? (slot) : kProfSlots - 1] += (unsigned long long)(t3_ - prof_t2); prof_t2 = t3_; } while (0)
 #define PROF_FLUSH(role) do { if ((threadIdx.x & 31u) == 0 && blockIdx.x < 160) \
-    for (int q_ = 0; q_ < kProfSlots; q_++) g_prof[((blockIdx.x * 3 + grp) * 3 + (role)) * kProfSlots + q_] = prof_acc[q_]; } while (0)
+    for (int q_ = 0; q_ < kProfSlots; q_++) g_prof[((blockIdx.x * 3 + grp) * kProfRoles + (role)) * kProfSlots + q_] = prof_acc[q_]; } while (0)
 #else
 #define PROF_DECL
 #define PROF_MARK(slot) do { } while (0)
@@ -220,6 +221,23 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+// Long waits (the producer warp waiting for a tile's gates): the hardware parks the thread for up to `hint_ns` or
+// until the phase completes, instead of re-issuing the test every few hundred cycles on a sub-partition that the
+// compute warps need.
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+        : "memory");
+  } while (!done);
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t done;
@@ -526,7 +544,8 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
       PROF_DECL
       for (u64 t = t_begin; t < t_end; t++, i++) {
         const uint32_t buf = i & 1u;
-        mbar_wait(&done_bar[grp][buf], (i >> 1) & 1u);
+        if (dbg & 1024u) mbar_wait(&done_bar[grp][buf], (i >> 1) & 1u);
+        else mbar_wait_parked(&done_bar[grp][buf], (i >> 1) & 1u, 20000u);
         PROF_MARK(0);
         if (elect_one()) {
           if (st_on) {
@@ -551,7 +570,7 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
         PROF_MARK(3);
       }
       if (elect_one()) bulk_wait_read();
-      PROF_FLUSH(2);
+      PROF_FLUSH(8);
       return;
     }
   }
@@ -958,8 +977,7 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
     }
   }
   bulk_wait_read();
-  if constexpr (kProd)
-    if (wid == 0 || wid == 7) PROF_FLUSH(wid == 0 ? 0 : 1);
+  if constexpr (kProd) PROF_FLUSH(wid);
 }
 
 // One body, three launch shapes: several resident CTAs per SM (4 x 256 threads for the default 11-qubit
@@ -2069,6 +2087,7 @@ int qsv_debug_set_flags(uint32_t flags) {
 #endif
   g_debug_flags = flags;
   g_debug_flags_set = true;
+  g_p2p_unroll = ((flags >> 12) & 3u) == 1u ? 8 : ((flags >> 12) & 3u) == 2u ? 2 : ((flags >> 12) & 3u) == 3u ? 1 : 4;
   return 0;
 }
 

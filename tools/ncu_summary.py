@@ -1,5 +1,8 @@
 #!/usr/bin/env python
-"""Summarise an ncu raw-page CSV + source-page CSV (see B200_PROFILING.md)."""
+"""Summarise an ncu raw-page CSV + source-page CSV (see B200_PROFILING.md).
+    python tools/ncu_summary.py raw.csv source.csv [--dram-json out.json n_qubits kernel_regex]
+--dram-json writes the per-launch DRAM bytes of the first launch whose kernel name matches (bench.py reads that file for
+`roofline.traffic`)."""
 import csv, sys
 from collections import Counter
 raw, src = sys.argv[1], sys.argv[2]
@@ -30,3 +33,18 @@ for r in body:
 for op,v in c.most_common(16): print('  ',op, v, round(100*v/tot,1), ci[op])
 top=sorted(body,key=lambda r:-int(r[si]) if len(r)>si and r[si].isdigit() else 0)[:16]
 for r in top: print('  ',r[si], r[ii], r[1][:90])
+
+if '--dram-json' in sys.argv:
+    import json, re
+    j=sys.argv.index('--dram-json'); out,nq,rx=sys.argv[j+1],int(sys.argv[j+2]),sys.argv[j+3]
+    rows=list(csv.reader(open(raw))); hdr=rows[0]; units=rows[1]
+    kn=hdr.index('Kernel Name')
+    def val(r,key):
+        i=hdr.index(key); v=float(r[i].replace(',','')); u=units[i].lower()
+        return v*{'gbyte':1e9,'mbyte':1e6,'kbyte':1e3,'byte':1.0}.get(u,1.0)
+    for r in rows[2:]:
+        if re.search(rx,r[kn]):
+            rec={'n_qubits':nq,'kernel':r[kn][:120],'dram_bytes_read':val(r,'dram__bytes_read.sum'),
+                 'dram_bytes_write':val(r,'dram__bytes_write.sum'),'gpu_time_ms':val(r,'gpu__time_duration.sum')/1e6 if units[hdr.index('gpu__time_duration.sum')].lower().startswith('n') else None,
+                 'source':'ncu --set full --clock-control none, raw page '+raw}
+            json.dump(rec,open(out,'w'),indent=1); print('wrote',out,rec); break

@@ -1,0 +1,71 @@
+#!/usr/bin/env python
+"""NVLink peer-memory qubit swap (qsv_swap_bits_p2p) under torchrun on 2+ GPUs: GB/s per GPU and direction as a
+function of the swapped local bit, the loads in flight per thread and the grid size.
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/p2p_swap_probe.py [n_local]"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from qiskit_sdk_py_b200 import _lib  # noqa: E402
+from qiskit_sdk_py_b200.dist import ShardedState  # noqa: E402
+from qiskit_sdk_py_b200.engine import DeviceState  # noqa: E402
+
+local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local_rank)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+rank, world = dist.get_rank(), dist.get_world_size()
+g = world.bit_length() - 1
+n_local = int(sys.argv[1]) if len(sys.argv) > 1 else 30
+st = ShardedState(n_local + g, DeviceState)
+st.init_basis0()
+lib = _lib.load()
+
+
+def timed(pairs, ctas, reps=3):
+    beta = 0
+    for i, (pg, _) in enumerate(pairs):
+        beta |= ((rank >> (pg - n_local)) & 1) << i
+    lbits = [pl for _, pl in pairs]
+    ptrs = [None] * (1 << len(pairs))
+    for lam in range(1 << len(pairs)):
+        if lam == beta:
+            continue
+        r = rank
+        for i, (pg, _) in enumerate(pairs):
+            j = pg - n_local
+            r = (r & ~(1 << j)) | (((lam >> i) & 1) << j)
+        ptrs[lam] = st._peers[r][0]
+    st._stream_barrier()
+    st.shard.swap_bits_p2p(lbits, beta, ptrs, ctas)
+    st._stream_barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        st._stream_barrier()
+        st.shard.swap_bits_p2p(lbits, beta, ptrs, ctas)
+    st._stream_barrier()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / reps], device="cuda")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    k = len(pairs)
+    gb = 16.0 * (1 << (n_local - k)) * ((1 << k) - 1) / 1e9
+    return float(ms.item()), gb
+
+
+for unroll_flag, unroll in ((0, 4), (1 << 12, 8), (2 << 12, 2)):
+    lib.qsv_debug_set_flags(unroll_flag)
+    for ctas in (74, 148, 296, 592):
+        for bit in (n_local - 1, n_local // 2, 5):
+            pairs = [(n_local + j, bit - j) for j in range(g)]
+            ms, gb = timed(pairs, ctas)
+            if rank == 0:
+                print("unroll %d ctas %3d swapped local bits %s: %.2f ms  %.1f GB per GPU and direction  %.0f GB/s" % (
+                    unroll, ctas, [pl for _, pl in pairs], ms, gb, gb / ms * 1e3), flush=True)
+lib.qsv_debug_set_flags(0)
+st.close()
+dist.destroy_process_group()

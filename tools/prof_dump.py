@@ -23,7 +23,8 @@ st = DeviceState(n)
 st.init_basis0()
 lib = _lib.load()
 SLOTS = 20
-words = 148 * 3 * 3 * SLOTS
+ROLES = 9
+words = 148 * 3 * ROLES * SLOTS
 buf = (ctypes.c_uint64 * words)()
 tiles_per_group = (1 << (n - 11)) / (148 * 3)
 print("n=%d: %d passes, %.0f tiles per group; clocks per tile" % (n, len(passes), tiles_per_group))
@@ -40,11 +41,13 @@ for k, p in enumerate(passes[:n_passes]):
     e1.record()
     torch.cuda.synchronize()
     _lib.check(lib.qsv_debug_profile(buf, words), "qsv_debug_profile")
-    a = np.frombuffer(buf, dtype=np.uint64).reshape(148, 3, 3, SLOTS).astype(np.float64) / tiles_per_group
+    a = np.frombuffer(buf, dtype=np.uint64).reshape(148, 3, ROLES, SLOTS).astype(np.float64) / tiles_per_group
     m = a.mean(axis=(0, 1))
     print("%4d %5d %4d | %7.0f %7.0f %6.0f | %7.0f %7.0f %6.0f | %7.0f %7.0f %7.0f %7.0f | %.3f" % (
-        k, len(p.ops), info["ops"], m[0, 0], m[0, 1], m[0, 2], m[1, 0], m[1, 1], m[1, 2], m[2, 0], m[2, 1], m[2, 2],
-        m[2, 3], e0.elapsed_time(e1)))
+        k, len(p.ops), info["ops"], m[0, 0], m[0, 1], m[0, 2], m[7, 0], m[7, 1], m[7, 2], m[8, 0], m[8, 1], m[8, 2],
+        m[8, 3], e0.elapsed_time(e1)))
+    print("       gates per warp 0..7: %s | wait_tile: %s" % (" ".join("%6.0f" % v for v in m[:8, 1]),
+                                                                " ".join("%5.0f" % v for v in m[:8, 0])))
     kinds = DeviceState.pass_ops(n, p.tile_qubits, p.ops) if hasattr(DeviceState, "pass_ops") else None
     print("       warp0 per op: barrier %5.0f | %s" % (m[0, 4], " ".join("%5.0f" % v for v in m[0, 5:5 + info["ops"]])))
-    print("       warp7 per op: barrier %5.0f | %s" % (m[1, 4], " ".join("%5.0f" % v for v in m[1, 5:5 + info["ops"]])))
+    print("       warp7 per op: barrier %5.0f | %s" % (m[7, 4], " ".join("%5.0f" % v for v in m[7, 5:5 + info["ops"]])))
