@@ -113,6 +113,15 @@ int qsv_apply_pass_tail(double* sv, int n_qubits, const int32_t* tile_qubits, in
                         const qsv_gate_t* tail, int n_tail, void* dev_scratch, void* stream);
 size_t qsv_tail_scratch_bytes(void);
 
+/* qsv_apply_pass_tail restricted to a SUB-BLOCK of the state: only the amplitudes whose qubits fixed_qubits[i] read
+ * bit i of fixed_pattern are touched (the fixed qubits are neither tile qubits nor acted on by any gate), on at most
+ * max_sms SMs (0 = all).  The multi-GPU engine applies the passes that commute with a qubit-swap exchange sub-block by
+ * sub-block while the other sub-blocks are in flight over NVLink, the exchange kernel running on the SMs left free
+ * (dist.ShardedState).  Same gates / tail / scratch conventions as qsv_apply_pass_tail; no write-back permutation. */
+int qsv_apply_pass_sub(double* sv, int n_qubits, const int32_t* tile_qubits, int n_tile, const qsv_gate_t* gates,
+                       int n_gates, const qsv_gate_t* tail, int n_tail, void* dev_scratch,
+                       const int32_t* fixed_qubits, int n_fixed, uint32_t fixed_pattern, int max_sms, void* stream);
+
 /* Host-only introspection of the lowering qsv_apply_pass[_remap] would do for these arguments (no GPU is
  * touched, nothing is launched): info[0] = kernel ops after gate fusion (2-qubit gates that share a qubit
  * are merged into 3-qubit blocks), info[1] = stages (block-wide barriers + 1), info[2] = fused 3-qubit

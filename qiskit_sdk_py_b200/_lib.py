@@ -68,6 +68,9 @@ SIGNATURES = {
     "qsv_apply_pass_tail": (_c_int, [_c_void_p, _c_int, _p_int32, _c_int, ctypes.POINTER(QsvGate), _c_int, _p_int32,
                                      ctypes.POINTER(QsvGate), _c_int, _c_void_p, _c_void_p]),
     "qsv_tail_scratch_bytes": (_c_size_t, []),
+    "qsv_apply_pass_sub": (_c_int, [_c_void_p, _c_int, _p_int32, _c_int, ctypes.POINTER(QsvGate), _c_int,
+                                    ctypes.POINTER(QsvGate), _c_int, _c_void_p, _p_int32, _c_int, ctypes.c_uint32, _c_int,
+                                    _c_void_p]),
     "qsv_pass_info": (_c_int, [_c_int, _p_int32, _c_int, ctypes.POINTER(QsvGate), _c_int, _p_int32, _p_int32]),
     "qsv_pass_ops": (_c_int, [_c_int, _p_int32, _c_int, ctypes.POINTER(QsvGate), _c_int, _p_int32, _p_int32, _c_int]),
     "qsv_apply_matrix": (_c_int, [_c_void_p, _c_int, _p_int32, _c_int, _c_void_p, _c_void_p, _c_void_p]),

@@ -161,11 +161,13 @@ struct PassDesc {
   int32_t nruns;        // tabulated diagonal runs
   int32_t run_entries;  // their tables together (complex entries)
   uint32_t n_tiles;
+  int32_t n_spread;     // entries of tbs: the tile bits plus the FIXED bits of a sub-block pass (qsv_apply_pass_sub)
+  uint64_t fixed_mask;  // physical bits that keep the value the caller folded into the state pointer
   uint32_t flags;       // QSV_DEBUG_FLAGS (profiling experiments)
   uint32_t pb_ld;       // log2(amplitudes per bulk-load piece): contiguous low tile bits, at most 4 (256 B)
   uint32_t pb_st;       // same for the write-back (smaller if the write-back permutes low bits)
   uint8_t tb[16];       // physical bit of tile-local position j (positions 0..3 = the four lowest tile qubits)
-  uint8_t tbs[16];      // the tile's physical bits in ascending order (tile base computation)
+  uint8_t tbs[16];      // the tile's (and the fixed) physical bits in ascending order (tile base computation)
   uint16_t cj[16];      // shared-memory slot increment of tile-local bit j (see slot layout below)
   uint8_t src_of[16];   // write-back permutation: tile-local position j receives the content of bit src_of[j]
   // warp-group variant: offsets of bulk-copy piece p (its index bits = the tile-local bits pb_ld..b-1), in
@@ -296,7 +298,7 @@ __device__ __forceinline__ void dmma884_c(double& d0, double& d1, double a, doub
 
 // physical base address (in amplitudes) of tile t: spread t over the non-tile bits
 __device__ __forceinline__ u64 tile_base(const PassDesc& d, u64 t) {
-  for (int j = 0; j < d.b; j++) {
+  for (int j = 0; j < d.n_spread; j++) {
     const int p = d.tbs[j];
     t = ((t >> p) << (p + 1)) | (t & ((1ull << p) - 1ull));
   }
@@ -373,7 +375,7 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
 
   // ---- per-kernel setup (amortised over all tiles of this CTA): every lane/warp dependent index of
   // the pass is tile-invariant, so it is digested once into shared-memory tables / registers ----
-  u64 tile_mask = 0;  // physical bit mask of the tile qubits
+  u64 tile_mask = d.fixed_mask;  // physical bits the tile walk skips: the tile qubits and a sub-block's fixed bits
   for (int j = 0; j < b; j++) tile_mask |= 1ull << d.tb[j];
   if (ctid == 0) {
     // kDB: one arrival per issuing warp (kProd: the producer's single arrive.expect_tx)
@@ -1282,7 +1284,8 @@ struct PassPlan {
 static int lower_pass(PassDesc& d, PassPlan& plan, int n, const int32_t* tile_qubits, int n_tile,
                       const qsv_gate_t* gates, int n_gates, const int32_t* dest_qubits,
                       const qsv_gate_t* tail = nullptr, int n_tail = 0, double* tail_ent = nullptr,
-                      const double* block8 = nullptr, const int32_t* block_qubits = nullptr) {
+                      const double* block8 = nullptr, const int32_t* block_qubits = nullptr,
+                      const int32_t* fixed_qubits = nullptr, int n_fixed = 0) {
   if (n_tail < 0 || n_tail > kMaxTail) return fail(QSV_ERANGE, "qsv_apply_pass_tail: too many tail gates");
   if (n_tail > 0 && (!tail || !tail_ent)) return fail(QSV_EINVAL, "qsv_apply_pass_tail: null pointer");
   if (n < 1 || n > 40) return fail(QSV_EINVAL, "qsv_apply_pass: bad state / n_qubits");
@@ -1305,6 +1308,18 @@ static int lower_pass(PassDesc& d, PassPlan& plan, int n, const int32_t* tile_qu
   for (int j = 0; j + 1 < b; j++)
     if (sorted[j] == sorted[j + 1]) return fail(QSV_EINVAL, "qsv_apply_pass: duplicate tile qubit");
   for (int j = 0; j < b; j++) d.tbs[j] = (uint8_t)sorted[j];
+  d.n_spread = b;
+  if (n_fixed < 0 || n_fixed > 4 || (n_fixed > 0 && !fixed_qubits) || b + n_fixed > n)
+    return fail(QSV_EINVAL, "qsv_apply_pass_sub: bad fixed qubits");
+  for (int i = 0; i < n_fixed; i++) {
+    const int q = fixed_qubits[i];
+    bool clash = q < 0 || q >= n || ((d.fixed_mask >> q) & 1ull);
+    for (int j = 0; j < b; j++) clash |= sorted[j] == q;
+    if (clash) return fail(QSV_EINVAL, "qsv_apply_pass_sub: fixed qubits must be distinct and outside the tile");
+    d.fixed_mask |= 1ull << q;
+    d.tbs[d.n_spread++] = (uint8_t)q;
+  }
+  std::sort(d.tbs, d.tbs + d.n_spread);
 
   // ---- tile-local positions: 0..3 = the four lowest tile qubits (they form the contiguous 256-byte
   // pieces when they are physical qubits 0..3); the others are placed so that the two qubits of every
@@ -1312,12 +1327,7 @@ static int lower_pass(PassDesc& d, PassPlan& plan, int n, const int32_t* tile_qu
   int pos_phys[16];
   {
     const int n_fixed = std::min(b, 4);
-    int cls_of[64];
-    for (int q = 0; q < 64; q++) cls_of[q] = -1;
-    for (int j = 0; j < n_fixed; j++) {
-      pos_phys[j] = sorted[j];
-      cls_of[sorted[j]] = bank_class(j);
-    }
+    for (int j = 0; j < n_fixed; j++) pos_phys[j] = sorted[j];
     uint64_t adj[64] = {0};
     int deg[64] = {0};
     for (int i = 0; i < n_gates; i++) {
@@ -1326,33 +1336,62 @@ static int lower_pass(PassDesc& d, PassPlan& plan, int n, const int32_t* tile_qu
       if (a < 0 || a >= n || c < 0 || c >= n || a == c) continue;  // reported below
       if (!((adj[a] >> c) & 1ull)) { adj[a] |= 1ull << c; adj[c] |= 1ull << a; deg[a]++; deg[c]++; }
     }
-    bool pos_used[16] = {false};
-    bool placed[16] = {false};
-    for (int round = n_fixed; round < b; round++) {
-      // next qubit: the unplaced one with the most already-placed neighbours, then highest degree
-      int best_i = -1, best_key = -1;
-      for (int i = n_fixed; i < b; i++) {
-        if (placed[i]) continue;
-        const int q = sorted[i];
-        int placed_nb = 0;
-        for (int k = 0; k < b; k++)
-          if (((adj[q] >> sorted[k]) & 1ull) && cls_of[sorted[k]] >= 0) placed_nb++;
-        const int key = placed_nb * 64 + deg[q];
-        if (key > best_key) { best_key = key; best_i = i; }
+    // Exhaustive search over the bank classes of the free positions (7 positions -> 210 distinct assignments; 8 ->
+    // 560): minimise the number of dense gates whose two qubits share a class (2-way bank conflicts on every access
+    // of that gate), then the number of qubit pairs of one class that are both neighbours of a third qubit (such a
+    // gate finds no conflict-free third bit).  The greedy colouring this replaces left ~8 % of the dense ops of a
+    // quantum-volume circuit with conflicts -- on the busiest pipe of the kernel (L1TEX ~80 %).
+    const int m = b - n_fixed;
+    if (m > 0) {
+      int cap[3] = {0, 0, 0};
+      for (int ps = n_fixed; ps < b; ps++) cap[bank_class(ps)]++;
+      int fq[16];  // free qubits, highest degree first (prunes the search early)
+      for (int i = 0; i < m; i++) fq[i] = sorted[n_fixed + i];
+      std::sort(fq, fq + m, [&](int x, int y) { return deg[x] != deg[y] ? deg[x] > deg[y] : x < y; });
+      int cur[16], best[16], best_cost = 1 << 30;
+      auto cost_of = [&](int upto) {  // conflicts among the fixed qubits and fq[0..upto)
+        int c = 0;
+        for (int i = 0; i < upto; i++) {
+          const int q = fq[i];
+          for (int j = 0; j < n_fixed; j++)
+            if (((adj[q] >> sorted[j]) & 1ull) && bank_class(j) == cur[i]) c += 4;
+          for (int j = 0; j < i; j++)
+            if (((adj[q] >> fq[j]) & 1ull) && cur[j] == cur[i]) c += 4;
+        }
+        return c;
+      };
+      // iterative depth-first enumeration
+      int depth = 0;
+      cur[0] = -1;
+      int used_cap[3] = {0, 0, 0};
+      while (depth >= 0) {
+        if (cur[depth] >= 0) used_cap[cur[depth]]--;
+        int c = cur[depth] + 1;
+        while (c < 3 && used_cap[c] >= cap[c]) c++;
+        if (c >= 3) { depth--; continue; }
+        cur[depth] = c;
+        used_cap[c]++;
+        const int partial = cost_of(depth + 1);
+        if (partial >= best_cost) continue;  // prune: costs only grow
+        if (depth + 1 == m) {
+          best_cost = partial;
+          memcpy(best, cur, sizeof(int) * m);
+          if (best_cost == 0) break;
+          continue;
+        }
+        depth++;
+        cur[depth] = -1;
       }
-      const int q = sorted[best_i];
-      int best_pos = -1, best_conf = 1 << 30;
-      for (int ps = n_fixed; ps < b; ps++) {
-        if (pos_used[ps]) continue;
-        int conf = 0;
-        for (int k = 0; k < b; k++)
-          if (((adj[q] >> sorted[k]) & 1ull) && cls_of[sorted[k]] == bank_class(ps)) conf++;
-        if (conf < best_conf) { best_conf = conf; best_pos = ps; }
+      // positions of a class are handed out in ascending order
+      bool pos_used[16] = {false};
+      for (int i = 0; i < m; i++) {
+        for (int ps = n_fixed; ps < b; ps++)
+          if (!pos_used[ps] && bank_class(ps) == best[i]) {
+            pos_used[ps] = true;
+            pos_phys[ps] = fq[i];
+            break;
+          }
       }
-      placed[best_i] = true;
-      pos_used[best_pos] = true;
-      pos_phys[best_pos] = q;
-      cls_of[q] = bank_class(best_pos);
     }
   }
   int local_of[64];
@@ -1799,6 +1838,8 @@ static int lower_pass(PassDesc& d, PassPlan& plan, int n, const int32_t* tile_qu
       const bool two = g.kind == QSV_GATE_DIAG2;
       if (g.q0 < 0 || g.q0 >= n || (two && (g.q1 < 0 || g.q1 >= n || g.q1 == g.q0)))
         return fail(QSV_EINVAL, "qsv_apply_pass_tail: tail gate qubit out of range");
+      if (((d.fixed_mask >> g.q0) & 1ull) || (two && ((d.fixed_mask >> g.q1) & 1ull)))
+        return fail(QSV_EINVAL, "qsv_apply_pass_sub: a tail gate may not act on a fixed qubit");
       const int l0 = local_of[g.q0], l1 = two ? local_of[g.q1] : -1;
       if (two && l0 >= 0 && l1 >= 0)
         return fail(QSV_EINVAL, "qsv_apply_pass_tail: a 2-qubit tail gate needs a qubit outside the tile");
@@ -1896,7 +1937,7 @@ static int lower_pass(PassDesc& d, PassPlan& plan, int n, const int32_t* tile_qu
   const size_t smem = tile_slots * sizeof(double2) + (size_t)nfrag * 64 * sizeof(double) +
                       (size_t)n_gates * (sizeof(OpRec) + 32 * 4) + (size_t)n_stages * ((kWarps + 32 + 8) * 4) + 16 +
                       (size_t)d.run_entries * sizeof(double2) + (size_t)d.nruns * 56 * sizeof(uint16_t);
-  d.n_tiles = 1u << (n - b);
+  d.n_tiles = 1u << (n - b - n_fixed);
   // one warp per 2^8 amplitudes: 512 threads for b = 12, 256 for b = 11, ...; at least one warp
   plan.smem = smem;
   plan.threads = std::max(32, std::min(kMaxPT, 1 << std::max(0, b - 3)));
@@ -1921,15 +1962,21 @@ static int lower_pass(PassDesc& d, PassPlan& plan, int n, const int32_t* tile_qu
 static int launch_pass(double* sv, int n, const int32_t* tile_qubits, int n_tile, const qsv_gate_t* gates,
                        int n_gates, cudaStream_t stream, const int32_t* dest_qubits = nullptr,
                        const qsv_gate_t* tail = nullptr, int n_tail = 0, void* dev_scratch = nullptr,
-                       const double* block8 = nullptr, const int32_t* block_qubits = nullptr) {
+                       const double* block8 = nullptr, const int32_t* block_qubits = nullptr,
+                       const int32_t* fixed_qubits = nullptr, int n_fixed = 0, uint32_t fixed_pattern = 0,
+                       int max_ctas = 0) {
   if (!sv) return fail(QSV_EINVAL, "qsv_apply_pass: bad state / n_qubits");
   if (n_tail > 0 && !dev_scratch) return fail(QSV_EINVAL, "qsv_apply_pass_tail: null device scratch");
   static thread_local PassDesc d;
   static thread_local double tail_ent[kMaxTail * 8];
   PassPlan plan;
   if (int rc = lower_pass(d, plan, n, tile_qubits, n_tile, gates, n_gates, dest_qubits, tail, n_tail, tail_ent, block8,
-                          block_qubits))
+                          block_qubits, fixed_qubits, n_fixed))
     return rc;
+  // a sub-block pass walks only the tiles whose fixed bits read `fixed_pattern`: their value goes into the pointer
+  for (int i = 0; i < n_fixed; i++)
+    if ((fixed_pattern >> i) & 1u) sv += 2 * ((size_t)1 << fixed_qubits[i]);
+  const unsigned cta_cap = max_ctas > 0 ? (unsigned)max_ctas : 0xffffffffu;
   if (int rc = ensure_attrs()) return rc;
   if (n_tail > 0)  // small pageable copy: staged by the driver before the call returns, ordered on the stream
     QSV_CUDA(cudaMemcpyAsync(dev_scratch, tail_ent, sizeof(double) * 8 * (size_t)n_tail, cudaMemcpyHostToDevice, stream));
@@ -1937,7 +1984,7 @@ static int launch_pass(double* sv, int n, const int32_t* tile_qubits, int n_tile
   const size_t smem = plan.smem;
   const int threads = plan.threads;
   if (plan.groups) {
-    const unsigned grid3 = std::min<unsigned>((d.n_tiles + 2) / 3, (unsigned)sm_count());
+    const unsigned grid3 = std::min(std::min<unsigned>((d.n_tiles + 2) / 3, (unsigned)sm_count()), cta_cap);
     if (d.flags & 512u)  // A/B: compute warps issue their own bulk copies (round-1 shape)
       tile_pass_kernel<768, 1, 3><<<grid3, 768, smem, stream>>>(reinterpret_cast<double2*>(sv), d, d_tail);
     else
@@ -1955,7 +2002,8 @@ static int launch_pass(double* sv, int n, const int32_t* tile_qubits, int n_tile
     QSV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tile_pass_kernel<128, 8>, threads, smem));
   }
   if (per_sm < 1) return fail(QSV_ERANGE, "qsv_apply_pass: pass does not fit in shared memory");
-  const unsigned grid = std::min<unsigned>(d.n_tiles, (unsigned)per_sm * (unsigned)sm_count());
+  const unsigned grid = std::min(std::min<unsigned>(d.n_tiles, (unsigned)per_sm * (unsigned)sm_count()),
+                                 cta_cap == 0xffffffffu ? cta_cap : cta_cap * (unsigned)per_sm);
   if (threads >= 512)
     tile_pass_kernel<512, 2><<<grid, threads, smem, stream>>>(reinterpret_cast<double2*>(sv), d, d_tail);
   else if (threads >= 256)
@@ -2058,6 +2106,15 @@ int qsv_apply_pass_tail(double* sv, int n, const int32_t* tile_qubits, int n_til
   if (!tile_qubits || (n_gates > 0 && !gates)) return fail(QSV_EINVAL, "qsv_apply_pass_tail: null pointer");
   return launch_pass(sv, n, tile_qubits, n_tile, gates, n_gates, (cudaStream_t)stream, dest_qubits, tail, n_tail,
                      dev_scratch);
+}
+
+int qsv_apply_pass_sub(double* sv, int n, const int32_t* tile_qubits, int n_tile, const qsv_gate_t* gates, int n_gates,
+                       const qsv_gate_t* tail, int n_tail, void* dev_scratch, const int32_t* fixed_qubits, int n_fixed,
+                       uint32_t fixed_pattern, int max_sms, void* stream) {
+  if (!tile_qubits || (n_gates > 0 && !gates)) return fail(QSV_EINVAL, "qsv_apply_pass_sub: null pointer");
+  if (n_fixed > 0 && fixed_pattern >= (1u << n_fixed)) return fail(QSV_EINVAL, "qsv_apply_pass_sub: bad pattern");
+  return launch_pass(sv, n, tile_qubits, n_tile, gates, n_gates, (cudaStream_t)stream, nullptr, tail, n_tail, dev_scratch,
+                     nullptr, nullptr, fixed_qubits, n_fixed, fixed_pattern, max_sms);
 }
 
 size_t qsv_tail_scratch_bytes(void) { return sizeof(double) * 8 * kMaxTail; }

@@ -30,6 +30,7 @@ from .planner import DEFAULT_TILE_QUBITS as DEFAULT_TILE
 
 DEFAULT_CHUNK_AMPS = 1 << 26  # 1 GiB staging buffers (torch.distributed transport of the CPU tests)
 _IPC_OPEN = {}                 # CUDA IPC handle -> [mapped base pointer, references]
+_LOW_BITS = 4                  # the planner pins the lowest local bits into every tile (256-byte runs)
 
 
 class ShardedState:
@@ -37,7 +38,7 @@ class ShardedState:
     double with the same interface) holding this rank's 2^(n - log2(world)) amplitudes."""
 
     def __init__(self, n_qubits, shard_factory, rank=None, world=None, chunk_amps=DEFAULT_CHUNK_AMPS,
-                 group=None, p2p=True):
+                 group=None, p2p=True, overlap=True):
         import torch
         import torch.distributed as dist
 
@@ -62,6 +63,9 @@ class ShardedState:
         self.fused_exchanges = 0
         self.swap_bytes = 0
         self._xch_events = []   # (start, end) CUDA events around every exchange (device shards only)
+        self.overlap = bool(overlap)  # run the passes that commute with an exchange while it is in flight
+        self.overlapped_exchanges = 0
+        self._comm_stream = None
         # NVLink peer memory: shards that can export a CUDA IPC handle (engine.DeviceState) are mapped into every
         # rank of the group once, and the exchanges run as ONE in-place swap kernel per rank (qsv_swap_bits_p2p);
         # the numpy test double of the CPU tests has no such handle and goes through torch.distributed send/recv
@@ -266,7 +270,6 @@ class ShardedState:
             return self._swap_p2p(pairs)
         if len(pairs) == 1:
             return self.swap_global_local(*pairs[0])
-        dist = self._dist
         t_begin = self._xch_begin()
         k = len(pairs)
         gbits = [pg - self.n_local for pg, _ in pairs]
@@ -282,10 +285,24 @@ class ShardedState:
             for i, j in enumerate(gbits):
                 r = (r & ~(1 << j)) | (((lam >> i) & 1) << j)
             peers[lam] = r
+        self._swap_staged(lbits, beta, peers)
+        self._xch_end(t_begin)
+        for pg, pl in pairs:
+            qa, qb = self._logical_at(pg), self._logical_at(pl)
+            self.pos[qa], self.pos[qb] = pl, pg
+        self.swaps += k
+        self.fused_exchanges += 1
+        self.swap_bytes += 16 * (1 << (self.n_local - k)) * ((1 << k) - 1)
+
+    def _swap_staged(self, lbits, beta, peers):
+        """torch.distributed transport (CPU tests): my sub-blocks [lbits = lam] trade places with rank peers[lam]'s
+        sub-block [lbits = beta], for every lam in ``peers``; pack -> send/recv -> unpack through staging buffers."""
+        dist = self._dist
+        k = len(lbits)
         sub = 1 << (self.n_local - k)
-        chunk = max(1, min(self.chunk_amps // max(1, (1 << k) - 1), sub))
+        chunk = max(1, min(self.chunk_amps // max(1, len(peers)), sub))
         spans = [(begin, min(chunk, sub - begin)) for begin in range(0, sub, chunk)]
-        send, recv = self._staging(chunk * ((1 << k) - 1))
+        send, recv = self._staging(chunk * len(peers))
         lams = sorted(peers)
 
         def view(bufs, i, slot, cnt):
@@ -323,13 +340,6 @@ class ShardedState:
             unpack(i)
             if i + 2 < len(spans):
                 pack(i + 2)
-        self._xch_end(t_begin)
-        for pg, pl in pairs:
-            qa, qb = self._logical_at(pg), self._logical_at(pl)
-            self.pos[qa], self.pos[qb] = pl, pg
-        self.swaps += k
-        self.fused_exchanges += 1
-        self.swap_bytes += 16 * sub * ((1 << k) - 1)
 
     # -- gates -------------------------------------------------------------------------
     def _localise(self, op):
@@ -380,10 +390,117 @@ class ShardedState:
                     deferred.append(op)
                 elif loc is not None:
                     run.append(loc)
+            pairs = self._plan_swap(deferred) if deferred else []
+            late = []
+            if pairs and self.overlap:
+                run, late = self._split_for_overlap(run, [pl for _, pl in pairs])
             self._apply_local(run)
-            if deferred:
-                self._swap_in_for(deferred)
+            if late:
+                self._exchange_overlapped(pairs, late)
+            elif pairs:
+                self.swap_many(pairs)
             remaining = deferred
+
+    # -- exchange overlapped with the passes that commute with it ---------------------------------------
+    MIN_OVERLAP_GATES = 6    # fewer late gates than this: not worth splitting the passes
+    OVERLAP_TARGET_GATES = 30  # ... and no more than about four passes' worth (one exchange takes 2-4 pass times)
+    EXCHANGE_SMS = 16        # SMs left to the exchange kernel while sub-block passes run
+
+    def _split_for_overlap(self, run, victim_bits):
+        """Split the locally runnable ops (physical qubits, program order) into (early, late): ``late`` = the ops
+        with no successor-or-self on a victim bit -- they act on other qubits than the exchange moves, and nothing
+        that touches a victim bit has to wait for them, so they commute with the exchange and can run sub-block by
+        sub-block while it is in flight.  Global scalars stay early."""
+        if self.n_local - len(victim_bits) < self.shard.tile_qubits or any(v < _LOW_BITS for v in victim_bits):
+            return run, []
+        tainted = set(victim_bits)
+        late_flags = [False] * len(run)
+        for idx in range(len(run) - 1, -1, -1):
+            item = run[idx]
+            if isinstance(item, tuple):
+                continue
+            if set(item.qubits) & tainted:
+                tainted |= set(item.qubits)
+            else:
+                late_flags[idx] = True
+        # no more late work than the exchange can hide (the last OVERLAP_TARGET_GATES of them: a suffix of the late ops
+        # is closed under successors); the rest stays with the early ops, where it fuses into fuller passes
+        n_late = 0
+        for idx in range(len(run) - 1, -1, -1):
+            if late_flags[idx]:
+                n_late += 1
+                if n_late > self.OVERLAP_TARGET_GATES:
+                    late_flags[idx] = False
+        late = [op for op, f in zip(run, late_flags) if f]
+        if len(late) < self.MIN_OVERLAP_GATES:
+            return run, []
+        return [op for op, f in zip(run, late_flags) if not f], late
+
+    def _exchange_overlapped(self, pairs, late):
+        """The exchange of ``pairs`` with the ``late`` ops applied meanwhile: the swapped local bits split the shard
+        into 2^k sub-blocks; the late passes run on one sub-block after the other (qsv_apply_pass_sub, the swapped
+        bits fixed), and as soon as a sub-block is done on both partners it is exchanged (XOR schedule: in step j
+        rank beta trades with beta ^ j) -- on the GPU by the peer-memory swap kernel on a second stream and on the
+        SMs the passes leave free; the sub-block that stays is processed last, under the last transfers."""
+        k = len(pairs)
+        gbits = [pg - self.n_local for pg, _ in pairs]
+        lbits = [pl for _, pl in pairs]
+        beta = 0
+        for i, j in enumerate(gbits):
+            beta |= ((self.rank >> j) & 1) << i
+        rank_of = {}
+        for lam in range(1 << k):
+            r = self.rank
+            for i, j in enumerate(gbits):
+                r = (r & ~(1 << j)) | (((lam >> i) & 1) << j)
+            rank_of[lam] = r
+        passes = self.shard.plan_ops(late, avoid=lbits)
+        for p in passes:
+            if set(p.tile_qubits) & set(lbits):
+                raise _lib.QsvLibraryError("overlapped exchange: a late pass has a swapped bit in its tile")
+        order = [beta ^ j for j in range(1, 1 << k)] + [beta]
+        t_begin = self._xch_begin()
+        device = self._peers is not None
+        if device:
+            torch = self._torch
+            if self._comm_stream is None:
+                self._comm_stream = torch.cuda.Stream()
+            cur, comm = torch.cuda.current_stream(), self._comm_stream
+            n_sms = self.shard.sm_count
+            cap = max(1, n_sms - self.EXCHANGE_SMS)
+        for lam in order:
+            for p in passes:
+                self.shard.apply_pass_sub(p.tile_qubits, p.ops, p.tail, lbits, lam, cap if device else 0)
+            if lam == beta:
+                continue
+            if device:
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                with torch.cuda.stream(comm):
+                    comm.wait_event(ev)
+                    self._stream_barrier()  # this step's sub-block is finished on every rank
+                    ptrs = [None] * (1 << k)
+                    ptrs[lam] = self._peers[rank_of[lam]][0]
+                    self.shard.swap_bits_p2p(lbits, beta, ptrs, 2 * self.EXCHANGE_SMS)
+            else:
+                self._swap_staged(lbits, beta, {lam: rank_of[lam]})
+        if device:
+            with torch.cuda.stream(comm):
+                self._stream_barrier()      # every transfer has landed everywhere
+                done = torch.cuda.Event()
+                done.record(comm)
+            cur.wait_event(done)
+        self._xch_end(t_begin)
+        self.shard.passes_launched += len(passes)
+        self.shard.gates_applied += sum(len(p.ops) + len(p.tail) for p in passes)
+        for pg, pl in pairs:
+            qa, qb = self._logical_at(pg), self._logical_at(pl)
+            self.pos[qa], self.pos[qb] = pl, pg
+        self.swaps += k
+        self.overlapped_exchanges += 1
+        if k > 1:
+            self.fused_exchanges += 1
+        self.swap_bytes += 16 * (1 << (self.n_local - k)) * ((1 << k) - 1)
 
     def _apply_local(self, run):
         batch = []
@@ -401,6 +518,12 @@ class ShardedState:
 
     def _swap_in_for(self, deferred):
         """Bring the global qubits the deferred gates need into local bits."""
+        pairs = self._plan_swap(deferred)
+        if pairs:
+            self.swap_many(pairs)
+
+    def _plan_swap(self, deferred):
+        """[(physical global bit, physical local victim bit), ...] for the global qubits the deferred gates need."""
         first_use, order = {}, []
         for idx, op in enumerate(deferred):
             for q in op.qubits:
@@ -432,6 +555,10 @@ class ShardedState:
             for lq in range(self.n):
                 if self.pos[lq] >= self.n_local or lq in need or lq in partners or lq in taken:
                     continue
+                # the pinned low bits stay local when passes are to overlap the exchange: they are tile bits of every
+                # pass and a sub-block pass cannot have a swapped bit in its tile
+                if self.overlap and self.pos[lq] < _LOW_BITS and self.n_local - _LOW_BITS > 2 * self.g:
+                    continue
                 use = first_use.get(lq, never)
                 if use > best_use:
                     best, best_use = lq, use
@@ -439,8 +566,7 @@ class ShardedState:
                 raise RuntimeError("no local qubit available to swap out")
             taken.add(best)
             pairs.append((self.pos[q], self.pos[best]))
-        if pairs:
-            self.swap_many(pairs)
+        return pairs
 
     def ensure_local(self, qubit):
         """Make logical ``qubit`` a local bit (used before measure / reset on it)."""
@@ -816,7 +942,8 @@ def bench_main(args, bench):
     ins = [i for i in circuits.quantum_volume_instructions(n, depth, qv_seed) if i["name"] == "unitary"]
     ops = [lower.lower_gate(i["name"], i["qubits"], i.get("params")) for i in ins]
     n_gates = len(ops)
-    st = ShardedState(n, factory, chunk_amps=chunk_amps)
+    overlap = os.environ.get("QSV_DIST_OVERLAP", "1") == "1"  # A/B knob of tools/: exchanges without late passes
+    st = ShardedState(n, factory, chunk_amps=chunk_amps, overlap=overlap)
     uniforms = np.random.RandomState(sim_seed).random_sample(shots)
 
     def step():
@@ -851,6 +978,7 @@ def bench_main(args, bench):
     swaps0, bytes0, fused0 = st.swaps, st.swap_bytes, st.fused_exchanges
     passes0 = st.shard.passes_launched
     xch0 = st.exchange_ms
+    ovl0 = st.overlapped_exchanges
     step_ms, (samples, total) = timed(step, args.steps)
     launches = torch.tensor([_lib.launch_count() - launches0], device="cuda", dtype=torch.int64)
     dist.all_reduce(launches, op=dist.ReduceOp.SUM)
@@ -859,6 +987,7 @@ def bench_main(args, bench):
     fused_dev = (st.fused_exchanges - fused0) / args.steps
     swap_gb_dev = (st.swap_bytes - bytes0) / args.steps / 1e9
     exchange_ms = st.exchange_time_ms(xch0) / args.steps
+    st_overlapped = st.overlapped_exchanges - ovl0
     clock_info = clocks.stop() if rank == 0 else None
 
     # ---- the other circuit families of BASELINE's metric on the sharded state (one warm-up, one timed run each) ----
@@ -935,6 +1064,7 @@ def bench_main(args, bench):
             "circuit_s": step_ms * 1e-3,
             "schedule": {"local_passes_per_step": passes_dev, "qubit_swaps_per_step": swaps_dev,
                          "fused_exchanges_per_step": fused_dev, "swap_GB_per_gpu_per_step": swap_gb_dev,
+                         "overlapped_exchanges_per_step": (st_overlapped / args.steps),
                          "exchange_ms_per_step": exchange_ms,
                          "exchange_GBps_per_gpu_per_direction": (swap_gb_dev / (exchange_ms * 1e-3) if exchange_ms else None),
                          "nvlink_peak_GBps_per_direction": 900.0},

@@ -131,6 +131,35 @@ class DeviceState:
         self.passes_launched += 1
         self.gates_applied += len(ops)
 
+    def apply_pass_sub(self, tile_qubits, ops, tail, fixed_qubits, pattern, max_sms=0):
+        """One pass restricted to the sub-block whose qubits ``fixed_qubits[i]`` read bit i of ``pattern``, on at most
+        ``max_sms`` SMs (qsv_apply_pass_sub)."""
+        gates = (_lib.QsvGate * max(1, len(ops)))()
+        for i, op in enumerate(ops):
+            _fill_gate(gates[i], op)
+        tail = tail or []
+        tgates = (_lib.QsvGate * max(1, len(tail)))()
+        for i, op in enumerate(tail):
+            _fill_gate(tgates[i], op)
+        with self._ctx():
+            if tail and self._tail_scratch is None:
+                self._tail_scratch = self._torch.empty(int(self.lib.qsv_tail_scratch_bytes()) // 8,
+                                                       dtype=self._torch.float64, device=self.device)
+            scratch = ctypes.c_void_p(self._tail_scratch.data_ptr()) if tail else ctypes.c_void_p(0)
+            _lib.check(self.lib.qsv_apply_pass_sub(self.ptr, self.n, _int32_array(tile_qubits), len(tile_qubits), gates,
+                                                   len(ops), tgates, len(tail), scratch, _int32_array(fixed_qubits),
+                                                   len(fixed_qubits), int(pattern), int(max_sms), self.stream),
+                       "qsv_apply_pass_sub")
+
+    def plan_ops(self, ops, avoid=()):
+        """The passes apply_ops would run for 1-/2-qubit ``ops`` (host only); tile qubits never taken from ``avoid``
+        unless a gate needs them."""
+        return plan_passes(merge_ops(list(ops)), self.n, self.tile_qubits, tails=True, avoid=avoid)
+
+    @property
+    def sm_count(self):
+        return self._torch.cuda.get_device_properties(self.device).multi_processor_count
+
     @staticmethod
     def pass_info(n_qubits, tile_qubits, ops, dest=None):
         """Host-only: how qsv_apply_pass would lower this pass (no GPU needed).  Returns a dict with the

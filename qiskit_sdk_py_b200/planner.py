@@ -190,7 +190,8 @@ def _relabel(op, layout):
 
 
 def plan_passes(ops, n_qubits, tile_qubits=DEFAULT_TILE_QUBITS, max_gates=_lib.MAX_PASS_GATES,
-                max_payload=_lib.MAX_PASS_MATRIX_DOUBLES, layout=None, remap=False, tails=False, schedule=True):
+                max_payload=_lib.MAX_PASS_MATRIX_DOUBLES, layout=None, remap=False, tails=False, schedule=True,
+                avoid=()):
     """Group ``ops`` (GateOps on LOGICAL qubits, <= 2 qubits each) into passes.
 
     Frontier-greedy over the gate dependency DAG: a gate is *ready* when it is the first pending gate
@@ -221,6 +222,7 @@ def plan_passes(ops, n_qubits, tile_qubits=DEFAULT_TILE_QUBITS, max_gates=_lib.M
         n_low = 0  # tiny tiles (tests): no pinned low bits
     remap = remap and n_qubits > tile_size and n_low > 0
 
+    avoid_set = set(avoid)
     queues = {}
     for idx, op in enumerate(ops):
         for q in op.qubits:
@@ -269,7 +271,9 @@ def plan_passes(ops, n_qubits, tile_qubits=DEFAULT_TILE_QUBITS, max_gates=_lib.M
         far = len(ops) + 1
         # fill the tile: qubits needed soonest first (they can be made resident), then the lowest bits
         if len(used) < tile_size:
-            cand = sorted((q for q in range(n_qubits) if q not in used),
+            # ``avoid``: qubits that must stay outside the tile when no gate needs them (the fixed qubits of a
+            # sub-block pass, qsv_apply_pass_sub)
+            cand = sorted((q for q in range(n_qubits) if q not in used and q not in avoid_set),
                           key=lambda q: (next_use.get(q, far), layout[q]))
             used |= set(cand[: tile_size - len(used)])
         tile_log = sorted(used, key=lambda q: layout[q])

@@ -75,6 +75,24 @@ class FakeState:
         self.passes_launched += 1
         self.gates_applied += len(ops) + len(tail)
 
+    def plan_ops(self, ops, avoid=()):
+        return plan_passes(merge_ops(list(ops)), self.n, self.tile_qubits, tails=True, avoid=avoid)
+
+    def apply_pass_sub(self, tile_qubits, ops, tail, fixed_qubits, pattern, max_sms=0):
+        """The contract of qsv_apply_pass_sub: only the amplitudes whose fixed qubits read ``pattern`` change; the
+        fixed qubits are neither tile qubits nor gate qubits."""
+        assert not set(fixed_qubits) & set(tile_qubits)
+        assert len(tile_qubits) == min(self.n, self.tile_qubits)
+        before = self.vec.copy()
+        for op in list(ops) + list(tail or []):
+            assert not set(op.qubits) & set(fixed_qubits)
+            self._apply(op)
+        idx = np.arange(self.vec.size)
+        keep = np.ones(self.vec.size, dtype=bool)
+        for i, q in enumerate(fixed_qubits):
+            keep &= ((idx >> q) & 1) == ((pattern >> i) & 1)
+        self.vec = np.where(keep, self.vec, before)
+
     def prob_qubit(self, qubit):
         p = np.abs(self.vec) ** 2
         idx = np.arange(p.size)

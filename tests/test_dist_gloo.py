@@ -349,3 +349,50 @@ def test_bench_parity_gate(tmp_path, world):
     mp.spawn(_parity_gate_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     res = np.load(os.path.join(str(tmp_path), "gate_%d.npy" % world))
     assert res[0] >= 5
+
+
+def _overlap_worker(rank, world, port, n, out_dir):
+    for p in (ROOT, os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from fake_state import FakeState
+    from oracle import basicaer_oracle as orc
+    from qiskit_sdk_py_b200 import _lib, circuits, lower
+    from qiskit_sdk_py_b200.dist import ShardedState
+
+    ins = circuits.quantum_volume_instructions(n, 6, 5) + circuits.random_basis_instructions(n, 6, 9)
+    ops = [o for o in (lower.lower_gate(i["name"], i["qubits"], i.get("params")) for i in ins) if o is not None]
+    results = []
+    for overlap in (True, False):
+        st = ShardedState(n, lambda k: FakeState(k, tile_qubits=5), chunk_amps=16, overlap=overlap)
+        st.MIN_OVERLAP_GATES = 2
+        st.init_basis0()
+        st.apply_ops(ops)
+        results.append((st.gather_statevector(), st.overlapped_exchanges, st.swaps))
+    ref = np.zeros(2 ** n, dtype=complex)
+    ref[0] = 1.0
+    for o in ops:
+        mat = np.diag(o.matrix) if o.kind in (_lib.GATE_DIAG1, _lib.GATE_DIAG2) else \
+            orc.cx_gate_matrix() if o.kind == _lib.GATE_CX else o.matrix
+        ref = orc.apply_unitary(ref.reshape([2] * n), mat, list(o.qubits)).reshape(-1)
+    assert np.max(np.abs(results[0][0] - ref)) < 1e-12
+    assert np.max(np.abs(results[1][0] - ref)) < 1e-12
+    assert results[0][1] > 0, "the circuit should have had exchanges with late passes to overlap"
+    assert results[1][1] == 0
+    if rank == 0:
+        np.save(os.path.join(out_dir, "ovl_%d.npy" % world), np.array([results[0][1], results[0][2]]))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n", [(2, 11), (4, 12)])
+def test_exchange_overlapped_with_commuting_passes(tmp_path, world, n):
+    """ShardedState with overlap=True holds back the locally runnable gates that commute with the coming exchange
+    (no successor-or-self on a swapped bit) and applies them sub-block by sub-block between the partial exchanges
+    (qsv_apply_pass_sub + one partner per step): same state as the oracle and as the plain schedule."""
+    port = _free_port()
+    mp.spawn(_overlap_worker, args=(world, port, n, str(tmp_path)), nprocs=world, join=True)
+    res = np.load(os.path.join(str(tmp_path), "ovl_%d.npy" % world))
+    assert res[0] > 0

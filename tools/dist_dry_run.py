@@ -16,6 +16,7 @@ class CountingShard:
     def __init__(self, n):
         self.n = n
         self.passes = []  # (gates, kernel ops, fused blocks)
+        self.late = []    # ... of the passes that ran under an exchange
 
     def init_basis0(self, phase=1.0):
         pass
@@ -23,10 +24,22 @@ class CountingShard:
     def scale(self, f):
         pass
 
+    tile_qubits = DEFAULT_TILE_QUBITS
+    passes_launched = gates_applied = 0
+
     def apply_ops(self, ops):
         for p in plan_passes(merge_ops(ops), self.n, DEFAULT_TILE_QUBITS, tails=True):
             info = DeviceState.pass_info(self.n, p.tile_qubits, p.ops)
             self.passes.append((len(p.ops), info["ops"], info["fused3"]))
+
+    def plan_ops(self, ops, avoid=()):
+        return plan_passes(merge_ops(list(ops)), self.n, DEFAULT_TILE_QUBITS, tails=True, avoid=avoid)
+
+    def apply_pass_sub(self, tile_qubits, ops, tail, fixed_qubits, pattern, max_sms=0):
+        if pattern == 0:  # count every late pass once (it runs on all 2^k sub-blocks = once over the shard)
+            info = DeviceState.pass_info(self.n, tile_qubits, ops)
+            self.passes.append((len(ops), info["ops"], info["fused3"]))
+            self.late.append((len(ops), info["ops"], info["fused3"]))
 
 
 class DryState(ShardedState):
@@ -41,6 +54,20 @@ class DryState(ShardedState):
         self.pos = list(range(n))
         self.swaps = self.fused_exchanges = self.swap_bytes = 0
         self.events = []
+        self.overlap = os.environ.get("QSV_DRY_OVERLAP", "1") == "1"
+        self.overlapped_exchanges = 0
+        self._peers = self._comm_stream = None
+        self._xch_events = []
+        self.late_per_exchange = []
+
+    def _swap_staged(self, lbits, beta, peers):
+        pass
+
+    def _exchange_overlapped(self, pairs, late):
+        n0 = len(self.shard.late)
+        super()._exchange_overlapped(pairs, late)
+        self.late_per_exchange.append((len(pairs), len(late), len(self.shard.late) - n0))
+        self.events.append(("xo", len(pairs), len(self.shard.passes)))
 
     def swap_global_local(self, pg, pl):
         self.swap_many([(pg, pl)], force=True)
@@ -85,6 +112,11 @@ if __name__ == "__main__":
           "%d swaps in %d exchanges, %.1f GB per rank" % (n, world, n_local, len(ops), len(ps), len(ops) / len(ps),
           sum(p[1] for p in ps), sum(p[2] for p in ps), st.swaps, st.fused_exchanges, st.swap_bytes / 1e9))
     print("estimate: passes %.2f s + exchanges %.2f s = %.2f s" % (t_pass / 1e3, t_x / 1e3, (t_pass + t_x) / 1e3))
+    if st.late_per_exchange:
+        t_late, _ = estimate(st.shard.late, 0, n_local)
+        print("overlap: %d of %d exchanges ran under late passes; (swapped qubits, late gates, late passes) per exchange: %s; "
+              "late passes ~%.2f s in total" % (st.overlapped_exchanges, st.fused_exchanges + (st.swaps if world == 2 else 0),
+                                               st.late_per_exchange, t_late / 1e3))
     hist = {}
     for p in ps:
         hist[p[0]] = hist.get(p[0], 0) + 1

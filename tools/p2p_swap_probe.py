@@ -59,7 +59,7 @@ def timed(pairs, ctas, reps=3):
 
 for unroll_flag, unroll in ((0, 4), (1 << 12, 8), (2 << 12, 2)):
     lib.qsv_debug_set_flags(unroll_flag)
-    for ctas in (74, 148, 296, 592):
+    for ctas in (16, 32, 64, 148, 296):
         for bit in (n_local - 1, n_local // 2, 5):
             pairs = [(n_local + j, bit - j) for j in range(g)]
             ms, gb = timed(pairs, ctas)
