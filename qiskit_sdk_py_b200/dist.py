@@ -392,7 +392,9 @@ class ShardedState:
                     run.append(loc)
             pairs = self._plan_swap(deferred) if deferred else []
             late = []
-            if pairs and self.overlap:
+            # with k swapped qubits a fraction 1 - 2^-k of the late work runs under the transfers: worth the extra
+            # (less fused) passes from k = 2 on; a pairwise swap (k = 1) hides too little (measured on 2 GPUs)
+            if len(pairs) >= self.MIN_OVERLAP_SWAPS and self.overlap:
                 run, late = self._split_for_overlap(run, [pl for _, pl in pairs])
             self._apply_local(run)
             if late:
@@ -402,6 +404,7 @@ class ShardedState:
             remaining = deferred
 
     # -- exchange overlapped with the passes that commute with it ---------------------------------------
+    MIN_OVERLAP_SWAPS = 2    # overlap only fused exchanges of at least this many qubits
     MIN_OVERLAP_GATES = 6    # fewer late gates than this: not worth splitting the passes
     OVERLAP_TARGET_GATES = 30  # ... and no more than about four passes' worth (one exchange takes 2-4 pass times)
     EXCHANGE_SMS = 16        # SMs left to the exchange kernel while sub-block passes run
@@ -944,6 +947,8 @@ def bench_main(args, bench):
     n_gates = len(ops)
     overlap = os.environ.get("QSV_DIST_OVERLAP", "1") == "1"  # A/B knob of tools/: exchanges without late passes
     st = ShardedState(n, factory, chunk_amps=chunk_amps, overlap=overlap)
+    if os.environ.get("QSV_DIST_OVERLAP_GATES"):
+        st.OVERLAP_TARGET_GATES = int(os.environ["QSV_DIST_OVERLAP_GATES"])
     uniforms = np.random.RandomState(sim_seed).random_sample(shots)
 
     def step():

@@ -30,6 +30,7 @@ def main():
         ops = [lower.lower_gate(i["name"], i["qubits"], i.get("params")) for i in ins]
         ops = [o for o in ops if o is not None]
         st = ShardedState(n, DeviceState, chunk_amps=1 << 9)
+        st.MIN_OVERLAP_SWAPS = 1  # exercise the overlapped exchange (sub-block passes + per-partner swaps) on 2 ranks too
         st.init_basis0(np.exp(0.3j))
         st.apply_ops(ops)
         ref = np.zeros(2 ** n, dtype=complex)

@@ -369,6 +369,7 @@ def _overlap_worker(rank, world, port, n, out_dir):
     for overlap in (True, False):
         st = ShardedState(n, lambda k: FakeState(k, tile_qubits=5), chunk_amps=16, overlap=overlap)
         st.MIN_OVERLAP_GATES = 2
+        st.MIN_OVERLAP_SWAPS = 1
         st.init_basis0()
         st.apply_ops(ops)
         results.append((st.gather_statevector(), st.overlapped_exchanges, st.swaps))
