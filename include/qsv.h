@@ -161,6 +161,21 @@ int qsv_prob_qubit(const double* sv, int n_qubits, int qubit, void* ws, double* 
 int qsv_collapse(double* sv, int n_qubits, int qubit, int outcome, double prob, int is_reset,
                  void* stream);
 
+/* Shot-batched mid-circuit operations.  The reference simulates a circuit with mid-circuit
+ * measure / reset / conditionals once per shot (qasm_simulator.py:512-531); the host instead keeps 2^n_shot_qubits
+ * shots side by side in ONE vector of n_total = n + n_shot_qubits qubits (shot number = the top index bits): gates act
+ * on all shots through the ordinary passes, qsv_marginal over (qubit, shot qubits) gives every shot's outcome
+ * probabilities in one launch, and these two entry points do the per-shot parts:
+ *   qsv_collapse_batch  _add_qasm_measure / _add_qasm_reset (:247-253, :265-273) with a different outcome and
+ *                       1/sqrt(p) per shot (host arrays of 2^n_shot_qubits entries)
+ *   qsv_apply_masked    a 1- or 2-qubit gate on the shots whose mask byte is non-zero (conditional gates, :527-540)
+ * dev_ws: qsv_batch_workspace_bytes(n_shot_qubits) bytes of device memory.  Both synchronise the stream. */
+size_t qsv_batch_workspace_bytes(int n_shot_qubits);
+int qsv_collapse_batch(double* sv, int n_total, int n_shot_qubits, int qubit, const unsigned char* host_outcomes,
+                       const double* host_scales, int is_reset, void* dev_ws, void* stream);
+int qsv_apply_masked(double* sv, int n_total, int n_shot_qubits, const qsv_gate_t* gate, const unsigned char* host_mask,
+                     void* dev_ws, void* stream);
+
 /* Marginal probabilities of m measured qubits: probs[s] = sum |psi_i|^2 over all i whose bit
  * measured_sorted[pos] equals bit pos of s.  Replaces np.sum(np.abs(psi)**2, axis=...) in
  * _add_sample_measure (qasm_simulator.py:202-209).  dev_probs holds 2^m doubles. */

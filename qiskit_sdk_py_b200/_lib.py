@@ -77,6 +77,9 @@ SIGNATURES = {
     "qsv_reduce_workspace_bytes": (_c_size_t, []),
     "qsv_prob_qubit": (_c_int, [_c_void_p, _c_int, _c_int, _c_void_p, _p_double, _c_void_p]),
     "qsv_collapse": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_double, _c_int, _c_void_p]),
+    "qsv_batch_workspace_bytes": (_c_size_t, [_c_int]),
+    "qsv_collapse_batch": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_void_p]),
+    "qsv_apply_masked": (_c_int, [_c_void_p, _c_int, _c_int, ctypes.POINTER(QsvGate), _c_void_p, _c_void_p, _c_void_p]),
     "qsv_marginal_workspace_bytes": (_c_size_t, [_c_int, _c_int]),
     "qsv_marginal": (_c_int, [_c_void_p, _c_int, _p_int32, _c_int, _c_void_p, _c_void_p, _c_void_p]),
     "qsv_sample_workspace_bytes": (_c_size_t, [_c_int, _c_int]),

@@ -116,8 +116,11 @@ swap_p2p_kernel(double2* __restrict__ mine, const __grid_constant__ P2PDesc d) {
   const u64 dep_beta = p2p_deposit(d, d.beta);
   const u64 stride = (u64)gridDim.x * blockDim.x;
   const u64 t0 = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  for (uint32_t lam = 0; lam < (1u << d.k); lam++) {
-    if (lam == d.beta) continue;
+  // XOR schedule: in step j every rank works on its partner beta ^ j -- a perfect matching of the 2^k ranks per step,
+  // so no rank's memory or NVLink port is the target of more than one partner at a time (a common order 0, 1, 2, ...
+  // has everybody hit rank 0 first: measured 280 GB/s instead of 650 on 4 GPUs)
+  for (uint32_t j = 1; j < (1u << d.k); j++) {
+    const uint32_t lam = d.beta ^ j;
     if (!d.peer[lam]) continue;  // a partial exchange: only the peers given
     double2* __restrict__ theirs = d.peer[lam];
     const u64 dep_lam = p2p_deposit(d, lam);

@@ -110,6 +110,74 @@ expval_pauli_kernel(const double2* __restrict__ sv, u64 n_amps, u64 z_mask, u64 
   }
 }
 
+// ---- shot-batched mid-circuit operations: the top `b` qubits of the vector number independent shots ----------
+// The reference re-runs a circuit with mid-circuit measure / reset / conditionals once per shot
+// (qasm_simulator.py:512-531, :561-614).  Here 2^b shots are simulated side by side as one (n + b)-qubit vector:
+// gates on the n circuit qubits act on every shot at once through the ordinary pass kernel; the per-shot parts are
+// these two kernels.
+__global__ void __launch_bounds__(kThreads)
+collapse_batch_kernel(double2* __restrict__ sv, u64 n_pairs, int q, int shot_shift, const unsigned char* __restrict__ outcome,
+                      const double* __restrict__ scale, int is_reset) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  const u64 low_mask = (1ull << q) - 1ull;
+  for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j < n_pairs; j += stride) {
+    const u64 i0 = ((j >> q) << (q + 1)) | (j & low_mask);  // bit q clear
+    const u64 i1 = i0 | (1ull << q);
+    const u64 shot = i0 >> shot_shift;
+    const int out = outcome[shot];
+    const double f = scale[shot];
+    const double2 a0 = sv[i0], a1 = sv[i1];
+    double2 r0, r1 = make_double2(0.0, 0.0);
+    if (out == 0) {
+      r0 = make_double2(a0.x * f, a0.y * f);                      // diag(1/sqrt(p), 0)   (:249, :269)
+    } else if (is_reset) {
+      r0 = make_double2(a1.x * f, a1.y * f);                      // [[0, 1/sqrt(p)], [0, 0]]   (:272)
+    } else {
+      r0 = make_double2(0.0, 0.0);
+      r1 = make_double2(a1.x * f, a1.y * f);                      // diag(0, 1/sqrt(p))   (:251)
+    }
+    sv[i0] = r0;
+    sv[i1] = r1;
+  }
+}
+
+// a 1- or 2-qubit gate (dense 2x2 / 4x4 complex, row-major) on the shots whose mask byte is set (conditional gates)
+struct MaskedGate {
+  int32_t k, q0, q1, shot_shift;
+  double m[32];
+};
+
+__global__ void __launch_bounds__(kThreads)
+apply_masked_kernel(double2* __restrict__ sv, u64 n_groups, const __grid_constant__ MaskedGate g,
+                    const unsigned char* __restrict__ mask) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  const int lo = g.k == 2 ? (g.q0 < g.q1 ? g.q0 : g.q1) : g.q0, hi = g.k == 2 ? (g.q0 < g.q1 ? g.q1 : g.q0) : -1;
+  for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j < n_groups; j += stride) {
+    u64 base = ((j >> lo) << (lo + 1)) | (j & ((1ull << lo) - 1ull));
+    if (hi >= 0) base = ((base >> hi) << (hi + 1)) | (base & ((1ull << hi) - 1ull));
+    if (!mask[base >> g.shot_shift]) continue;
+    const int dim = 1 << g.k;
+    double2 a[4], r[4];
+    for (int c = 0; c < dim; c++) {
+      u64 idx = base;
+      if (c & 1) idx |= 1ull << g.q0;
+      if (c & 2) idx |= 1ull << g.q1;
+      a[c] = sv[idx];
+    }
+    for (int rr = 0; rr < dim; rr++) {
+      double2 acc = make_double2(0.0, 0.0);
+      for (int c = 0; c < dim; c++) cfma(acc, make_double2(g.m[2 * (dim * rr + c)], g.m[2 * (dim * rr + c) + 1]), a[c]);
+      r[rr] = acc;
+    }
+    for (int c = 0; c < dim; c++) {
+      u64 idx = base;
+      if (c & 1) idx |= 1ull << g.q0;
+      if (c & 2) idx |= 1ull << g.q1;
+      sv[idx] = r[c];
+    }
+  }
+}
+
 // ---- marginal over m measured qubits: grid = (parts, bins) ----
 struct MargDesc {
   int32_t n, m, log2_parts, pad;
@@ -758,6 +826,74 @@ int qsv_expval_pauli(const double* sv, int n, uint64_t z_mask, uint64_t x_mask, 
   QSV_CUDA(cudaMemcpyAsync(out, partial + 2 * kReduceBlocks, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
   QSV_CUDA(cudaStreamSynchronize(s));
   *host_out = out[0];
+  return 0;
+}
+
+int qsv_collapse_batch(double* sv, int n_total, int n_shot_qubits, int qubit, const unsigned char* host_outcomes,
+                       const double* host_scales, int is_reset, void* dev_ws, void* stream) {
+  const int n = n_total - n_shot_qubits;
+  if (!sv || !host_outcomes || !host_scales || !dev_ws || n_shot_qubits < 0 || n < 1 || n_total > 40 || qubit < 0 ||
+      qubit >= n)
+    return fail(QSV_EINVAL, "qsv_collapse_batch: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t shots = (size_t)1 << n_shot_qubits;
+  double* d_scale = reinterpret_cast<double*>(dev_ws);
+  unsigned char* d_out = reinterpret_cast<unsigned char*>(d_scale + shots);
+  QSV_CUDA(cudaMemcpyAsync(d_scale, host_scales, shots * sizeof(double), cudaMemcpyHostToDevice, s));
+  QSV_CUDA(cudaMemcpyAsync(d_out, host_outcomes, shots, cudaMemcpyHostToDevice, s));
+  const u64 n_pairs = 1ull << (n_total - 1);
+  const int blocks = (int)std::max<u64>(1, std::min<u64>((n_pairs + kThreads - 1) / kThreads, (u64)sm_count() * 16));
+  collapse_batch_kernel<<<blocks, kThreads, 0, s>>>(reinterpret_cast<double2*>(sv), n_pairs, qubit, n, d_out, d_scale,
+                                                    is_reset);
+  QSV_LAUNCHED();
+  QSV_CUDA(cudaStreamSynchronize(s));  // the host arrays may be pageable temporaries
+  return 0;
+}
+
+size_t qsv_batch_workspace_bytes(int n_shot_qubits) {
+  if (n_shot_qubits < 0 || n_shot_qubits > 30) return 0;
+  return ((size_t)1 << n_shot_qubits) * (sizeof(double) + 1) + 256;
+}
+
+int qsv_apply_masked(double* sv, int n_total, int n_shot_qubits, const qsv_gate_t* gate, const unsigned char* host_mask,
+                     void* dev_ws, void* stream) {
+  const int n = n_total - n_shot_qubits;
+  if (!sv || !gate || !host_mask || !dev_ws || n_shot_qubits < 0 || n < 1 || n_total > 40)
+    return fail(QSV_EINVAL, "qsv_apply_masked: bad arguments");
+  MaskedGate g;
+  memset(&g, 0, sizeof(g));
+  g.shot_shift = n;
+  g.q0 = gate->q0;
+  g.q1 = gate->q1;
+  const bool two = gate->kind == QSV_GATE_DENSE2 || gate->kind == QSV_GATE_DIAG2 || gate->kind == QSV_GATE_CX;
+  g.k = two ? 2 : 1;
+  if (g.q0 < 0 || g.q0 >= n || (two && (g.q1 < 0 || g.q1 >= n || g.q1 == g.q0)))
+    return fail(QSV_EINVAL, "qsv_apply_masked: gate qubit out of range");
+  switch (gate->kind) {  // every kind as a dense matrix in its own qubit order (q0 = index bit 0)
+    case QSV_GATE_DENSE1: memcpy(g.m, gate->m, sizeof(double) * 8); break;
+    case QSV_GATE_DENSE2: memcpy(g.m, gate->m, sizeof(double) * 32); break;
+    case QSV_GATE_DIAG1:
+      for (int i = 0; i < 2; i++) { g.m[2 * (2 * i + i)] = gate->m[2 * i]; g.m[2 * (2 * i + i) + 1] = gate->m[2 * i + 1]; }
+      break;
+    case QSV_GATE_DIAG2:
+      for (int i = 0; i < 4; i++) { g.m[2 * (4 * i + i)] = gate->m[2 * i]; g.m[2 * (4 * i + i) + 1] = gate->m[2 * i + 1]; }
+      break;
+    case QSV_GATE_CX: {
+      static const int to[4] = {0, 3, 2, 1};  // control = index bit 0 (basicaertools.py:70-72)
+      for (int c = 0; c < 4; c++) g.m[2 * (4 * to[c] + c)] = 1.0;
+      break;
+    }
+    default: return fail(QSV_EINVAL, "qsv_apply_masked: unknown gate kind");
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t shots = (size_t)1 << n_shot_qubits;
+  unsigned char* d_mask = reinterpret_cast<unsigned char*>(dev_ws);
+  QSV_CUDA(cudaMemcpyAsync(d_mask, host_mask, shots, cudaMemcpyHostToDevice, s));
+  const u64 n_groups = 1ull << (n_total - g.k);
+  const int blocks = (int)std::max<u64>(1, std::min<u64>((n_groups + kThreads - 1) / kThreads, (u64)sm_count() * 16));
+  apply_masked_kernel<<<blocks, kThreads, 0, s>>>(reinterpret_cast<double2*>(sv), n_groups, g, d_mask);
+  QSV_LAUNCHED();
+  QSV_CUDA(cudaStreamSynchronize(s));
   return 0;
 }
 

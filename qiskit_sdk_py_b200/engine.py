@@ -276,6 +276,39 @@ class DeviceState:
         self.passes_launched += 1
         self.gates_applied += 1
 
+    # -- shot-batched mid-circuit operations: the top ``n_shot_qubits`` of this state number independent shots ----
+    def _batch_ws(self, n_shot_qubits):
+        need = int(self.lib.qsv_batch_workspace_bytes(n_shot_qubits)) // 8 + 8
+        if getattr(self, "_batch_scratch", None) is None or self._batch_scratch.numel() < need:
+            self._batch_scratch = self._torch.empty(need, dtype=self._torch.float64, device=self.device)
+        return ctypes.c_void_p(self._batch_scratch.data_ptr())
+
+    def collapse_batch(self, n_shot_qubits, qubit, outcomes, scales, is_reset=False):
+        """Per-shot projective collapse of ``qubit``: shot s keeps outcome ``outcomes[s]`` scaled by ``scales[s]``
+        (= 1/sqrt(p_s)); with ``is_reset`` the |1> half moves to |0> (qsv_collapse_batch)."""
+        out = np.ascontiguousarray(outcomes, dtype=np.uint8)
+        sc = np.ascontiguousarray(scales, dtype=np.float64)
+        assert out.size == sc.size == 1 << n_shot_qubits
+        with self._ctx():
+            _lib.check(self.lib.qsv_collapse_batch(self.ptr, self.n, int(n_shot_qubits), int(qubit),
+                                                   ctypes.c_void_p(out.ctypes.data), ctypes.c_void_p(sc.ctypes.data),
+                                                   1 if is_reset else 0, self._batch_ws(n_shot_qubits), self.stream),
+                       "qsv_collapse_batch")
+        self.passes_launched += 1
+
+    def apply_masked(self, n_shot_qubits, op, mask):
+        """The 1-/2-qubit GateOp ``op`` on the shots whose ``mask`` entry is true (qsv_apply_masked)."""
+        gate = _lib.QsvGate()
+        _fill_gate(gate, op)
+        m = np.ascontiguousarray(mask, dtype=np.uint8)
+        assert m.size == 1 << n_shot_qubits
+        with self._ctx():
+            _lib.check(self.lib.qsv_apply_masked(self.ptr, self.n, int(n_shot_qubits), ctypes.byref(gate),
+                                                 ctypes.c_void_p(m.ctypes.data), self._batch_ws(n_shot_qubits),
+                                                 self.stream), "qsv_apply_masked")
+        self.passes_launched += 1
+        self.gates_applied += 1
+
     def marginal(self, measured_sorted):
         """Device tensor of 2^m marginal probabilities (bit pos <-> measured_sorted[pos])."""
         torch = self._torch

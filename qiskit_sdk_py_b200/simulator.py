@@ -388,6 +388,131 @@ class QasmSimulatorB200:
                 lowered.append(None)
         return lowered
 
+    # -- shot-batched execution of circuits that cannot be sampled --------------------
+    MAX_BATCH_STATE_QUBITS = 22   # circuit qubits + log2(shots per batch): 64 MiB of amplitudes
+    MIN_BATCH_BITS = 3
+
+    def _shot_batch_bits(self, instructions, lowered):
+        """log2 of the shots simulated side by side, or 0 if this experiment runs shot by shot.  Batched: several
+        shots, no sampling, a state type with the per-shot kernels (the single-GPU engine), no initial statevector,
+        and every measure / reset / bfunc unconditional -- then each shot draws the same number of random numbers and
+        the reference's stream (shot after shot, qasm_simulator.py:512-519) can be dealt out in advance."""
+        if self._shots < (1 << self.MIN_BATCH_BITS) or self.SHOW_FINAL_STATE or self._initial_statevector is not None:
+            return 0
+        bits = min(int(np.floor(np.log2(self._shots))), self.MAX_BATCH_STATE_QUBITS - self._number_of_qubits)
+        if bits < self.MIN_BATCH_BITS or self._number_of_cmembits > 62:
+            return 0
+        for operation, low in zip(instructions, lowered):
+            name = operation["name"]
+            if name in ("measure", "reset", "bfunc"):
+                if operation.get("conditional", None) is not None:
+                    return 0
+            elif low is None and name not in ("id", "u0", "barrier"):
+                return 0  # unknown instruction: let the shot-by-shot path raise the reference's error
+            elif low is not None and (low.kind == "densek" and operation.get("conditional", None) is not None):
+                return 0
+        ok = hasattr(self._state, "collapse_batch") and hasattr(self._state, "apply_masked")
+        return bits if ok else 0
+
+    def _run_shots_batched(self, instructions, lowered, global_phase, bits):
+        """All shots of a non-sampled experiment, 2^bits at a time, as ONE (n + bits)-qubit vector whose top qubits
+        number the shots: gates act on every shot through the ordinary fused passes; a measure / reset reads all
+        shots' outcome probabilities with one marginal (qubit + shot qubits), decides every shot's outcome with the
+        random number the reference would have drawn for it (shot s, k-th draw = element s * D + k of the stream),
+        and collapses all shots in one launch; conditional gates run on the shots whose classical bits satisfy the
+        condition (qasm_simulator.py:512-614).  Returns the memory list (one hex string per shot, shot order)."""
+        from .lower import GateOp
+
+        n = self._number_of_qubits
+        batch = 1 << bits
+        shot_qubits = list(range(n, n + bits))
+        draws = sum(1 for op in instructions if op["name"] in ("measure", "reset"))
+        fan = np.array([[1, 0], [1, 0]], dtype=complex)  # |0> -> |0> + |1>: one copy of |0..0> per shot
+        phase = complex(np.exp(1j * global_phase))
+        memory = []
+        done = 0
+        self._state = self._state_factory(n + bits)
+        while done < self._shots:
+            live = min(batch, self._shots - done)
+            rand = self._local_random.rand(live * draws).reshape(live, draws) if draws else None
+            cmem = np.zeros(batch, dtype=np.int64)
+            creg = np.zeros(batch, dtype=np.int64)
+            self._state.init_basis0(phase)
+            pending = [GateOp(lower._lib.GATE_DENSE1, [q], fan) for q in shot_qubits]
+            draw = 0
+            for operation, low in zip(instructions, lowered):
+                name = operation["name"]
+                conditional = operation.get("conditional", None)
+                if low is not None:
+                    if conditional is None:
+                        pending.append(low)
+                    else:
+                        self._flush(pending)
+                        mask = self._condition_mask(conditional, cmem, creg)
+                        if mask.any():
+                            self._state.apply_masked(bits, low, mask)
+                elif name in ("id", "u0", "barrier"):
+                    pass
+                elif name in ("measure", "reset"):
+                    self._flush(pending)
+                    qubit = operation["qubits"][0]
+                    probs = self._state.marginal([qubit] + shot_qubits).cpu().numpy().reshape(batch, 2)
+                    r = np.ones(batch)
+                    r[:live] = rand[:, draw]
+                    draw += 1
+                    outcome = np.where(r < probs[:, 0], 0, 1)           # _get_measure_outcome :178-182
+                    outcome = np.where(probs[np.arange(batch), outcome] > 0.0, outcome, 1 - outcome)  # unused slots
+                    chosen = probs[np.arange(batch), outcome]
+                    self._state.collapse_batch(bits, qubit, outcome, 1.0 / np.sqrt(chosen), is_reset=(name == "reset"))
+                    if name == "measure":
+                        cmembit = operation["memory"][0]
+                        cmem = (cmem & ~np.int64(1 << cmembit)) | (outcome.astype(np.int64) << cmembit)
+                        if "register" in operation:
+                            cregbit = operation["register"][0]
+                            creg = (creg & ~np.int64(1 << cregbit)) | (outcome.astype(np.int64) << cregbit)
+                elif name == "bfunc":
+                    mask = int(operation["mask"], 16)
+                    val = int(operation["val"], 16)
+                    compared = (creg & mask) - val
+                    relation = operation["relation"]
+                    if relation == "==":
+                        out = compared == 0
+                    elif relation == "!=":
+                        out = compared != 0
+                    elif relation == "<":
+                        out = compared < 0
+                    elif relation == "<=":
+                        out = compared <= 0
+                    elif relation == ">":
+                        out = compared > 0
+                    elif relation == ">=":
+                        out = compared >= 0
+                    else:
+                        raise BasicAerError("Invalid boolean function relation.")
+                    cregbit = operation["register"]
+                    creg = (creg & ~np.int64(1 << cregbit)) | (out.astype(np.int64) << cregbit)
+                    cmembit = operation.get("memory", None)
+                    if cmembit is not None:
+                        cmem = (cmem & ~np.int64(1 << cmembit)) | (out.astype(np.int64) << cmembit)
+            self._flush(pending)
+            memory.extend(hex(int(v)) for v in cmem[:live])
+            done += live
+        return memory
+
+    @staticmethod
+    def _condition_mask(conditional, cmem, creg):
+        """_passes_condition (qasm_simulator.py:527-540) for every shot of a batch."""
+        if isinstance(conditional, int) and not isinstance(conditional, bool):
+            return ((creg >> conditional) & 1).astype(bool)
+        mask = int(conditional["mask"], 16)
+        if mask <= 0:
+            return np.ones(cmem.size, dtype=bool)
+        value = cmem & mask
+        while (mask & 0x1) == 0:
+            mask >>= 1
+            value = value >> 1
+        return value == int(conditional["val"], 16)
+
     def run_experiment(self, experiment):
         """qasm_simulator.py:459-653."""
         start = time.time()
@@ -428,6 +553,11 @@ class QasmSimulatorB200:
             measure_sample_ops = []
         else:
             shots = self._shots
+
+        batch_bits = 0 if self._sample_measure else self._shot_batch_bits(instructions, lowered)
+        if batch_bits:
+            memory = self._run_shots_batched(instructions, lowered, global_phase, batch_bits)
+            shots = 0  # the per-shot loop below is skipped
 
         # The gate-only, unconditional prefix of the circuit is shot-independent and draws no random
         # numbers: simulate it once and restore it for every further shot.
@@ -517,6 +647,8 @@ class QasmSimulatorB200:
                 else:
                     memory.append(hex(self._classical_memory))
 
+        if batch_bits and self._number_of_cmembits == 0:
+            memory = []
         data = {"counts": dict(Counter(memory))}
         if self._memory:
             data["memory"] = memory
@@ -529,6 +661,7 @@ class QasmSimulatorB200:
         self.last_stats = {
             "passes": getattr(self._state, "passes_launched", None),
             "gates": getattr(self._state, "gates_applied", None),
+            "shot_batch_bits": batch_bits,
         }
         self._state = None
         end = time.time()

@@ -109,6 +109,33 @@ class FakeState:
             mat = [[0, 0], [0, s]]
         self.vec = orc.apply_unitary(self.vec.reshape([2] * self.n), mat, [qubit]).reshape(-1)
 
+    # shot-batched mid-circuit operations (engine.DeviceState.collapse_batch / apply_masked)
+    def collapse_batch(self, n_shot_qubits, qubit, outcomes, scales, is_reset=False):
+        n = self.n - n_shot_qubits
+        vec = self.vec.reshape(1 << n_shot_qubits, 1 << n).copy()
+        idx = np.arange(1 << n)
+        bit = (idx >> qubit) & 1
+        for s in range(1 << n_shot_qubits):
+            out, f = int(outcomes[s]), float(scales[s])
+            row = vec[s]
+            if is_reset and out == 1:
+                new = np.zeros_like(row)
+                new[idx[bit == 0]] = row[idx[bit == 0] | (1 << qubit)] * f
+            else:
+                new = np.where(bit == out, row * f, 0.0)
+            vec[s] = new
+        self.vec = vec.reshape(-1)
+        self.passes_launched += 1
+
+    def apply_masked(self, n_shot_qubits, op, mask):
+        n = self.n - n_shot_qubits
+        before = self.vec.copy()
+        self._apply(op)
+        keep = np.repeat(np.asarray(mask, dtype=bool), 1 << n)
+        self.vec = np.where(keep, self.vec, before)
+        self.passes_launched += 1
+        self.gates_applied += 1
+
     def scale(self, factor):
         self.vec = self.vec * complex(factor)
 

@@ -190,3 +190,48 @@ def test_midcircuit_measure_reset_conditional_large_shots():
     exp = circuits.make_experiment("mid", 5, ins, memory_slots=4)
     _same_as_oracle("qasm_simulator", circuits.make_qobj(exp, shots=400, seed_simulator=77, memory=True))
     _same_as_oracle("statevector_simulator", circuits.make_qobj(exp, shots=1, seed_simulator=78))
+
+
+@pytest.mark.parametrize("name", ["midcircuit_8", "teleport", "reset_midcircuit", "if_statement",
+                                  "transpiled_init_reset_cond_counts"])
+def test_shot_batched_execution_on_the_gpu(name):
+    """Circuits with mid-circuit measure / reset / conditionals: all shots side by side in one (n + b)-qubit device
+    vector (qsv_marginal over qubit + shot qubits, qsv_collapse_batch, qsv_apply_masked) -- memory and counts identical
+    to the shot-by-shot path and to the reference's recorded output (qasm_simulator.py:512-614)."""
+    import copy
+
+    import golden_io
+    import helpers
+    from qiskit_sdk_py_b200 import _lib, simulator
+
+    case = golden_io.load_case(name)
+    batched = simulator.QasmSimulatorB200()
+    before = _lib.launch_count()
+    res_b = batched.run(copy.deepcopy(case["qobj"]), **case.get("options", {}))
+    launches_b = _lib.launch_count() - before
+    assert batched.last_stats["shot_batch_bits"] >= 3
+    serial = simulator.QasmSimulatorB200()
+    serial.MIN_BATCH_BITS = 99
+    before = _lib.launch_count()
+    res_s = serial.run(copy.deepcopy(case["qobj"]), **case.get("options", {}))
+    launches_s = _lib.launch_count() - before
+    assert res_b["results"][0]["data"] == res_s["results"][0]["data"]
+    helpers.compare_result(res_b, case)
+    assert launches_b * 4 < launches_s, (launches_b, launches_s)  # a few launches per batch instead of per shot
+
+
+def test_shot_batched_wide_circuit_against_oracle():
+    """A 12-qubit mid-circuit experiment, 600 shots in batches of 512 + 88 (partial last batch)."""
+    rng = np.random.RandomState(5)
+    n = 12
+    ins = [circuits.u3(*rng.uniform(0, np.pi, 3), q) for q in range(n)]
+    ins += [circuits.cx(q, q + 1) for q in range(n - 1)]
+    ins += [{"name": "measure", "qubits": [n - 1], "memory": [0], "register": [0]},
+            {"name": "x", "qubits": [2], "conditional": 0},
+            {"name": "reset", "qubits": [5]},
+            circuits.u2(0.2, 0.7, 5), circuits.cx(5, 0),
+            {"name": "bfunc", "mask": "0x1", "relation": "!=", "val": "0x1", "register": 3, "memory": 2},
+            {"name": "u1", "qubits": [7], "params": [0.4], "conditional": 3}]
+    ins += [{"name": "measure", "qubits": [q], "memory": [3 + q], "register": [4 + q]} for q in range(n)]
+    exp = circuits.make_experiment("mid12", n, ins, memory_slots=3 + n)
+    _same_as_oracle("qasm_simulator", circuits.make_qobj(exp, shots=600, seed_simulator=5, memory=True))

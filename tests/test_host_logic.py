@@ -319,3 +319,21 @@ def test_device_statevector_handle_against_oracle():
     assert sum(sv.sample_counts(500, qargs=[0, 5], seed=1).values()) == 500
     sv.evolve([circuits.u3(0.3, 0.2, 0.1, 2)])
     assert abs(sv.norm() - 1.0) < 1e-12
+
+
+@pytest.mark.parametrize("name", ["midcircuit_8", "teleport", "reset_midcircuit", "if_statement",
+                                  "transpiled_init_reset_cond_counts"])
+def test_shot_batched_execution_equals_shot_by_shot(name):
+    """circuits that cannot be sampled run 2^b shots side by side in one (n + b)-qubit vector
+    (per-shot outcomes from the same RandomState stream, per-shot collapse, masked conditional gates) -- memory and
+    counts identical to the shot-by-shot path and to the reference's recorded output (qasm_simulator.py:512-614)."""
+    case = golden_io.load_case(name)
+    batched = simulator.QasmSimulatorB200(state_factory=FakeState, max_qubits=24)
+    res_b = batched.run(copy.deepcopy(case["qobj"]), **case.get("options", {}))
+    assert batched.last_stats["shot_batch_bits"] >= 3
+    serial = simulator.QasmSimulatorB200(state_factory=FakeState, max_qubits=24)
+    serial.MIN_BATCH_BITS = 99
+    res_s = serial.run(copy.deepcopy(case["qobj"]), **case.get("options", {}))
+    assert serial.last_stats["shot_batch_bits"] == 0
+    assert res_b["results"][0]["data"] == res_s["results"][0]["data"]
+    helpers.compare_result(res_b, case)
