@@ -566,6 +566,8 @@ class ShardedState:
                 if use > best_use:
                     best, best_use = lq, use
             if best is None:
+                if pairs:  # tiny shards: this one comes in with a later exchange, after the gates of the others ran
+                    continue
                 raise RuntimeError("no local qubit available to swap out")
             taken.add(best)
             pairs.append((self.pos[q], self.pos[best]))

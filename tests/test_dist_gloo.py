@@ -337,12 +337,13 @@ def _parity_gate_worker(rank, world, port, out_dir):
     assert summary.startswith("golden %d/%d identical" % (len(details), len(details))) and "FAILED" not in summary, summary
     assert "bell_seed42" not in details          # 2 qubits do not leave two local qubits per rank
     assert "midcircuit_8" in details and details["midcircuit_8"]["ok"]
+    assert ("sampler_marginal_subset" in details) and details["sampler_marginal_subset"]["ok"]  # 2 local qubits at world 8
     if rank == 0:
         np.save(os.path.join(out_dir, "gate_%d.npy" % world), np.array([len(details), len(fits)]))
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_bench_parity_gate(tmp_path, world):
     """The golden parity gate bench.py --gpus N runs before its timed region (dist.parity_gate), here over gloo."""
     port = _free_port()
