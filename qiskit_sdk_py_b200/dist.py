@@ -163,8 +163,14 @@ class ShardedState:
 
     def _swap_p2p(self, pairs):
         """The exchange as one in-place NVLink kernel per rank (see qsv_swap_bits_p2p)."""
-        t_begin = self._xch_begin()
         k = len(pairs)
+        if k > 1 and self.n_local - k < 1:
+            # tiny shards (2 local qubits on 8 ranks): a sub-block of one amplitude has no halves for the two partners
+            # to share -- the same permutation as k pairwise swaps (the pairs are disjoint)
+            for pair in pairs:
+                self._swap_p2p([pair])
+            return
+        t_begin = self._xch_begin()
         gbits = [pg - self.n_local for pg, _ in pairs]
         lbits = [pl for _, pl in pairs]
         beta = 0
