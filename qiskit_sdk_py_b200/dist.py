@@ -63,6 +63,7 @@ class ShardedState:
         self.fused_exchanges = 0
         self.swap_bytes = 0
         self._xch_events = []   # (start, end) CUDA events around every exchange (device shards only)
+        self._xch_wait_events = []  # (start, after the opening barrier) of the exchanges that are not overlapped
         self.overlap = bool(overlap)  # run the passes that commute with an exchange while it is in flight
         self.overlapped_exchanges = 0
         self._comm_stream = None
@@ -185,6 +186,10 @@ class ShardedState:
                 r = (r & ~(1 << j)) | (((lam >> i) & 1) << j)
             ptrs[lam] = self._peers[r][0]
         self._stream_barrier()
+        if t_begin is not None:  # time spent waiting for the slowest rank (bench.py: exchange_wait_ms)
+            mid = self._torch.cuda.Event(enable_timing=True)
+            mid.record()
+            self._xch_wait_events.append((t_begin, mid))
         self.shard.swap_bits_p2p(lbits, beta, ptrs)
         self._stream_barrier()
         self._xch_end(t_begin)
@@ -214,6 +219,12 @@ class ShardedState:
     def exchange_ms(self):
         """Marker for exchange_time_ms: exchanges recorded so far."""
         return len(self._xch_events)
+
+    def exchange_wait_ms(self):
+        """Device time (ms) this rank spent in the opening barrier of its (not overlapped) exchanges so far, i.e. waiting
+        for the slowest rank (synchronises)."""
+        self._torch.cuda.synchronize()
+        return float(sum(a.elapsed_time(b) for a, b in self._xch_wait_events))
 
     def exchange_time_ms(self, since=0):
         """Device time (ms) of the exchanges recorded after marker ``since`` (synchronises)."""
@@ -388,6 +399,7 @@ class ShardedState:
         remaining = ops
         while remaining:
             run, deferred, blocked = [], [], set()
+            plain = True   # every runnable op acts on local qubits only: the same GateOps on every rank
             for op in remaining:
                 qs = set(op.qubits)
                 loc = False if (qs & blocked) else self._localise(op)
@@ -396,18 +408,61 @@ class ShardedState:
                     deferred.append(op)
                 elif loc is not None:
                     run.append(loc)
+                if loc is not False and any(self.pos[q] >= self.n_local for q in op.qubits):
+                    plain = False
             pairs = self._plan_swap(deferred) if deferred else []
-            late = []
+            late, carry = [], []
             # with k swapped qubits a fraction 1 - 2^-k of the late work runs under the transfers: worth the extra
             # (less fused) passes from k = 2 on; a pairwise swap (k = 1) hides too little (measured on 2 GPUs)
-            if len(pairs) >= self.MIN_OVERLAP_SWAPS and self.overlap:
-                run, late = self._split_for_overlap(run, [pl for _, pl in pairs])
-            self._apply_local(run)
+            want_late = len(pairs) >= self.MIN_OVERLAP_SWAPS and self.overlap
+            if pairs and plain and self.carry_over:
+                late, carry = self._run_must_then_split(run, [pl for _, pl in pairs], want_late)
+            else:
+                if want_late:
+                    run, late = self._split_for_overlap(run, [pl for _, pl in pairs])
+                self._apply_local(run)
             if late:
                 self._exchange_overlapped(pairs, late)
             elif pairs:
                 self.swap_many(pairs)
-            remaining = deferred
+            remaining = carry + deferred
+
+    carry_over = True  # gates that need not run before an exchange wait for the passes after it (fuller passes)
+
+    def _run_must_then_split(self, run, victim_bits, want_late):
+        """Before an exchange only the gates on a victim bit (the local bits about to leave the shard) and their
+        predecessors MUST run.  Plan exactly those (planner.plan_passes(must=...): other ready gates just fill the tiles
+        these open), apply the passes, and split what is left -- gates on other qubits, closed under successors -- into
+        ``late`` (a prefix of at most OVERLAP_TARGET_GATES gates, applied sub-block by sub-block under the transfers)
+        and ``carry`` (returned as ops on LOGICAL qubits: they join the gates that become runnable after the exchange,
+        where they fuse into full passes instead of the sparse last passes of this batch).  ``run`` holds plain local
+        GateOps, the same on every rank, so every rank takes the same decisions."""
+        from .planner import merge_ops, plan_passes
+
+        merged = merge_ops(run)
+        tainted = set(victim_bits)
+        must = set()
+        for idx in range(len(merged) - 1, -1, -1):
+            qs = set(merged[idx].qubits)
+            if qs & tainted:
+                tainted |= qs
+                must.add(idx)
+        left = []
+        if must:
+            for p in plan_passes(merged, self.n_local, self.shard.tile_qubits, tails=True, must=must, leftover=left):
+                self.shard.apply_pass(p.tile_qubits, p.ops, tail=p.tail)
+        else:
+            left = list(range(len(merged)))
+        rest = [merged[idx] for idx in left]
+        n_late = 0
+        if want_late and self.n_local - len(victim_bits) >= self.shard.tile_qubits and \
+                not any(v < _LOW_BITS for v in victim_bits):
+            n_late = min(len(rest), self.OVERLAP_TARGET_GATES)
+            if n_late < self.MIN_OVERLAP_GATES:
+                n_late = 0
+        late = rest[:n_late]
+        carry = [GateOp(op.kind, [self._logical_at(b) for b in op.qubits], op.matrix) for op in rest[n_late:]]
+        return late, carry
 
     # -- exchange overlapped with the passes that commute with it ---------------------------------------
     MIN_OVERLAP_SWAPS = 2    # overlap only fused exchanges of at least this many qubits
@@ -512,16 +567,23 @@ class ShardedState:
         self.swap_bytes += 16 * (1 << (self.n_local - k)) * ((1 << k) - 1)
 
     def _apply_local(self, run):
-        batch = []
+        """Apply localised ops (GateOps on local bits and ("scale", factor) items: diagonal gates whose qubits are all
+        global).  A scalar commutes with everything, so the factors of a batch are multiplied up and folded into the
+        matrix of one of its gates -- no launch, and the batch is not cut into pieces at every scalar (a QFT's
+        controlled phases between global qubits used to split its Hadamard passes into single-gate passes)."""
+        batch, factor = [], 1.0 + 0.0j
         for item in run:
-            if isinstance(item, tuple):  # ("scale", factor): a diagonal gate on global qubits
-                if batch:
-                    self.shard.apply_ops(batch)
-                    batch = []
-                if item[1] != 1.0:
-                    self.shard.scale(item[1])
+            if isinstance(item, tuple):
+                factor *= complex(item[1])
             else:
                 batch.append(item)
+        if factor != 1.0:
+            for i, op in enumerate(batch):
+                if op.kind in (_lib.GATE_DENSE1, _lib.GATE_DENSE2, _lib.GATE_DIAG1, _lib.GATE_DIAG2):
+                    batch[i] = GateOp(op.kind, op.qubits, np.asarray(op.matrix, dtype=complex) * factor)
+                    break
+            else:
+                self.shard.scale(factor)
         if batch:
             self.shard.apply_ops(batch)
 
@@ -957,6 +1019,10 @@ def bench_main(args, bench):
     st = ShardedState(n, factory, chunk_amps=chunk_amps, overlap=overlap)
     if os.environ.get("QSV_DIST_OVERLAP_GATES"):
         st.OVERLAP_TARGET_GATES = int(os.environ["QSV_DIST_OVERLAP_GATES"])
+    if os.environ.get("QSV_DIST_CARRY"):      # A/B knobs of tools/: carry-over of the gates an exchange does not need,
+        st.carry_over = os.environ["QSV_DIST_CARRY"] == "1"
+    if os.environ.get("QSV_DIST_XSMS"):       # SMs left to the exchange kernel under the sub-block passes
+        st.EXCHANGE_SMS = int(os.environ["QSV_DIST_XSMS"])
     uniforms = np.random.RandomState(sim_seed).random_sample(shots)
 
     def step():
@@ -992,6 +1058,7 @@ def bench_main(args, bench):
     passes0 = st.shard.passes_launched
     xch0 = st.exchange_ms
     ovl0 = st.overlapped_exchanges
+    wait0 = st.exchange_wait_ms()
     step_ms, (samples, total) = timed(step, args.steps)
     launches = torch.tensor([_lib.launch_count() - launches0], device="cuda", dtype=torch.int64)
     dist.all_reduce(launches, op=dist.ReduceOp.SUM)
@@ -1001,7 +1068,12 @@ def bench_main(args, bench):
     swap_gb_dev = (st.swap_bytes - bytes0) / args.steps / 1e9
     exchange_ms = st.exchange_time_ms(xch0) / args.steps
     st_overlapped = st.overlapped_exchanges - ovl0
+    per_rank = torch.tensor([exchange_ms, (st.exchange_wait_ms() - wait0) / args.steps], device="cuda", dtype=torch.float64)
+    per_rank_all = [torch.zeros_like(per_rank) for _ in range(world)]
+    dist.all_gather(per_rank_all, per_rank)
+    per_rank_all = [[round(float(v), 1) for v in t.tolist()] for t in per_rank_all]
     clock_info = clocks.stop() if rank == 0 else None
+    st_carry, st_xsms = st.carry_over, st.EXCHANGE_SMS
 
     # ---- the other circuit families of BASELINE's metric on the sharded state (one warm-up, one timed run each) ----
     families = {}
@@ -1079,6 +1151,9 @@ def bench_main(args, bench):
                          "fused_exchanges_per_step": fused_dev, "swap_GB_per_gpu_per_step": swap_gb_dev,
                          "overlapped_exchanges_per_step": (st_overlapped / args.steps),
                          "exchange_ms_per_step": exchange_ms,
+                         "exchange_ms_per_step_by_rank": [v[0] for v in per_rank_all],
+                         "exchange_barrier_wait_ms_per_step_by_rank": [v[1] for v in per_rank_all],
+                         "carry_over": bool(st_carry), "exchange_sms": st_xsms,
                          "exchange_GBps_per_gpu_per_direction": (swap_gb_dev / (exchange_ms * 1e-3) if exchange_ms else None),
                          "nvlink_peak_GBps_per_direction": 900.0},
             "roofline": {"bound": "hbm", "kernel": "tile_pass_kernel", "achieved": None, "peak": peak, "unit": "GB/s",

@@ -121,6 +121,7 @@ def merge_ops(ops):
 
 
 _DIAG_KINDS = (_lib.GATE_DIAG1, _lib.GATE_DIAG2)
+_RUN_BITS = 8  # tile bits one diagonal lookup table of the pass kernel can span (tile_pass.cu kRunBits)
 
 
 def schedule_pass_ops(ops):
@@ -160,10 +161,35 @@ def schedule_pass_ops(ops):
             if indeg[j] == 0:
                 ready.add(j)
 
+    def packed(indices):
+        # order commuting diagonal gates so that the kernel's sequential folding (consecutive gates while they touch at
+        # most _RUN_BITS tile bits) yields few, long runs: grow one run at a time by the gate that adds the fewest bits
+        rest, order = list(indices), []
+        while rest:
+            bits = set(qsets[rest[0]])
+            order.append(rest.pop(0))
+            while rest:
+                best, best_new = None, 99
+                for j in rest:
+                    new = len(qsets[j] - bits)
+                    if len(bits) + new <= _RUN_BITS and new < best_new:
+                        best, best_new = j, new
+                        if new == 0:
+                            break
+                if best is None:
+                    break
+                bits |= qsets[best]
+                order.append(best)
+                rest.remove(best)
+        return order
+
     while ready:
         dense_ready = [i for i in sorted(ready) if not diag[i]]
         if not dense_ready:
-            for i in sorted(ready):
+            # diagonal gates nothing in the pass waits for (a QFT fan's phases onto qubits whose Hadamard comes in a later
+            # pass) stay back: a later block may absorb them for free, and what is left at the end folds into long runs
+            needed = [i for i in sorted(ready) if succs[i]]
+            for i in packed(needed if needed else sorted(ready)):
                 emit(i)
             continue
         seed = dense_ready[0]
@@ -191,7 +217,7 @@ def _relabel(op, layout):
 
 def plan_passes(ops, n_qubits, tile_qubits=DEFAULT_TILE_QUBITS, max_gates=_lib.MAX_PASS_GATES,
                 max_payload=_lib.MAX_PASS_MATRIX_DOUBLES, layout=None, remap=False, tails=False, schedule=True,
-                avoid=()):
+                avoid=(), must=None, leftover=None):
     """Group ``ops`` (GateOps on LOGICAL qubits, <= 2 qubits each) into passes.
 
     Frontier-greedy over the gate dependency DAG: a gate is *ready* when it is the first pending gate
@@ -208,7 +234,12 @@ def plan_passes(ops, n_qubits, tile_qubits=DEFAULT_TILE_QUBITS, max_gates=_lib.M
 
     ``layout[q]`` is the physical bit of logical qubit q (identity if None); it is updated in place when
     given.  With ``remap`` the write-back of each pass moves the tile qubits that the following gates
-    need first into the always-resident low bits (qsv_apply_pass_remap)."""
+    need first into the always-resident low bits (qsv_apply_pass_remap).
+
+    ``must`` (a set of indices into ``ops``) turns the call into a PARTIAL plan (dist.ShardedState before a qubit
+    exchange): only the ``must`` gates have to run now.  They are preferred whenever one fits; other ready gates only
+    fill the tiles the ``must`` gates open, and planning stops with the pass that takes the last ``must`` gate.  The
+    indices of the gates left unplanned (closed under successors, program order) are appended to ``leftover``."""
     from collections import deque
 
     if layout is None:
@@ -234,7 +265,9 @@ def plan_passes(ops, n_qubits, tile_qubits=DEFAULT_TILE_QUBITS, max_gates=_lib.M
     frontier = set(idx for idx in range(len(ops)) if is_ready(idx))
     n_left = len(ops)
     passes = []
-    while n_left:
+    must_left = None if must is None else len(set(must))
+    taken = set()
+    while n_left and (must is None or must_left > 0):
         inv = [0] * n_qubits
         for q, ph in enumerate(layout):
             inv[ph] = q
@@ -249,12 +282,15 @@ def plan_passes(ops, n_qubits, tile_qubits=DEFAULT_TILE_QUBITS, max_gates=_lib.M
                 cost = sum(1 for q in op.qubits if q not in used)
                 if len(used) + cost > tile_size or payload + op.payload_doubles > max_payload:
                     continue
+                if must is not None and idx not in must:
+                    cost += 50  # a gate that may wait only fills what the gates that must run leave free
                 if cost < best_cost or (cost == best_cost and idx < best):
                     best, best_cost = idx, cost
             if best is None:
                 break
             op = ops[best]
             frontier.discard(best)
+            taken.add(best)
             chosen.append(op)
             used.update(op.qubits)
             payload += op.payload_doubles
@@ -281,24 +317,43 @@ def plan_passes(ops, n_qubits, tile_qubits=DEFAULT_TILE_QUBITS, max_gates=_lib.M
         tail = []
         if tails:
             diag = (_lib.GATE_DIAG1, _lib.GATE_DIAG2)
+
+            def take(idx):
+                nonlocal n_left
+                frontier.discard(idx)
+                taken.add(idx)
+                n_left -= 1
+                for q in ops[idx].qubits:
+                    queues[q].popleft()
+                for q in ops[idx].qubits:
+                    if queues[q] and is_ready(queues[q][0]):
+                        frontier.add(queues[q][0])
+
             grew = True
-            while grew and len(tail) < _lib.MAX_TAIL_GATES:
+            while grew:
                 grew = False
                 for idx in sorted(frontier):
                     op = ops[idx]
-                    if op.kind not in diag or (len(op.qubits) == 2 and all(q in used for q in op.qubits)):
-                        continue  # a 2-qubit diagonal inside the tile is an ordinary gate of a pass
-                    frontier.discard(idx)
-                    tail.append(op)
-                    n_left -= 1
-                    for q in op.qubits:
-                        queues[q].popleft()
-                    for q in op.qubits:
-                        if queues[q] and is_ready(queues[q][0]):
-                            frontier.add(queues[q][0])
-                    grew = True
+                    if op.kind not in diag:
+                        continue
+                    if len(op.qubits) == 2 and all(q in used for q in op.qubits):
+                        # a 2-qubit diagonal inside the tile is an ordinary gate of the pass.  One that became ready
+                        # only behind tail gates (the controlled phases onto the pinned low qubits at the end of a QFT
+                        # fan) still joins THIS pass: it is appended to the pass's gates, which run before the tail --
+                        # diagonal gates commute with the (all-diagonal) tail, and every non-diagonal gate before it on
+                        # its qubits is already in the pass or done
+                        if not tail or len(chosen) >= max_gates or payload + op.payload_doubles > max_payload:
+                            continue
+                        chosen.append(op)
+                        payload += op.payload_doubles
+                        take(idx)
+                        grew = True
+                        continue
                     if len(tail) >= _lib.MAX_TAIL_GATES:
-                        break
+                        continue
+                    tail.append(op)
+                    take(idx)
+                    grew = True
         dest = None
         if remap and n_left:
             # the n_low tile qubits needed soonest become the residents of the low bits
@@ -319,6 +374,10 @@ def plan_passes(ops, n_qubits, tile_qubits=DEFAULT_TILE_QUBITS, max_gates=_lib.M
         if dest is not None:
             for q, d in zip(tile_log, dest):
                 layout[q] = d
+        if must is not None:
+            must_left = sum(1 for idx in must if idx not in taken)
+    if leftover is not None:
+        leftover.extend(idx for idx in range(len(ops)) if idx not in taken)
     return passes
 
 

@@ -367,13 +367,14 @@ def _overlap_worker(rank, world, port, n, out_dir):
     ins = circuits.quantum_volume_instructions(n, 6, 5) + circuits.random_basis_instructions(n, 6, 9)
     ops = [o for o in (lower.lower_gate(i["name"], i["qubits"], i.get("params")) for i in ins) if o is not None]
     results = []
-    for overlap in (True, False):
+    for overlap, carry in ((True, False), (False, False), (True, True), (False, True)):
         st = ShardedState(n, lambda k: FakeState(k, tile_qubits=5), chunk_amps=16, overlap=overlap)
+        st.carry_over = carry  # gates an exchange does not need wait for the passes after it (plan_passes(must=...))
         st.MIN_OVERLAP_GATES = 2
         st.MIN_OVERLAP_SWAPS = 1
         st.init_basis0()
         st.apply_ops(ops)
-        results.append((st.gather_statevector(), st.overlapped_exchanges, st.swaps))
+        results.append((st.gather_statevector(), st.overlapped_exchanges, st.swaps, st.shard.passes_launched))
     ref = np.zeros(2 ** n, dtype=complex)
     ref[0] = 1.0
     for o in ops:
@@ -382,8 +383,11 @@ def _overlap_worker(rank, world, port, n, out_dir):
         ref = orc.apply_unitary(ref.reshape([2] * n), mat, list(o.qubits)).reshape(-1)
     assert np.max(np.abs(results[0][0] - ref)) < 1e-12
     assert np.max(np.abs(results[1][0] - ref)) < 1e-12
+    assert np.max(np.abs(results[2][0] - ref)) < 1e-12
+    assert np.max(np.abs(results[3][0] - ref)) < 1e-12
     assert results[0][1] > 0, "the circuit should have had exchanges with late passes to overlap"
-    assert results[1][1] == 0
+    assert results[1][1] == 0 and results[3][1] == 0
+    assert results[3][3] <= results[1][3], "carry-over must not cost passes"
     if rank == 0:
         np.save(os.path.join(out_dir, "ovl_%d.npy" % world), np.array([results[0][1], results[0][2]]))
     dist.destroy_process_group()

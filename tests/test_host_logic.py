@@ -278,8 +278,79 @@ def test_schedule_turns_qft_fans_into_blocks_and_long_runs():
         passes = planner.plan_passes(merged, n, tails=True, schedule=sched)
         kinds = [o["kind"] for p in passes for o in DeviceState.pass_ops(n, p.tile_qubits, p.ops)]
         count[sched] = (len(passes), kinds.count(6), kinds.count(2))
-    assert count[True][0] == count[False][0] == 13
+    assert count[True][0] == count[False][0] == 10  # 13 before the in-tile diagonals behind a tail joined its pass
     assert count[True][1] >= 2 * count[False][1] and count[True][2] <= count[False][2] // 2
+
+
+def test_in_tile_diagonals_behind_a_tail_join_the_pass():
+    """plan_passes(tails=True): the controlled phases onto the pinned low qubits at the end of a QFT fan become ready
+    only behind tail gates; they are appended to the pass's gates (diagonal gates commute with the all-diagonal tail)
+    instead of costing a pass of their own.  Same state as the oracle, fewer passes than gates-then-tail planning."""
+    from fake_state import FakeState
+    from oracle import basicaer_oracle as orc
+    from qiskit_sdk_py_b200 import _lib, circuits, lower, planner
+
+    n = 12
+    ins = circuits.qft(n, state_seed=5)["experiments"][0]["instructions"]
+    ops = [o for o in (lower.lower_gate(i["name"], i["qubits"], i.get("params")) for i in ins if
+                       i["name"] not in ("measure", "barrier")) if o is not None]
+    merged = planner.merge_ops(ops)
+    passes = planner.plan_passes(merged, n, tile_qubits=7, tails=True)
+    assert sum(len(p.ops) + len(p.tail) for p in passes) == len(merged)
+    assert any(p.tail and any(o.kind == _lib.GATE_DIAG2 for o in p.ops) for p in passes)
+    st = FakeState(n, tile_qubits=7)
+    st.init_basis0()
+    for p in passes:
+        st.apply_pass(p.tile_qubits, p.ops, tail=p.tail)
+    ref = np.zeros(2 ** n, dtype=complex)
+    ref[0] = 1.0
+    for o in ops:
+        mat = np.diag(o.matrix) if o.kind in (_lib.GATE_DIAG1, _lib.GATE_DIAG2) else \
+            orc.cx_gate_matrix() if o.kind == _lib.GATE_CX else o.matrix
+        ref = orc.apply_unitary(ref.reshape([2] * n), mat, list(o.qubits)).reshape(-1)
+    assert np.max(np.abs(st.vec - ref)) < 1e-12
+
+
+def test_partial_plan_runs_what_must_run_and_leaves_a_successor_closed_rest():
+    """plan_passes(must=..., leftover=...) (dist.ShardedState before a qubit exchange): every ``must`` gate and all its
+    predecessors are planned, the rest is closed under successors, and planned + rest applied in that order give the
+    oracle's state."""
+    from fake_state import FakeState
+    from oracle import basicaer_oracle as orc
+    from qiskit_sdk_py_b200 import _lib, circuits, lower, planner
+
+    n = 10
+    ins = circuits.quantum_volume_instructions(n, 5, 11) + circuits.random_basis_instructions(n, 4, 3)
+    ops = [o for o in (lower.lower_gate(i["name"], i["qubits"], i.get("params")) for i in ins) if o is not None]
+    merged = planner.merge_ops(ops)
+    victims = {7, 9}
+    tainted, must = set(victims), set()
+    for idx in range(len(merged) - 1, -1, -1):
+        if set(merged[idx].qubits) & tainted:
+            tainted |= set(merged[idx].qubits)
+            must.add(idx)
+    assert 0 < len(must) < len(merged)
+    left = []
+    passes = planner.plan_passes(merged, n, tile_qubits=6, tails=True, must=must, leftover=left)
+    planned = sum(len(p.ops) + len(p.tail) for p in passes)
+    assert planned + len(left) == len(merged) and left == sorted(left) and not (set(left) & must)
+    for pos, idx in enumerate(left):       # closed under successors: nothing after a left gate on its qubits was planned
+        for later in range(idx + 1, len(merged)):
+            if set(merged[later].qubits) & set(merged[idx].qubits):
+                assert later in left
+    full = planner.plan_passes(merged, n, tile_qubits=6, tails=True)
+    assert len(passes) <= len(full)
+    st = FakeState(n, tile_qubits=6)
+    st.init_basis0()
+    for p in passes + planner.plan_passes([merged[i] for i in left], n, tile_qubits=6, tails=True):
+        st.apply_pass(p.tile_qubits, p.ops, tail=p.tail)
+    ref = np.zeros(2 ** n, dtype=complex)
+    ref[0] = 1.0
+    for o in ops:
+        mat = np.diag(o.matrix) if o.kind in (_lib.GATE_DIAG1, _lib.GATE_DIAG2) else \
+            orc.cx_gate_matrix() if o.kind == _lib.GATE_CX else o.matrix
+        ref = orc.apply_unitary(ref.reshape([2] * n), mat, list(o.qubits)).reshape(-1)
+    assert np.max(np.abs(st.vec - ref)) < 1e-12
 
 
 def test_device_statevector_handle_against_oracle():

@@ -32,6 +32,10 @@ class CountingShard:
             info = DeviceState.pass_info(self.n, p.tile_qubits, p.ops)
             self.passes.append((len(p.ops), info["ops"], info["fused3"]))
 
+    def apply_pass(self, tile_qubits, ops, dest=None, tail=None):
+        info = DeviceState.pass_info(self.n, tile_qubits, ops)
+        self.passes.append((len(ops), info["ops"], info["fused3"]))
+
     def plan_ops(self, ops, avoid=()):
         return plan_passes(merge_ops(list(ops)), self.n, DEFAULT_TILE_QUBITS, tails=True, avoid=avoid)
 
@@ -55,6 +59,7 @@ class DryState(ShardedState):
         self.swaps = self.fused_exchanges = self.swap_bytes = 0
         self.events = []
         self.overlap = os.environ.get("QSV_DRY_OVERLAP", "1") == "1"
+        self.carry_over = os.environ.get("QSV_DRY_CARRY", "1") == "1"
         self.overlapped_exchanges = 0
         self._peers = self._comm_stream = None
         self._xch_events = []
