@@ -108,14 +108,21 @@ __device__ __forceinline__ u64 p2p_deposit(const P2PDesc& d, uint32_t pattern) {
   return v;
 }
 
-template <int kU>  // independent remote loads in flight per thread
+template <int kU, bool kChunked>  // kU independent remote loads in flight per thread
 __global__ void __launch_bounds__(1024)
 swap_p2p_kernel(double2* __restrict__ mine, const __grid_constant__ P2PDesc d) {
   const u64 sub = 1ull << (d.n_local - d.k);  // amplitudes per sub-block
   const u64 half = sub >> 1;
   const u64 dep_beta = p2p_deposit(d, d.beta);
-  const u64 stride = (u64)gridDim.x * blockDim.x;
-  const u64 t0 = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  // kChunked: every CTA walks ONE contiguous slice of the index range (1024 * kU amplitudes per iteration), so an SM
+  // touches 1/gridDim of the pages of the two shards instead of all of them (grid-stride: consecutive CTAs take
+  // consecutive 16 KiB pieces, every SM's TLB sees every page of a 128 GiB shard and of its peer mapping)
+  const u64 per_iter = (u64)blockDim.x * kU;
+  const u64 per_cta = kChunked ? ((half + gridDim.x - 1) / gridDim.x + per_iter - 1) / per_iter * per_iter : 0;
+  const u64 lo = kChunked ? (u64)blockIdx.x * per_cta : 0;
+  const u64 hi = kChunked ? (lo + per_cta < half ? lo + per_cta : half) : half;
+  const u64 step = kChunked ? (u64)blockDim.x : (u64)gridDim.x * blockDim.x;  // distance between the unrolled accesses
+  const u64 t0 = kChunked ? lo + threadIdx.x : (u64)blockIdx.x * blockDim.x + threadIdx.x;
   // XOR schedule: in step j every rank works on its partner beta ^ j -- a perfect matching of the 2^k ranks per step,
   // so no rank's memory or NVLink port is the target of more than one partner at a time (a common order 0, 1, 2, ...
   // has everybody hit rank 0 first: measured 280 GB/s instead of 650 on 4 GPUs)
@@ -125,28 +132,28 @@ swap_p2p_kernel(double2* __restrict__ mine, const __grid_constant__ P2PDesc d) {
     double2* __restrict__ theirs = d.peer[lam];
     const u64 dep_lam = p2p_deposit(d, lam);
     const u64 begin = d.beta < lam ? 0 : half;
-    for (u64 h0 = t0; h0 < half; h0 += stride * kU) {
+    for (u64 h0 = t0; h0 < hi; h0 += step * kU) {
       double2 a[kU], b[kU];
       u64 im[kU], ip[kU];
 #pragma unroll
       for (int u = 0; u < kU; u++) {
-        const u64 h = h0 + (u64)u * stride;
-        u64 x = begin + (h < half ? h : 0);
+        const u64 h = h0 + (u64)u * step;
+        u64 x = begin + (h < hi ? h : 0);
         for (int i = 0; i < d.k; i++) {
           const int p = d.bits[i];
           x = ((x >> p) << (p + 1)) | (x & ((1ull << p) - 1ull));
         }
         im[u] = x | dep_lam;   // my sub-block that leaves
         ip[u] = x | dep_beta;  // the partner's sub-block that comes here
-        if (h < half) {
+        if (h < hi) {
           b[u] = __ldcv(theirs + ip[u]);
           a[u] = mine[im[u]];
         }
       }
 #pragma unroll
       for (int u = 0; u < kU; u++) {
-        const u64 h = h0 + (u64)u * stride;
-        if (h < half) {
+        const u64 h = h0 + (u64)u * step;
+        if (h < hi) {
           mine[im[u]] = b[u];
           theirs[ip[u]] = a[u];
         }
@@ -155,6 +162,7 @@ swap_p2p_kernel(double2* __restrict__ mine, const __grid_constant__ P2PDesc d) {
   }
 }
 
+bool g_p2p_chunked = false;  // qsv_debug_set_flags bit 14 (tools/p2p_swap_probe.py)
 int g_p2p_unroll = 4;  // tools/p2p_swap_probe.py sweeps it through qsv_debug_set_flags (bits 12-13)
 
 static int make_sub(int n_local, const int32_t* local_qubits, int k, uint32_t pattern, SubDesc* d) {
@@ -278,12 +286,18 @@ int qsv_swap_bits_p2p(double* sv, int n_local, const int32_t* local_qubits, int 
   int ctas = max_ctas > 0 ? max_ctas : 2 * sm_count();
   const u64 need = (half + 1023) / 1024;
   if ((u64)ctas > need) ctas = (int)need;
+#define QSV_P2P_LAUNCH(U)                                                                                         \
+  if (g_p2p_chunked)                                                                                              \
+    swap_p2p_kernel<U, true><<<ctas, 1024, 0, (cudaStream_t)stream>>>(reinterpret_cast<double2*>(sv), d);        \
+  else                                                                                                            \
+    swap_p2p_kernel<U, false><<<ctas, 1024, 0, (cudaStream_t)stream>>>(reinterpret_cast<double2*>(sv), d)
   switch (g_p2p_unroll) {
-    case 1: swap_p2p_kernel<1><<<ctas, 1024, 0, (cudaStream_t)stream>>>(reinterpret_cast<double2*>(sv), d); break;
-    case 2: swap_p2p_kernel<2><<<ctas, 1024, 0, (cudaStream_t)stream>>>(reinterpret_cast<double2*>(sv), d); break;
-    case 8: swap_p2p_kernel<8><<<ctas, 1024, 0, (cudaStream_t)stream>>>(reinterpret_cast<double2*>(sv), d); break;
-    default: swap_p2p_kernel<4><<<ctas, 1024, 0, (cudaStream_t)stream>>>(reinterpret_cast<double2*>(sv), d); break;
+    case 1: QSV_P2P_LAUNCH(1); break;
+    case 2: QSV_P2P_LAUNCH(2); break;
+    case 8: QSV_P2P_LAUNCH(8); break;
+    default: QSV_P2P_LAUNCH(4); break;
   }
+#undef QSV_P2P_LAUNCH
   QSV_LAUNCHED();
   return 0;
 }

@@ -2145,6 +2145,7 @@ int qsv_debug_set_flags(uint32_t flags) {
   g_debug_flags = flags;
   g_debug_flags_set = true;
   g_p2p_unroll = ((flags >> 12) & 3u) == 1u ? 8 : ((flags >> 12) & 3u) == 2u ? 2 : ((flags >> 12) & 3u) == 3u ? 1 : 4;
+  g_p2p_chunked = (flags >> 14) & 1u;
   return 0;
 }
 

@@ -190,7 +190,17 @@ class ShardedState:
             mid = self._torch.cuda.Event(enable_timing=True)
             mid.record()
             self._xch_wait_events.append((t_begin, mid))
-        self.shard.swap_bits_p2p(lbits, beta, ptrs)
+        if k > 1 and self.p2p_stepwise:
+            # one launch per partner (XOR order) with a barrier in between: every step is a perfect matching of the ranks;
+            # inside ONE kernel the ranks drift apart and two of them end up loading the same partner's links
+            for j in range(1, 1 << k):
+                if j > 1:
+                    self._stream_barrier()
+                step = [None] * (1 << k)
+                step[beta ^ j] = ptrs[beta ^ j]
+                self.shard.swap_bits_p2p(lbits, beta, step)
+        else:
+            self.shard.swap_bits_p2p(lbits, beta, ptrs)
         self._stream_barrier()
         self._xch_end(t_begin)
         for pg, pl in pairs:
@@ -427,6 +437,7 @@ class ShardedState:
                 self.swap_many(pairs)
             remaining = carry + deferred
 
+    p2p_stepwise = False  # fused peer-memory exchanges partner by partner (A/B: QSV_DIST_STEPWISE)
     carry_over = True  # gates that need not run before an exchange wait for the passes after it (fuller passes)
 
     def _run_must_then_split(self, run, victim_bits, want_late):
@@ -468,7 +479,7 @@ class ShardedState:
     MIN_OVERLAP_SWAPS = 2    # overlap only fused exchanges of at least this many qubits
     MIN_OVERLAP_GATES = 6    # fewer late gates than this: not worth splitting the passes
     OVERLAP_TARGET_GATES = 30  # ... and no more than about four passes' worth (one exchange takes 2-4 pass times)
-    EXCHANGE_SMS = 16        # SMs left to the exchange kernel while sub-block passes run
+    EXCHANGE_SMS = 32        # SMs left to the exchange kernel while sub-block passes run (4 GPUs: 16 -> 6.90 s, 32 -> 6.72 s)
 
     def _split_for_overlap(self, run, victim_bits):
         """Split the locally runnable ops (physical qubits, program order) into (early, late): ``late`` = the ops
@@ -1021,6 +1032,8 @@ def bench_main(args, bench):
         st.OVERLAP_TARGET_GATES = int(os.environ["QSV_DIST_OVERLAP_GATES"])
     if os.environ.get("QSV_DIST_CARRY"):      # A/B knobs of tools/: carry-over of the gates an exchange does not need,
         st.carry_over = os.environ["QSV_DIST_CARRY"] == "1"
+    if os.environ.get("QSV_DIST_STEPWISE"):
+        st.p2p_stepwise = os.environ["QSV_DIST_STEPWISE"] == "1"
     if os.environ.get("QSV_DIST_XSMS"):       # SMs left to the exchange kernel under the sub-block passes
         st.EXCHANGE_SMS = int(os.environ["QSV_DIST_XSMS"])
     uniforms = np.random.RandomState(sim_seed).random_sample(shots)
@@ -1073,7 +1086,7 @@ def bench_main(args, bench):
     dist.all_gather(per_rank_all, per_rank)
     per_rank_all = [[round(float(v), 1) for v in t.tolist()] for t in per_rank_all]
     clock_info = clocks.stop() if rank == 0 else None
-    st_carry, st_xsms = st.carry_over, st.EXCHANGE_SMS
+    st_carry, st_xsms, st_stepwise = st.carry_over, st.EXCHANGE_SMS, st.p2p_stepwise
 
     # ---- the other circuit families of BASELINE's metric on the sharded state (one warm-up, one timed run each) ----
     families = {}
@@ -1153,7 +1166,7 @@ def bench_main(args, bench):
                          "exchange_ms_per_step": exchange_ms,
                          "exchange_ms_per_step_by_rank": [v[0] for v in per_rank_all],
                          "exchange_barrier_wait_ms_per_step_by_rank": [v[1] for v in per_rank_all],
-                         "carry_over": bool(st_carry), "exchange_sms": st_xsms,
+                         "carry_over": bool(st_carry), "exchange_sms": st_xsms, "p2p_stepwise": bool(st_stepwise),
                          "exchange_GBps_per_gpu_per_direction": (swap_gb_dev / (exchange_ms * 1e-3) if exchange_ms else None),
                          "nvlink_peak_GBps_per_direction": 900.0},
             "roofline": {"bound": "hbm", "kernel": "tile_pass_kernel", "achieved": None, "peak": peak, "unit": "GB/s",

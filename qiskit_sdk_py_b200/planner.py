@@ -211,13 +211,34 @@ def schedule_pass_ops(ops):
     return out
 
 
+def pair_isolated_1q(ops):
+    """Dense 1-qubit gates of a pass whose qubit no other gate of the pass touches (a layer of state-preparation
+    rotations, the first Hadamard layer) are multiplied up two by two into 2-qubit gates M_b (x) M_a: the kernel widens
+    a lone 1-qubit gate to a 4x4 block anyway (tile_pass.cu), so a pair costs one FP64 tensor op instead of two.  The
+    gates commute with everything else in the pass; each pair takes the position of its first member."""
+    touched = {}
+    for op in ops:
+        for q in op.qubits:
+            touched[q] = touched.get(q, 0) + 1
+    lone = [i for i, op in enumerate(ops) if op.kind == _lib.GATE_DENSE1 and touched[op.qubits[0]] == 1]
+    if len(lone) < 2:
+        return list(ops)
+    out = list(ops)
+    for a, b in zip(lone[0::2], lone[1::2]):
+        qa, qb = ops[a].qubits[0], ops[b].qubits[0]
+        mat = np.kron(np.asarray(ops[b].matrix, dtype=complex), np.asarray(ops[a].matrix, dtype=complex))
+        out[a] = GateOp(_lib.GATE_DENSE2, [qa, qb], mat)
+        out[b] = None
+    return [op for op in out if op is not None]
+
+
 def _relabel(op, layout):
     return GateOp(op.kind, [layout[q] for q in op.qubits], op.matrix)
 
 
 def plan_passes(ops, n_qubits, tile_qubits=DEFAULT_TILE_QUBITS, max_gates=_lib.MAX_PASS_GATES,
                 max_payload=_lib.MAX_PASS_MATRIX_DOUBLES, layout=None, remap=False, tails=False, schedule=True,
-                avoid=(), must=None, leftover=None):
+                avoid=(), must=None, leftover=None, pair_1q=True):
     """Group ``ops`` (GateOps on LOGICAL qubits, <= 2 qubits each) into passes.
 
     Frontier-greedy over the gate dependency DAG: a gate is *ready* when it is the first pending gate
@@ -367,6 +388,8 @@ def plan_passes(ops, n_qubits, tile_qubits=DEFAULT_TILE_QUBITS, max_gates=_lib.M
                 new_pos[qi], new_pos[qe] = layout[qe], layout[qi]
             if incoming:
                 dest = [new_pos[q] for q in tile_log]
+        if pair_1q:
+            chosen = pair_isolated_1q(chosen)
         if schedule:
             chosen = schedule_pass_ops(chosen)
         passes.append(Pass(tile_phys, [_relabel(op, layout) for op in chosen], dest,

@@ -39,7 +39,7 @@ def test_planner_preserves_order_on_shared_qubits():
            for i in circuits.random_basis_instructions(10, 30, 5)]
     ops = [o for o in ops if o is not None]
     for tile in (3, 4, 6, 10, 12):
-        passes = plan_passes(ops, 10, tile_qubits=tile)
+        passes = plan_passes(ops, 10, tile_qubits=tile, pair_1q=False)  # the same op objects
         flat = [op for p in passes for op in p.ops]
         assert sorted(map(_key, flat)) == sorted(map(_key, ops))
         # per qubit, the subsequence of gates touching it is unchanged
@@ -282,6 +282,33 @@ def test_schedule_turns_qft_fans_into_blocks_and_long_runs():
     assert count[True][1] >= 2 * count[False][1] and count[True][2] <= count[False][2] // 2
 
 
+def test_isolated_1q_gates_of_a_pass_are_paired():
+    """planner.pair_isolated_1q: a layer of 1-qubit rotations costs one 2-qubit tensor op per PAIR of gates; gates whose
+    qubit another gate of the pass touches are left alone (merge_ops / the kernel's blocks take care of those)."""
+    from fake_state import FakeState
+    from oracle import basicaer_oracle as orc
+    from qiskit_sdk_py_b200 import _lib, lower, planner
+
+    rng = np.random.RandomState(3)
+    n = 9
+    ops = [lower.lower_gate("u3", [q], list(rng.uniform(0, 3, 3))) for q in range(n)]
+    ops.append(lower.lower_gate("cx", [0, 1], None))
+    passes = planner.plan_passes(ops, n, tile_qubits=9)
+    assert len(passes) == 1
+    kinds = [o.kind for o in passes[0].ops]
+    # u3(0), u3(1) keep their cx (order preserved); the other seven pair up into three 2-qubit gates + one left over
+    assert kinds.count(_lib.GATE_DENSE2) == 3 and kinds.count(_lib.GATE_DENSE1) == 3 and kinds.count(_lib.GATE_CX) == 1
+    st = FakeState(n, tile_qubits=9)
+    st.init_basis0()
+    st.apply_pass(passes[0].tile_qubits, passes[0].ops)
+    ref = np.zeros(2 ** n, dtype=complex)
+    ref[0] = 1.0
+    for o in ops:
+        mat = orc.cx_gate_matrix() if o.kind == _lib.GATE_CX else o.matrix
+        ref = orc.apply_unitary(ref.reshape([2] * n), mat, list(o.qubits)).reshape(-1)
+    assert np.max(np.abs(st.vec - ref)) < 1e-12
+
+
 def test_in_tile_diagonals_behind_a_tail_join_the_pass():
     """plan_passes(tails=True): the controlled phases onto the pinned low qubits at the end of a QFT fan become ready
     only behind tail gates; they are appended to the pass's gates (diagonal gates commute with the all-diagonal tail)
@@ -295,8 +322,9 @@ def test_in_tile_diagonals_behind_a_tail_join_the_pass():
     ops = [o for o in (lower.lower_gate(i["name"], i["qubits"], i.get("params")) for i in ins if
                        i["name"] not in ("measure", "barrier")) if o is not None]
     merged = planner.merge_ops(ops)
-    passes = planner.plan_passes(merged, n, tile_qubits=7, tails=True)
+    passes = planner.plan_passes(merged, n, tile_qubits=7, tails=True, pair_1q=False)
     assert sum(len(p.ops) + len(p.tail) for p in passes) == len(merged)
+    passes = planner.plan_passes(merged, n, tile_qubits=7, tails=True)  # the default: state-preparation gates paired
     assert any(p.tail and any(o.kind == _lib.GATE_DIAG2 for o in p.ops) for p in passes)
     st = FakeState(n, tile_qubits=7)
     st.init_basis0()

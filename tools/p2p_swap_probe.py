@@ -57,15 +57,19 @@ def timed(pairs, ctas, reps=3):
     return float(ms.item()), gb
 
 
-for unroll_flag, unroll in ((0, 4), (1 << 12, 8), (2 << 12, 2)):
-    lib.qsv_debug_set_flags(unroll_flag)
-    for ctas in (16, 32, 64, 148, 296):
+quick = len(sys.argv) > 2 and sys.argv[2] == "quick"  # chunked vs grid-stride only
+variants = ((0, 4, 0), (1 << 14, 4, 1)) if quick else \
+    ((0, 4, 0), (1 << 14, 4, 1), (1 << 12, 8, 0), (2 << 12, 2, 0), ((2 << 12) | (1 << 14), 2, 1))
+for flags, unroll, chunked in variants:
+    lib.qsv_debug_set_flags(flags)
+    for ctas in ((32, 296) if quick else (16, 32, 64, 148, 296)):
         for bit in (n_local - 1, n_local // 2, 5):
             pairs = [(n_local + j, bit - j) for j in range(g)]
             ms, gb = timed(pairs, ctas)
             if rank == 0:
-                print("unroll %d ctas %3d swapped local bits %s: %.2f ms  %.1f GB per GPU and direction  %.0f GB/s" % (
-                    unroll, ctas, [pl for _, pl in pairs], ms, gb, gb / ms * 1e3), flush=True)
+                print("unroll %d %s ctas %3d swapped local bits %s: %.2f ms  %.1f GB per GPU and direction  %.0f GB/s" % (
+                    unroll, "chunked    " if chunked else "grid-stride", ctas, [pl for _, pl in pairs], ms, gb,
+                    gb / ms * 1e3), flush=True)
 lib.qsv_debug_set_flags(0)
 st.close()
 dist.destroy_process_group()
