@@ -12,6 +12,7 @@ extern thread_local char g_err[512];
 extern unsigned long long g_launches;
 extern int g_p2p_unroll;
 extern bool g_p2p_chunked;
+extern uint32_t g_p2p_mode;
 
 inline int fail(int code, const char* msg) {
   snprintf(g_err, sizeof(g_err), "%s", msg);

@@ -98,6 +98,8 @@ struct P2PDesc {
   int32_t k, n_local;
   int32_t bits[8];        // ascending local bit positions
   uint32_t beta;          // this rank's pattern of the k global bits
+  uint32_t mode;          // 0 = swap; debug library only (bandwidth probes, destroy the data): 1 = push only (local
+                          // load + remote store), 2 = pull only (remote load + local store)
   uint32_t perm[8];       // bit i of a pattern <-> position bits[perm[i]] ... (patterns are given in the caller's order)
   double2* peer[256];     // peer[lam]: base of the shard of the rank whose global bits read lam (beta: unused)
 };
@@ -146,16 +148,26 @@ swap_p2p_kernel(double2* __restrict__ mine, const __grid_constant__ P2PDesc d) {
         im[u] = x | dep_lam;   // my sub-block that leaves
         ip[u] = x | dep_beta;  // the partner's sub-block that comes here
         if (h < hi) {
+#ifdef QSV_DEBUG_BUILD
+          if (d.mode != 1u) b[u] = __ldcv(theirs + ip[u]);
+          if (d.mode != 2u) a[u] = mine[im[u]];
+#else
           b[u] = __ldcv(theirs + ip[u]);
           a[u] = mine[im[u]];
+#endif
         }
       }
 #pragma unroll
       for (int u = 0; u < kU; u++) {
         const u64 h = h0 + (u64)u * step;
         if (h < hi) {
+#ifdef QSV_DEBUG_BUILD
+          if (d.mode != 1u) mine[im[u]] = b[u];
+          if (d.mode != 2u) theirs[ip[u]] = a[u];
+#else
           mine[im[u]] = b[u];
           theirs[ip[u]] = a[u];
+#endif
         }
       }
     }
@@ -163,6 +175,7 @@ swap_p2p_kernel(double2* __restrict__ mine, const __grid_constant__ P2PDesc d) {
 }
 
 bool g_p2p_chunked = false;  // qsv_debug_set_flags bit 14 (tools/p2p_swap_probe.py)
+uint32_t g_p2p_mode = 0;     // ... bits 15-16, debug library only: P2PDesc::mode
 int g_p2p_unroll = 4;  // tools/p2p_swap_probe.py sweeps it through qsv_debug_set_flags (bits 12-13)
 
 static int make_sub(int n_local, const int32_t* local_qubits, int k, uint32_t pattern, SubDesc* d) {
@@ -268,6 +281,7 @@ int qsv_swap_bits_p2p(double* sv, int n_local, const int32_t* local_qubits, int 
   d.k = k;
   d.n_local = n_local;
   d.beta = my_pattern;
+  d.mode = g_p2p_mode;
   int order[8];
   for (int i = 0; i < k; i++) order[i] = i;
   for (int i = 0; i < k; i++)

@@ -61,7 +61,7 @@ unsigned long long g_launches = 0;
 // qsv_debug_set_flags(); the production library accepts only the bits that select an equivalent kernel variant
 // (results unchanged) and never reads the environment, so a stray variable cannot change results.  The debug
 // library (libqsv_dbg.so, -DQSV_DEBUG_BUILD, used by tools/) also takes QSV_DEBUG_FLAGS and the bits that switch
-// loads / stores / gates off.
+// loads / stores / gates off.  2048 = full group barrier at every stage boundary (no partial barriers).
 [[maybe_unused]] constexpr uint32_t kResultChangingFlags = 1u | 2u | 4u;
 static uint32_t g_debug_flags = 0;
 static bool g_debug_flags_set = false;
@@ -118,6 +118,8 @@ struct __align__(4) PassStage {
   uint8_t first_op, n_ops, n_inner, n_outer;
   uint8_t ebit[kInner];   // inner tile bits in element order (bit j of the in-warp element index)
   uint8_t obit[4];        // outer tile bits (bit j of the warp id)
+  uint8_t sync_mask;      // warp-id bits whose outer tile bit is the same as in the previous stage: at the stage
+  uint8_t sync_pad;       // boundary only the warps that agree on them exchange data (partial barrier); 0 = all warps
   uint16_t ecol[kInner];  // cj[ebit[j]]
   uint16_t ocol[4];       // cj[obit[j]]
 };
@@ -673,7 +675,19 @@ __device__ __forceinline__ void tile_pass_body(double2* __restrict__ sv, const P
     int o = 0;
     PROF_OP_BEGIN
     for (int sidx = 0; sidx < nstages; sidx++) {
-      if (sidx > 0) gsync();  // stage boundary: warps re-partition the tile
+      if (sidx > 0) {  // stage boundary: warps re-partition the tile
+        const uint32_t sm = kDB ? d.stages[sidx].sync_mask : 0u;  // (one CTA per SM: its 16 named barriers are free)
+        if (sm == 0u) {
+          gsync();
+        } else if constexpr (kDB) {
+          // only the warps that agree on the outer bits both stages share exchange data: a barrier among those
+          // 2 or 4 warps (named barriers 4 .. 15: four per group) instead of the whole group
+          uint32_t sub = 0, k2 = 0;
+          for (uint32_t j = 0; j < 3u; j++)
+            if ((sm >> j) & 1u) sub |= ((wid_u >> j) & 1u) << k2++;
+          asm volatile("bar.sync %0, %1;\n" ::"r"(4u + grp * 4u + sub), "r"(256u >> k2) : "memory");
+        }
+      }
       PROF_OP_MARK(4);
       const uint32_t n_inner = d.stages[sidx].n_inner, n_outer = d.stages[sidx].n_outer;
       const int o_end = o + d.stages[sidx].n_ops;
@@ -1198,6 +1212,9 @@ static int build_stages(const HostOp* ops, int n_ops, int b, int* order, PassSta
   const int n_inner = std::min(b, kInner);
   bool done[kMaxOps] = {false};
   int n_done = 0, n_stages = 0, pos = 0;
+  uint32_t all_need = 0;
+  for (int i = 0; i < n_ops; i++) all_need |= ops[i].need;
+  if (popc(all_need) <= n_inner) all_need = 0;  // a single stage: plain padding
   while (n_done < n_ops) {
     uint32_t inner = 0, blocked = 0;
     const int first = pos;
@@ -1213,7 +1230,11 @@ static int build_stages(const HostOp* ops, int n_ops, int b, int* order, PassSta
         blocked |= op.touch;
       }
     }
-    // pad the inner set with the lowest unused tile bits
+    // pad the inner set with the lowest unused tile bits -- in a pass of several stages first with the bits some op
+    // of the pass needs, so that the bits NO op needs stay outer bits in every stage (the warps that agree on them
+    // never exchange data, see PassStage::sync_mask)
+    for (int j = 0; j < b && popc(inner) < n_inner; j++)
+      if (!((inner >> j) & 1u) && ((all_need >> j) & 1u)) inner |= 1u << j;
     for (int j = 0; j < b && popc(inner) < n_inner; j++)
       if (!((inner >> j) & 1u)) inner |= 1u << j;
     PassStage& st = stages[n_stages];
@@ -1711,6 +1732,24 @@ static int lower_pass(PassDesc& d, PassPlan& plan, int n, const int32_t* tile_qu
       st.ebit[j] = (uint8_t)(j < ni ? eo[j] : 0);
       st.ecol[j] = j < ni ? sw1(eo[j]) : 0;
     }
+    // outer bits shared with the previous stage keep their warp-id position
+    st.sync_mask = 0;
+    if (s > 0 && no == d.stages[s - 1].n_outer && !(d.flags & 2048u)) {
+      const PassStage& prev = d.stages[s - 1];
+      int placed[4] = {-1, -1, -1, -1};
+      bool used_ob[16] = {false};
+      for (int j = 0; j < no; j++)
+        for (int q = 0; q < no; q++)
+          if (!used_ob[q] && ob[q] == prev.obit[j]) { placed[j] = ob[q]; used_ob[q] = true; st.sync_mask |= (uint8_t)(1u << j); break; }
+      int q = 0;
+      for (int j = 0; j < no; j++) {
+        if (placed[j] >= 0) continue;
+        while (used_ob[q]) q++;
+        placed[j] = ob[q];
+        used_ob[q] = true;
+      }
+      for (int j = 0; j < no; j++) ob[j] = placed[j];
+    }
     for (int j = 0; j < 4; j++) {
       st.obit[j] = (uint8_t)(j < no ? ob[j] : 0);
       st.ocol[j] = j < no ? sw1(ob[j]) : 0;
@@ -2146,6 +2185,9 @@ int qsv_debug_set_flags(uint32_t flags) {
   g_debug_flags_set = true;
   g_p2p_unroll = ((flags >> 12) & 3u) == 1u ? 8 : ((flags >> 12) & 3u) == 2u ? 2 : ((flags >> 12) & 3u) == 3u ? 1 : 4;
   g_p2p_chunked = (flags >> 14) & 1u;
+#ifdef QSV_DEBUG_BUILD
+  g_p2p_mode = (flags >> 15) & 3u;
+#endif
   return 0;
 }
 

@@ -257,6 +257,53 @@ def test_group_kernel_passes(n, seed, n_tail):
     assert np.array_equal(results[0], results[2])
 
 
+@pytest.mark.parametrize("cover", [9, 10, 11])
+def test_group_kernel_stage_boundaries(cover):
+    """Passes of two and more stages on the warp-group variant: at a stage boundary only the warps that agree on the
+    outer bits both stages share exchange data, so the kernel synchronises just those 2 or 4 warps (PassStage::sync_mask;
+    gates on 9 / 10 / 11 of the tile qubits leave 2 / 1 / 0 shared outer bits).  Same amplitudes as the oracle and, bit
+    for bit, as the kernel with a full group barrier at every boundary (flag 2048) and as the single-buffer variant."""
+    from qiskit_sdk_py_b200.engine import DeviceState
+
+    n = 22
+    rng = np.random.RandomState(100 + cover)
+    vec = rand_state(n, 70 + cover)
+    plan = []
+    for rep in range(3):
+        tile = [0, 1, 2, 3] + sorted(int(q) for q in rng.choice(np.arange(4, n), 7, replace=False))
+        t = [tile[i] for i in rng.permutation(11)]
+        pairs = [(t[0], t[1]), (t[2], t[3]), (t[4], t[5]), (t[6], t[7]), (t[8], t[0])]
+        if cover >= 10:
+            pairs.append((t[9], t[1]))
+        if cover >= 11:
+            pairs.append((t[10], t[2]))
+        ops = [GateOp(_lib.GATE_DENSE2, [a, b], rand_unitary(2, rng)) for a, b in pairs]  # need `cover` > 8 inner bits
+        for a, b in [(t[1], t[2]), (t[8], t[3]), (t[5], t[0])]:
+            ops.append(GateOp(_lib.GATE_DENSE2, [a, b], rand_unitary(2, rng)) if rng.randint(3) else
+                       GateOp(_lib.GATE_DIAG2, [a, b], np.exp(1j * rng.uniform(0, 6, 4))))
+        assert DeviceState.pass_info(n, tile, ops)["stages"] >= 2
+        plan.append((tile, ops))
+    results = []
+    lib = _lib.load()
+    try:
+        for flags in (0, 2048, 16):
+            assert lib.qsv_debug_set_flags(flags) == 0
+            st = make_state(n, vec)
+            for tile, ops in plan:
+                st.apply_pass(tile, ops)
+            results.append(st.download())
+            del st
+    finally:
+        lib.qsv_debug_set_flags(0)
+    ref = vec.copy()
+    for tile, ops in plan:
+        for op in ops:
+            ref = oracle_apply(ref, op, n)
+    assert np.max(np.abs(results[0] - ref)) < TOL
+    assert np.array_equal(results[0], results[1])
+    assert np.array_equal(results[0], results[2])
+
+
 def test_tail_argument_errors():
     st = make_state(10, rand_state(10, 1))
     tile = list(range(8))

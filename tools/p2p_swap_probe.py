@@ -57,18 +57,23 @@ def timed(pairs, ctas, reps=3):
     return float(ms.item()), gb
 
 
-quick = len(sys.argv) > 2 and sys.argv[2] == "quick"  # chunked vs grid-stride only
-variants = ((0, 4, 0), (1 << 14, 4, 1)) if quick else \
-    ((0, 4, 0), (1 << 14, 4, 1), (1 << 12, 8, 0), (2 << 12, 2, 0), ((2 << 12) | (1 << 14), 2, 1))
+mode_arg = sys.argv[2] if len(sys.argv) > 2 else ""
+quick = mode_arg == "quick"  # chunked vs grid-stride only
+if mode_arg == "modes":      # debug library (QSV_LIB_PATH=libqsv_dbg.so): swap vs push-only vs pull-only, all pairs active
+    variants = ((0, 4, 0), (1 << 15, 4, 0), (2 << 15, 4, 0))
+elif quick:
+    variants = ((0, 4, 0), (1 << 14, 4, 1))
+else:
+    variants = ((0, 4, 0), (1 << 14, 4, 1), (1 << 12, 8, 0), (2 << 12, 2, 0), ((2 << 12) | (1 << 14), 2, 1))
 for flags, unroll, chunked in variants:
     lib.qsv_debug_set_flags(flags)
-    for ctas in ((32, 296) if quick else (16, 32, 64, 148, 296)):
-        for bit in (n_local - 1, n_local // 2, 5):
+    for ctas in ((64, 296) if mode_arg == "modes" else (32, 296) if quick else (16, 32, 64, 148, 296)):
+        for bit in ((n_local - 1,) if mode_arg == "modes" else (n_local - 1, n_local // 2, 5)):
             pairs = [(n_local + j, bit - j) for j in range(g)]
             ms, gb = timed(pairs, ctas)
             if rank == 0:
-                print("unroll %d %s ctas %3d swapped local bits %s: %.2f ms  %.1f GB per GPU and direction  %.0f GB/s" % (
-                    unroll, "chunked    " if chunked else "grid-stride", ctas, [pl for _, pl in pairs], ms, gb,
+                print("mode %s unroll %d %s ctas %3d swapped local bits %s: %.2f ms  %.1f GB per GPU and direction  %.0f GB/s" % (
+                    {0: "swap", 1: "push", 2: "pull"}[(flags >> 15) & 3], unroll, "chunked    " if chunked else "grid-stride", ctas, [pl for _, pl in pairs], ms, gb,
                     gb / ms * 1e3), flush=True)
 lib.qsv_debug_set_flags(0)
 st.close()
