@@ -22,6 +22,16 @@ n_local = int(sys.argv[1]) if len(sys.argv) > 1 else 30
 st = ShardedState(n_local + g, DeviceState)
 st.init_basis0()
 lib = _lib.load()
+if len(sys.argv) > 3 and sys.argv[3] == "dense":  # a dense random state instead of |0...0> (are the links data-dependent?)
+    from qiskit_sdk_py_b200 import circuits, lower
+    ins = [i for i in circuits.quantum_volume_instructions(n_local + g, 3, 5) if i["name"] == "unitary"]
+    st.apply_ops([lower.lower_gate(i["name"], i["qubits"], i.get("params")) for i in ins])
+    st.restore_identity_layout()
+    torch.cuda.synchronize()
+    if rank == 0:
+        print("dense random state (3 layers of SU(4)), norm2 = %.12f" % st.norm2(), flush=True)
+    else:
+        st.norm2()
 
 
 def timed(pairs, ctas, reps=3):
@@ -65,6 +75,18 @@ elif quick:
     variants = ((0, 4, 0), (1 << 14, 4, 1))
 else:
     variants = ((0, 4, 0), (1 << 14, 4, 1), (1 << 12, 8, 0), (2 << 12, 2, 0), ((2 << 12) | (1 << 14), 2, 1))
+if mode_arg == "bits":       # the swapped local bits as the circuits choose them (k = log2(world) bits per exchange)
+    variants = ((0, 4, 0),)
+    bit_sets = [[n_local - 1 - j for j in range(g)], [20 - 7 * j for j in range(g)], [9 - 2 * j for j in range(g)],
+                [n_local - 1] + [5 + j for j in range(g - 1)]]
+    for bits in bit_sets:
+        pairs = [(n_local + j, bits[j]) for j in range(g)]
+        for ctas in (296,):
+            ms, gb = timed(pairs, ctas)
+            if rank == 0:
+                print("swapped local bits %s ctas %d: %.2f ms  %.1f GB per GPU and direction  %.0f GB/s" % (
+                    bits, ctas, ms, gb, gb / ms * 1e3), flush=True)
+    variants = ()
 for flags, unroll, chunked in variants:
     lib.qsv_debug_set_flags(flags)
     for ctas in ((64, 296) if mode_arg == "modes" else (32, 296) if quick else (16, 32, 64, 148, 296)):
