@@ -258,14 +258,15 @@ def pick_qubits(requested, torch, reserve=3 << 30):
     return n
 
 
-def timed_passes(st, passes, torch, n):
-    """Run planned passes one by one with CUDA events; returns per-pass ms."""
+def timed_steps(st, steps, torch, n):
+    """Run the steps of DeviceState.plan_flush (pass-kernel launches and qubit-permutation launches) one by one with CUDA
+    events; returns per-step ms."""
     stream = torch.cuda.current_stream()
     events = []
-    for p in passes:
+    for step in steps:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        st.apply_pass(p.tile_qubits, p.ops, tail=p.tail or None)
+        st.run_step(step)
         e1.record(stream)
         events.append((e0, e1))
     torch.cuda.synchronize()
@@ -273,24 +274,28 @@ def timed_passes(st, passes, torch, n):
 
 
 def family_block(name, instructions, n, tile, st, torch, peak):
-    """Per-pass roofline of another circuit family (QFT, random basis-gate circuit) on the resident state."""
+    """Per-pass roofline of another circuit family (QFT, random basis-gate circuit) on the resident state: the launches
+    DeviceState.apply_ops makes for it (fused passes; one in-place permutation launch for the swaps taken out of the
+    stream), each a read + write of the whole state."""
     from qiskit_sdk_py_b200 import lower, planner
 
     ops = [o for o in (lower.lower_gate(i["name"], i["qubits"], i.get("params")) for i in instructions) if o is not None]
-    merged = planner.merge_ops(ops)
-    passes = planner.plan_passes(merged, n, tile, tails=True)
+    steps = st.plan_flush(ops)
+    passes = [what for kind, what in steps if kind == "pass"]
     st.init_basis0()
-    timed_passes(st, passes, torch, n)  # warm-up
-    ms = timed_passes(st, passes, torch, n)
+    timed_steps(st, steps, torch, n)  # warm-up
+    ms = timed_steps(st, steps, torch, n)
     per_pass_gbs = [32.0 * 2 ** n / (t * 1e-3) / 1e9 for t in ms]
     return {
-        "workload": name, "instructions": len(ops), "merged_ops": len(merged), "passes": len(passes),
+        "workload": name, "instructions": len(ops), "merged_ops": len(planner.merge_ops(ops)), "passes": len(steps),
+        "swap_kernel_launches": len(steps) - len(passes),
         "tail_gates": sum(len(p.tail) for p in passes), "pass_section_ms": sum(ms),
         "reference_equivalent_GBps": len(ops) * 32.0 * 2 ** n / (sum(ms) * 1e-3) / 1e9,
         "roofline": {"bound": "hbm", "kernel": "tile_pass_kernel", "unit": "GB/s", "peak": peak,
-                     "achieved": len(passes) * 32.0 * 2 ** n / (sum(ms) * 1e-3) / 1e9,
-                     "frac": len(passes) * 32.0 * 2 ** n / (sum(ms) * 1e-3) / 1e9 / peak,
+                     "achieved": len(steps) * 32.0 * 2 ** n / (sum(ms) * 1e-3) / 1e9,
+                     "frac": len(steps) * 32.0 * 2 ** n / (sum(ms) * 1e-3) / 1e9 / peak,
                      "per_pass_ms": [round(t, 3) for t in ms],
+                     "per_pass_kind": ["pass" if kind == "pass" else "swap_pairs" for kind, _ in steps],
                      "per_pass_frac": [round(g / peak, 3) for g in per_pass_gbs],
                      "worst_pass_frac": min(per_pass_gbs) / peak},
     }

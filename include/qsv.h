@@ -276,6 +276,15 @@ int qsv_ipc_release(void* peer_ptr, uint64_t offset);
 int qsv_scatter_bits(const double* dev_src, int m, const int32_t* dest_bit, uint64_t base, double* dev_dst,
                      int log2_dst, void* stream);
 
+/* SWAP gates on `n_pairs` disjoint qubit pairs (a_i = pairs[2 i], b_i = pairs[2 i + 1]) as ONE in-place pass over the
+ * state: amplitude i trades places with amplitude pi(i) = i with the index bits of every pair exchanged.  The reference
+ * applies a swap as three cx gates = three einsum passes over the vector (qasm_simulator.py:145-161, 545-552; the final
+ * swaps of a QFT, the routing swaps of a transpiled circuit); the host takes swaps out of the gate stream by relabelling
+ * the later gates and settles the accumulated qubit permutation here.  Every amplitude is read and written once (32 * 2^n
+ * bytes); pairs of qubits >= 4 keep 256-byte runs on both sides.  n_pairs <= QSV_MAX_SWAP_PAIRS. */
+#define QSV_MAX_SWAP_PAIRS 20
+int qsv_swap_qubit_pairs(double* sv, int n_qubits, const int32_t* pairs, int n_pairs, void* stream);
+
 /* Sum of |psi|^2 over the local shard (for distributed normalisation / sampling). */
 int qsv_norm2(const double* sv, int n_qubits, void* ws, double* host_out, void* stream);
 

@@ -110,6 +110,7 @@ SIGNATURES = {
     "qsv_alloc": (_c_int, [ctypes.POINTER(_c_void_p), _c_size_t]),
     "qsv_free": (_c_int, [_c_void_p]),
     "qsv_copy_d2d": (_c_int, [_c_void_p, _c_void_p, _c_size_t, _c_void_p]),
+    "qsv_swap_qubit_pairs": (_c_int, [_c_void_p, _c_int, _p_int32, _c_int, _c_void_p]),
     "qsv_debug_set_flags": (_c_int, [ctypes.c_uint32]),
     "qsv_debug_profile": (_c_int, [ctypes.POINTER(ctypes.c_uint64), _c_size_t]),
 }

@@ -196,6 +196,49 @@ static int make_sub(int n_local, const int32_t* local_qubits, int k, uint32_t pa
   return 0;
 }
 
+// ---- SWAP gates on disjoint qubit pairs: one in-place permutation pass over HBM -----------------------------------
+struct SwapPairsDesc {
+  int32_t n_pairs;
+  int32_t a[QSV_MAX_SWAP_PAIRS], b[QSV_MAX_SWAP_PAIRS];
+};
+
+// pi(i) = i with the bits of every pair exchanged, an involution: the thread of the smaller index of {i, pi(i)} swaps the
+// two amplitudes.  Whether a thread is that one is decided by the pair with the highest bit that differs; with all pair
+// bits >= 5 a warp's 32 consecutive indices decide alike, so active warps move 512 contiguous bytes on both sides and the
+// others leave at once.  kU independent index pairs per thread keep enough loads in flight.
+template <int kU>
+__global__ void __launch_bounds__(kThreads)
+swap_pairs_kernel(double2* __restrict__ sv, const __grid_constant__ SwapPairsDesc d, u64 n_amps) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 i0 = (u64)blockIdx.x * blockDim.x + threadIdx.x; i0 < n_amps; i0 += stride * kU) {
+    u64 ii[kU], pp[kU];
+    double2 x[kU], y[kU];
+    bool act[kU];
+#pragma unroll
+    for (int u = 0; u < kU; u++) {
+      const u64 i = i0 + (u64)u * stride;
+      u64 p = i;
+      for (int q = 0; q < d.n_pairs; q++) {
+        const u64 t = ((i >> d.a[q]) ^ (i >> d.b[q])) & 1ull;
+        p ^= (t << d.a[q]) | (t << d.b[q]);
+      }
+      ii[u] = i;
+      pp[u] = p;
+      act[u] = i < n_amps && p > i;
+      if (act[u]) {
+        x[u] = sv[i];
+        y[u] = sv[p];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kU; u++)
+      if (act[u]) {
+        sv[ii[u]] = y[u];
+        sv[pp[u]] = x[u];
+      }
+  }
+}
+
 static int grid_for(u64 n) {
   u64 blocks = (n + kThreads - 1) / kThreads;
   const u64 cap = (u64)sm_count() * 16;
@@ -312,6 +355,30 @@ int qsv_swap_bits_p2p(double* sv, int n_local, const int32_t* local_qubits, int 
     default: QSV_P2P_LAUNCH(4); break;
   }
 #undef QSV_P2P_LAUNCH
+  QSV_LAUNCHED();
+  return 0;
+}
+
+int qsv_swap_qubit_pairs(double* sv, int n_qubits, const int32_t* pairs, int n_pairs, void* stream) {
+  if (!sv || n_qubits < 1 || n_qubits > 40 || n_pairs < 0 || n_pairs > QSV_MAX_SWAP_PAIRS || (n_pairs > 0 && !pairs))
+    return fail(QSV_EINVAL, "qsv_swap_qubit_pairs: bad arguments");
+  if (n_pairs == 0) return 0;
+  SwapPairsDesc d;
+  memset(&d, 0, sizeof(d));
+  d.n_pairs = n_pairs;
+  uint64_t seen = 0;
+  for (int i = 0; i < 2 * n_pairs; i++) {
+    const int q = pairs[i];
+    if (q < 0 || q >= n_qubits || ((seen >> q) & 1ull))
+      return fail(QSV_EINVAL, "qsv_swap_qubit_pairs: the pairs must be disjoint qubits of the register");
+    seen |= 1ull << q;
+    (i & 1 ? d.b : d.a)[i >> 1] = q;
+  }
+  const u64 n_amps = 1ull << n_qubits;
+  const u64 blocks = (n_amps + (u64)kThreads * 4 - 1) / ((u64)kThreads * 4);
+  const u64 cap = (u64)sm_count() * 8;
+  swap_pairs_kernel<4><<<(unsigned)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks)), kThreads, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<double2*>(sv), d, n_amps);
   QSV_LAUNCHED();
   return 0;
 }

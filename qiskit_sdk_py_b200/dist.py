@@ -66,6 +66,7 @@ class ShardedState:
         self._xch_wait_events = []  # (start, after the opening barrier) of the exchanges that are not overlapped
         self.overlap = bool(overlap)  # run the passes that commute with an exchange while it is in flight
         self.overlapped_exchanges = 0
+        self.relabelled_swaps = 0
         self._comm_stream = None
         # NVLink peer memory: shards that can export a CUDA IPC handle (engine.DeviceState) are mapped into every
         # rank of the group once, and the exchanges run as ONE in-place swap kernel per rank (qsv_swap_bits_p2p);
@@ -406,12 +407,23 @@ class ShardedState:
                 self._apply_dense_k(op)
                 self.apply_ops(ops[k + 1:])
                 return
-        remaining = ops
+        remaining = self._mark_swaps(ops)
         while remaining:
             run, deferred, blocked = [], [], set()
             plain = True   # every runnable op acts on local qubits only: the same GateOps on every rank
             for op in remaining:
                 qs = set(op.qubits)
+                if op.kind == "swap":
+                    # a SWAP gate is a relabelling of the two logical qubits: no data moves now, the layout restore (or
+                    # the next exchange that needs one of them) pays for it -- on any rank, global qubits included
+                    if qs & blocked:
+                        blocked |= qs
+                        deferred.append(op)
+                    else:
+                        a, b = op.qubits
+                        self.pos[a], self.pos[b] = self.pos[b], self.pos[a]
+                        self.relabelled_swaps += 1
+                    continue
                 loc = False if (qs & blocked) else self._localise(op)
                 if loc is False:
                     blocked |= qs
@@ -436,6 +448,22 @@ class ShardedState:
             elif pairs:
                 self.swap_many(pairs)
             remaining = carry + deferred
+
+    @staticmethod
+    def _mark_swaps(ops):
+        """cx a,b; cx b,a; cx a,b (a SWAP in the simulator basis, back to back) -> one ("swap", [a, b]) marker op."""
+        out, i = [], 0
+        while i < len(ops):
+            o = ops[i]
+            if (o.kind == _lib.GATE_CX and i + 2 < len(ops) and ops[i + 1].kind == _lib.GATE_CX
+                    and ops[i + 2].kind == _lib.GATE_CX and tuple(ops[i + 1].qubits) == tuple(o.qubits)[::-1]
+                    and tuple(ops[i + 2].qubits) == tuple(o.qubits)):
+                out.append(GateOp("swap", list(o.qubits), None))
+                i += 3
+            else:
+                out.append(o)
+                i += 1
+        return out
 
     p2p_stepwise = True   # fused peer-memory exchanges partner by partner (4 GPUs: 1886 -> 1815 ms of exchanges per step)
     carry_over = True  # gates that need not run before an exchange wait for the passes after it (fuller passes)
@@ -606,15 +634,28 @@ class ShardedState:
 
     def _plan_swap(self, deferred):
         """[(physical global bit, physical local victim bit), ...] for the global qubits the deferred gates need."""
+        # a deferred SWAP marker renames its two qubits for everything behind it: look at the deferred gates through the
+        # names their qubits have NOW
+        alias, seen_by = {}, []
+        for op in deferred:
+            if op.kind == "swap":
+                a, b = op.qubits
+                alias[a], alias[b] = alias.get(b, b), alias.get(a, a)
+                seen_by.append(None)
+            else:
+                seen_by.append((op, [alias.get(q, q) for q in op.qubits]))
         first_use, order = {}, []
-        for idx, op in enumerate(deferred):
-            for q in op.qubits:
+        for idx, item in enumerate(seen_by):
+            for q in (item[1] if item else ()):
                 if q not in first_use:
                     first_use[q] = idx
                     order.append(q)
         need = []
-        for op in deferred:
-            for k, q in enumerate(op.qubits):
+        for item in seen_by:
+            if item is None:
+                continue
+            op, qubits = item
+            for k, q in enumerate(qubits):
                 if self.pos[q] < self.n_local or q in need:
                     continue
                 diag_ok = op.kind in (_lib.GATE_DIAG1, _lib.GATE_DIAG2) or (op.kind == _lib.GATE_CX and k == 0)
@@ -629,9 +670,9 @@ class ShardedState:
                 continue
             # victim: local logical qubit used furthest in the future (and not a partner of q's next gate)
             partners = set()
-            for op in deferred:
-                if q in op.qubits:
-                    partners = set(op.qubits)
+            for item in seen_by:
+                if item and q in item[1]:
+                    partners = set(item[1])
                     break
             best, best_use = None, -1
             for lq in range(self.n):

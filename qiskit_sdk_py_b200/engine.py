@@ -11,7 +11,7 @@ import numpy as np
 
 from . import _lib
 from .lower import GateOp
-from .planner import DEFAULT_TILE_QUBITS, merge_ops, plan_passes
+from .planner import DEFAULT_TILE_QUBITS, eliminate_swaps, merge_ops, plan_passes
 
 _p_int32 = ctypes.POINTER(ctypes.c_int32)
 
@@ -222,11 +222,36 @@ class DeviceState:
                 run.append(op)
         self._flush(run)
 
+    def plan_flush(self, run):
+        """What _flush does for a run of 1-/2-qubit ops, as a list of steps (host only): ("pass", planner.Pass) = one
+        launch of the fused pass kernel, ("swap", pairs) = one qsv_swap_qubit_pairs launch.  SWAP gates are taken out of the
+        stream by relabelling (planner.eliminate_swaps) and the qubit permutation they leave is settled at the end."""
+        ops, rounds = eliminate_swaps(merge_ops(run), self.n)
+        steps = [("pass", p) for p in plan_passes(ops, self.n, self.tile_qubits, tails=True)]
+        steps += [("swap", pairs) for pairs in rounds]
+        return steps
+
+    def run_step(self, step):
+        kind, what = step
+        if kind == "pass":
+            self.apply_pass(what.tile_qubits, what.ops, tail=what.tail)
+        else:
+            self.swap_qubit_pairs(what)
+
+    def swap_qubit_pairs(self, pairs):
+        """SWAP gates on disjoint qubit pairs as one in-place pass over HBM (qsv_swap_qubit_pairs)."""
+        flat = [int(q) for pair in pairs for q in pair]
+        with self._ctx():
+            _lib.check(self.lib.qsv_swap_qubit_pairs(self.ptr, self.n, _int32_array(flat), len(pairs), self.stream),
+                       "qsv_swap_qubit_pairs")
+        self.passes_launched += 1
+        self.gates_applied += len(pairs)
+
     def _flush(self, run):
         if not run:
             return
-        for p in plan_passes(merge_ops(run), self.n, self.tile_qubits, tails=True):
-            self.apply_pass(p.tile_qubits, p.ops, tail=p.tail)
+        for step in self.plan_flush(run):
+            self.run_step(step)
 
     # -- measurement -----------------------------------------------------------------
     def prob_qubit(self, qubit):

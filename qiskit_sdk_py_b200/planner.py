@@ -232,6 +232,69 @@ def pair_isolated_1q(ops):
     return [op for op in out if op is not None]
 
 
+_SWAP = np.array([[1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=complex)
+MIN_SWAPS_TO_ELIMINATE = 4  # fewer swaps ride along in the passes of their neighbours for less than a pass of their own
+
+
+def is_swap(op):
+    """A dense 2-qubit op that is exactly the SWAP permutation matrix (three merged cx gates, qasm_simulator.py:145-161:
+    the products of 0/1 matrices are exact)."""
+    return op.kind == _lib.GATE_DENSE2 and op.matrix is not None and np.array_equal(np.asarray(op.matrix), _SWAP)
+
+
+def eliminate_swaps(ops, n_qubits, low_qubits=None, min_swaps=MIN_SWAPS_TO_ELIMINATE):
+    """Take the SWAP gates out of a (merged) op stream by relabelling: SWAP(a, b) G(a, ...) = G(b, ...) SWAP(a, b), so a
+    swap moves to the end of the stream when the qubits of every later gate are renamed, and all swaps together leave ONE
+    qubit permutation to settle there -- by qsv_swap_qubit_pairs, one in-place pass over HBM per round of disjoint
+    transpositions, instead of a dense 4x4 tensor op per swap and a pass per three swaps (the final swaps of a QFT are
+    16 swaps = 5 copy-only passes at 33 qubits; routing swaps of a transpiled circuit).
+
+    Returns (ops without the eliminated swaps, rounds): ``rounds`` is a list of at most two lists of disjoint qubit pairs
+    (any permutation is a product of two involutions); applying the ops, then round 0, then round 1 equals the input
+    stream.  A swap on one of the ``low_qubits`` pinned bits (at the time it is met) stays a gate: the pass kernel moves
+    those in 256-byte pieces, the permutation kernel would scatter 16-byte accesses.  Streams with fewer than
+    ``min_swaps`` eliminable swaps are returned unchanged."""
+    n_low = LOW_QUBITS if low_qubits is None else low_qubits
+    where = list(range(n_qubits))  # where[q] = qubit that currently holds the content the stream calls q
+    out, n_elim = [], 0
+    for op in ops:
+        if op.kind == "densek":
+            return list(ops), []
+        qs = [where[q] for q in op.qubits]
+        if is_swap(op) and min(qs) >= n_low:
+            where[op.qubits[0]], where[op.qubits[1]] = where[op.qubits[1]], where[op.qubits[0]]
+            n_elim += 1
+            continue
+        out.append(op if list(op.qubits) == qs else GateOp(op.kind, qs, op.matrix))
+    if n_elim < min_swaps:
+        return list(ops), []
+    # settle: the content of q sits at where[q] and has to move to q, i.e. position p -> m(p) with m = where^-1
+    m = [0] * n_qubits
+    for q, p in enumerate(where):
+        m[p] = q
+    rounds = [[], []]
+    seen = [False] * n_qubits
+    for start in range(n_qubits):
+        if seen[start] or m[start] == start:
+            continue
+        cyc = []
+        p = start
+        while not seen[p]:
+            seen[p] = True
+            cyc.append(p)
+            p = m[p]
+        length = len(cyc)
+        # m = t2 o t1 on the cycle c_0 -> c_1 -> ...: t1(c_i) = c_(-i), t2(c_i) = c_(1-i), two reflections
+        for i in range(length):
+            j = (-i) % length
+            if i < j:
+                rounds[0].append((cyc[i], cyc[j]))
+            j = (1 - i) % length
+            if i < j:
+                rounds[1].append((cyc[i], cyc[j]))
+    return out, [r for r in rounds if r]
+
+
 def _relabel(op, layout):
     return GateOp(op.kind, [layout[q] for q in op.qubits], op.matrix)
 

@@ -1,4 +1,5 @@
 """GPU parity tests of the libqsv kernels against the numpy oracle, through the C-ABI (ctypes)."""
+import ctypes
 import itertools
 
 import numpy as np
@@ -333,6 +334,57 @@ def test_qft_through_planner_tails(n):
     for op in ops:
         ref = oracle_apply(ref, op, n)
     assert np.max(np.abs(st.download() - ref)) < 1e-11
+
+
+@pytest.mark.parametrize("n,pairs", [(2, [(0, 1)]), (6, [(4, 5)]), (10, [(0, 9), (3, 4)]), (14, [(4, 13), (5, 12), (6, 11)]),
+                                     (18, [(4, 17), (9, 10), (1, 16)]), (21, [(20 - j, 4 + j) for j in range(8)]),
+                                     (22, [(5, 21), (4, 6)])])
+def test_swap_qubit_pairs(n, pairs):
+    """qsv_swap_qubit_pairs: SWAP gates on disjoint qubit pairs as one in-place pass -- bit for bit the state with those
+    index bits exchanged (the reference applies a swap as three cx einsum passes, qasm_simulator.py:545-552: exact
+    permutations either way)."""
+    vec = rand_state(n, 300 + n)
+    st = make_state(n, vec)
+    st.swap_qubit_pairs(pairs)
+    t = vec.reshape([2] * n)
+    for a, b in pairs:
+        t = np.swapaxes(t, n - 1 - a, n - 1 - b)
+    assert np.array_equal(st.download(), np.ascontiguousarray(t).reshape(-1))
+    st.swap_qubit_pairs(pairs)  # an involution
+    assert np.array_equal(st.download(), vec)
+    lib = _lib.load()
+    bad = (ctypes.c_int32 * 4)(0, 1, 1, 2) if n > 2 else (ctypes.c_int32 * 4)(0, 0, 1, 1)
+    assert lib.qsv_swap_qubit_pairs(st.ptr, n, bad, 2, None) != 0  # overlapping pairs are refused
+
+
+def test_swaps_leave_the_gate_stream():
+    """DeviceState.apply_ops takes SWAP gates (three cx) out of the stream by relabelling the later gates and settles the
+    qubit permutation with qsv_swap_qubit_pairs (planner.eliminate_swaps): same state as the oracle applying every cx,
+    with fewer launches than gates-only planning."""
+    from qiskit_sdk_py_b200 import planner
+
+    n = 16
+    rng = np.random.RandomState(77)
+    vec = rand_state(n, 78)
+    ops = []
+    for layer in range(4):
+        for _ in range(5):
+            a, b = (int(x) for x in rng.choice(n, 2, replace=False))
+            ops.append(GateOp(_lib.GATE_DENSE2, [a, b], rand_unitary(2, rng)))
+        for _ in range(4):
+            a, b = (int(x) for x in rng.choice(np.arange(4, n), 2, replace=False))
+            ops += [GateOp(_lib.GATE_CX, [a, b], None), GateOp(_lib.GATE_CX, [b, a], None), GateOp(_lib.GATE_CX, [a, b], None)]
+        ops.append(GateOp(_lib.GATE_DIAG2, [int(rng.randint(n // 2)), int(n // 2 + rng.randint(n // 2))],
+                          np.exp(1j * rng.uniform(0, 6, 4))))
+    st = make_state(n, vec)
+    steps = st.plan_flush(ops)
+    assert any(kind == "swap" for kind, _ in steps)
+    assert not any(planner.is_swap(o) and min(o.qubits) >= 4 for kind, p in steps if kind == "pass" for o in p.ops)
+    st.apply_ops(ops)
+    ref = vec.copy()
+    for op in ops:
+        ref = oracle_apply(ref, op, n)
+    assert np.max(np.abs(st.download() - ref)) < TOL
 
 
 @pytest.mark.parametrize("n,k", [(3, 3), (5, 3), (9, 4), (12, 5), (13, 6), (14, 7), (9, 9), (15, 3), (11, 4), (16, 4),

@@ -309,6 +309,57 @@ def test_isolated_1q_gates_of_a_pass_are_paired():
     assert np.max(np.abs(st.vec - ref)) < 1e-12
 
 
+def test_swaps_are_eliminated_by_relabelling():
+    """planner.eliminate_swaps: SWAP gates leave the stream (later gates renamed), the permutation they leave is at most two
+    rounds of disjoint transpositions; ops + rounds = the original stream (oracle), swaps on the pinned low qubits stay
+    gates, short streams are left alone, and a QFT's final swaps become one round."""
+    from oracle import basicaer_oracle as orc
+    from qiskit_sdk_py_b200 import _lib, circuits, lower, planner
+    from qiskit_sdk_py_b200.lower import GateOp
+
+    rng = np.random.RandomState(1)
+
+    def ru(k):
+        q, _ = np.linalg.qr(rng.standard_normal((2 ** k, 2 ** k)) + 1j * rng.standard_normal((2 ** k, 2 ** k)))
+        return q
+
+    def run(vec, ops, n):
+        for o in ops:
+            mat = np.diag(o.matrix) if o.kind in (_lib.GATE_DIAG1, _lib.GATE_DIAG2) else \
+                orc.cx_gate_matrix() if o.kind == _lib.GATE_CX else o.matrix
+            vec = orc.apply_unitary(vec.reshape([2] * n), mat, list(o.qubits)).reshape(-1)
+        return vec
+
+    n = 9
+    swap = planner._SWAP
+    for trial in range(20):
+        ops = []
+        for _ in range(25):
+            a, b = (int(x) for x in rng.choice(n, 2, replace=False))
+            r = rng.randint(4)
+            ops.append(GateOp(_lib.GATE_DENSE2, [a, b], swap.copy()) if r < 2 else
+                       GateOp(_lib.GATE_DENSE2, [a, b], ru(2)) if r == 2 else GateOp(_lib.GATE_DENSE1, [a], ru(1)))
+        vec = rng.standard_normal(2 ** n) + 1j * rng.standard_normal(2 ** n)
+        out, rounds = planner.eliminate_swaps(ops, n, low_qubits=2)
+        assert len(rounds) <= 2
+        got = run(vec.copy(), out, n)
+        for rnd in rounds:
+            qs = [q for pair in rnd for q in pair]
+            assert len(set(qs)) == len(qs) and min(qs) >= 2
+            got = run(got, [GateOp(_lib.GATE_DENSE2, list(pair), swap) for pair in rnd], n)
+        assert np.max(np.abs(got - run(vec.copy(), ops, n))) < 1e-12
+        assert all(min(o.qubits) < 2 for o in out if planner.is_swap(o))
+    few = [GateOp(_lib.GATE_DENSE2, [4, 5], swap.copy()), GateOp(_lib.GATE_DENSE1, [4], ru(1))]
+    out, rounds = planner.eliminate_swaps(few, n)
+    assert rounds == [] and out == few
+    ins = circuits.qft(33)["experiments"][0]["instructions"]
+    merged = planner.merge_ops([o for o in (lower.lower_gate(i["name"], i["qubits"], i.get("params")) for i in ins)
+                                if o is not None])
+    out, rounds = planner.eliminate_swaps(merged, 33)
+    assert rounds == [[(q, 32 - q) for q in range(4, 16)]]
+    assert len(planner.plan_passes(out, 33, tails=True)) == 6  # 10 with the swaps as gates
+
+
 def test_in_tile_diagonals_behind_a_tail_join_the_pass():
     """plan_passes(tails=True): the controlled phases onto the pinned low qubits at the end of a QFT fan become ready
     only behind tail gates; they are appended to the pass's gates (diagonal gates commute with the all-diagonal tail)

@@ -61,6 +61,7 @@ class DryState(ShardedState):
         self.overlap = os.environ.get("QSV_DRY_OVERLAP", "1") == "1"
         self.carry_over = os.environ.get("QSV_DRY_CARRY", "1") == "1"
         self.overlapped_exchanges = 0
+        self.relabelled_swaps = 0
         self._peers = self._comm_stream = None
         self._xch_events = []
         self.late_per_exchange = []

@@ -10,21 +10,26 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 30
 ins = circuits.qft(n)["experiments"][0]["instructions"]
 ops = [o for o in (lower.lower_gate(i["name"], i["qubits"], i.get("params")) for i in ins) if o is not None]
 merged = planner.merge_ops(ops)
-passes = planner.plan_passes(merged, n, tails=True)
 st = DeviceState(n)
+steps = st.plan_flush(ops)  # what DeviceState.apply_ops launches: fused passes + the permutation launch for the swaps
+passes = steps
 st.init_basis0()
-for p in passes:  # warm-up
-    st.apply_pass(p.tile_qubits, p.ops, tail=p.tail)
+for step in steps:  # warm-up
+    st.run_step(step)
 torch.cuda.synchronize()
 total = 0.0
-for p in passes:
+for step in steps:
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    st.apply_pass(p.tile_qubits, p.ops, tail=p.tail)
+    st.run_step(step)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     total += ms
+    if step[0] == "swap":
+        print("swap_qubit_pairs: %2d pairs %s : %7.3f ms" % (len(step[1]), step[1], ms))
+        continue
+    p = step[1]
     info = DeviceState.pass_info(n, p.tile_qubits, p.ops)
     kinds = {}
     for o in p.ops:
