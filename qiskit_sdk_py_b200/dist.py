@@ -1073,6 +1073,10 @@ def bench_main(args, bench):
         st.OVERLAP_TARGET_GATES = int(os.environ["QSV_DIST_OVERLAP_GATES"])
     if os.environ.get("QSV_DIST_CARRY"):      # A/B knobs of tools/: carry-over of the gates an exchange does not need,
         st.carry_over = os.environ["QSV_DIST_CARRY"] == "1"
+    if os.environ.get("QSV_DIST_MIN_OVL_SWAPS"):  # 1 = pairwise swaps overlap their late passes too
+        st.MIN_OVERLAP_SWAPS = int(os.environ["QSV_DIST_MIN_OVL_SWAPS"])
+    if os.environ.get("QSV_DIST_MIN_OVL_GATES"):
+        st.MIN_OVERLAP_GATES = int(os.environ["QSV_DIST_MIN_OVL_GATES"])
     if os.environ.get("QSV_DIST_STEPWISE"):
         st.p2p_stepwise = os.environ["QSV_DIST_STEPWISE"] == "1"
     if os.environ.get("QSV_DIST_XSMS"):       # SMs left to the exchange kernel under the sub-block passes
