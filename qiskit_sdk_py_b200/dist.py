@@ -680,7 +680,8 @@ class ShardedState:
                     continue
                 # the pinned low bits stay local when passes are to overlap the exchange: they are tile bits of every
                 # pass and a sub-block pass cannot have a swapped bit in its tile
-                if self.overlap and self.pos[lq] < _LOW_BITS and self.n_local - _LOW_BITS > 2 * self.g:
+                # (and exchanging one of them with a peer would move pieces of 16 ... 128 bytes over NVLink)
+                if self.pos[lq] < _LOW_BITS and self.n_local - _LOW_BITS > 2 * self.g:
                     continue
                 use = first_use.get(lq, never)
                 if use > best_use:
@@ -711,11 +712,23 @@ class ShardedState:
                 victim = max(p for p in range(self.n_local) if p not in homes)
                 self.swap_global_local(self.pos[q_home], victim)
         # ... then every misplaced global bit receives its home qubit in ONE fused exchange
+        swap = np.array([[1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=complex)
         pairs = [(phys, self.pos[phys]) for phys in range(self.n_local, self.n) if self.pos[phys] != phys]
+        # a home qubit that sits in one of the lowest local bits (a QFT's final swaps send qubit n-1 to bit 0) first moves
+        # to a high local bit inside the shard: exchanging bit 0 with a peer would move 16-byte pieces over NVLink
+        if any(pl < _LOW_BITS for _, pl in pairs) and self.n_local - _LOW_BITS > 2 * self.g:
+            busy = {pl for _, pl in pairs}
+            free_high = [p for p in range(self.n_local - 1, _LOW_BITS - 1, -1) if p not in busy]
+            ops = []
+            for (_, pl), high in zip([pr for pr in pairs if pr[1] < _LOW_BITS], free_high):
+                ops.append(GateOp(_lib.GATE_DENSE2, [pl, high], swap))
+                qa, qb = self._logical_at(pl), self._logical_at(high)
+                self.pos[qa], self.pos[qb] = high, pl
+            self.shard.apply_ops(ops)
+            pairs = [(phys, self.pos[phys]) for phys in range(self.n_local, self.n) if self.pos[phys] != phys]
         if pairs:
             self.swap_many(pairs)
         # now fix the local permutation with SWAP gates
-        swap = np.array([[1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=complex)
         ops = []
         pos = list(self.pos)
         for q in range(self.n_local):

@@ -292,7 +292,10 @@ def eliminate_swaps(ops, n_qubits, low_qubits=None, min_swaps=MIN_SWAPS_TO_ELIMI
             j = (1 - i) % length
             if i < j:
                 rounds[1].append((cyc[i], cyc[j]))
-    return out, [r for r in rounds if r]
+    rounds = [r for r in rounds if r]
+    if n_elim < min_swaps * len(rounds):  # chains of swaps (cycles) need two launches: they have to replace more gates
+        return list(ops), []
+    return out, rounds
 
 
 def _relabel(op, layout):

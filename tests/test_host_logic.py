@@ -340,8 +340,8 @@ def test_swaps_are_eliminated_by_relabelling():
             ops.append(GateOp(_lib.GATE_DENSE2, [a, b], swap.copy()) if r < 2 else
                        GateOp(_lib.GATE_DENSE2, [a, b], ru(2)) if r == 2 else GateOp(_lib.GATE_DENSE1, [a], ru(1)))
         vec = rng.standard_normal(2 ** n) + 1j * rng.standard_normal(2 ** n)
-        out, rounds = planner.eliminate_swaps(ops, n, low_qubits=2)
-        assert len(rounds) <= 2
+        out, rounds = planner.eliminate_swaps(ops, n, low_qubits=2, min_swaps=1)
+        assert 1 <= len(rounds) <= 2
         got = run(vec.copy(), out, n)
         for rnd in rounds:
             qs = [q for pair in rnd for q in pair]
@@ -352,6 +352,9 @@ def test_swaps_are_eliminated_by_relabelling():
     few = [GateOp(_lib.GATE_DENSE2, [4, 5], swap.copy()), GateOp(_lib.GATE_DENSE1, [4], ru(1))]
     out, rounds = planner.eliminate_swaps(few, n)
     assert rounds == [] and out == few
+    chain = [GateOp(_lib.GATE_DENSE2, [4 + i, 5 + i], swap.copy()) for i in range(4)]  # a 5-cycle: two launches for 4 swaps
+    out, rounds = planner.eliminate_swaps(chain, n)
+    assert rounds == [] and out == chain
     ins = circuits.qft(33)["experiments"][0]["instructions"]
     merged = planner.merge_ops([o for o in (lower.lower_gate(i["name"], i["qubits"], i.get("params")) for i in ins)
                                 if o is not None])
