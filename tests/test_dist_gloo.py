@@ -352,6 +352,56 @@ def test_bench_parity_gate(tmp_path, world):
     assert res[0] >= 5
 
 
+def _swap_relabel_worker(rank, world, port, n, out_dir):
+    for p in (ROOT, os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from fake_state import FakeState
+    from oracle import basicaer_oracle as orc
+    from qiskit_sdk_py_b200 import _lib, circuits, lower
+    from qiskit_sdk_py_b200.dist import ShardedState
+
+    # a QFT with its final swaps (qubit n-1 <-> 0, ...: the home qubits of the global bits end up in the LOWEST local
+    # bits), then a few more gates and swaps on global qubits behind deferred gates
+    ins = [i for i in circuits.qft(n, state_seed=3)["experiments"][0]["instructions"] if i["name"] not in ("measure", "barrier")]
+    ins += circuits.random_basis_instructions(n, 3, 21)
+    for a, b in ((n - 1, 2), (n - 2, n - 1), (0, n - 1)):
+        ins += [{"name": "cx", "qubits": [a, b]}, {"name": "cx", "qubits": [b, a]}, {"name": "cx", "qubits": [a, b]}]
+        ins += circuits.random_basis_instructions(n, 1, 30 + a)
+    ops = [o for o in (lower.lower_gate(i["name"], i["qubits"], i.get("params")) for i in ins) if o is not None]
+    st = ShardedState(n, lambda k: FakeState(k, tile_qubits=5), chunk_amps=16)
+    st.init_basis0()
+    st.apply_ops(ops)
+    assert st.relabelled_swaps >= n // 2 + 3
+    swaps_before_restore = st.swaps
+    full = st.gather_statevector()  # restores the identity layout
+    assert st.pos == list(range(n))
+    ref = np.zeros(2 ** n, dtype=complex)
+    ref[0] = 1.0
+    for o in ops:
+        mat = np.diag(o.matrix) if o.kind in (_lib.GATE_DIAG1, _lib.GATE_DIAG2) else \
+            orc.cx_gate_matrix() if o.kind == _lib.GATE_CX else o.matrix
+        ref = orc.apply_unitary(ref.reshape([2] * n), mat, list(o.qubits)).reshape(-1)
+    assert np.max(np.abs(full - ref)) < 1e-12
+    if rank == 0:
+        np.save(os.path.join(out_dir, "relabel_%d.npy" % world), np.array([st.relabelled_swaps, swaps_before_restore, st.swaps]))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n", [(2, 10), (4, 11), (8, 12)])
+def test_swaps_are_relabelled_on_the_sharded_state(tmp_path, world, n):
+    """ShardedState.apply_ops turns cx a,b; cx b,a; cx a,b into a relabelling of the two logical qubits (no exchange, no
+    pass), also for global qubits and behind deferred gates; restore_identity_layout settles the layout once and keeps the
+    lowest local bits out of the exchange.  Same state as the oracle applying every cx."""
+    port = _free_port()
+    mp.spawn(_swap_relabel_worker, args=(world, port, n, str(tmp_path)), nprocs=world, join=True)
+    res = np.load(os.path.join(str(tmp_path), "relabel_%d.npy" % world))
+    assert res[0] >= n // 2 + 3
+
+
 def _overlap_worker(rank, world, port, n, out_dir):
     for p in (ROOT, os.path.join(ROOT, "tests")):
         if p not in sys.path:
