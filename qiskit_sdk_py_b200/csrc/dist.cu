@@ -205,10 +205,32 @@ struct SwapPairsDesc {
 // pi(i) = i with the bits of every pair exchanged, an involution: the thread of the smaller index of {i, pi(i)} swaps the
 // two amplitudes.  Whether a thread is that one is decided by the pair with the highest bit that differs; with all pair
 // bits >= 5 a warp's 32 consecutive indices decide alike, so active warps move 512 contiguous bytes on both sides and the
-// others leave at once.  kU independent index pairs per thread keep enough loads in flight.
+// others leave at once.  kU independent index pairs per thread keep enough loads in flight.  pi is a permutation of the
+// index BITS, i.e. the OR of the images of the index's bytes: five 256-entry tables in shared memory (built per CTA from
+// the pairs) replace the per-pair 64-bit shift arithmetic, which made the first version ALU-bound (83 % ALU pipe, 49 %
+// DRAM: profiles/r2_swap_pairs_kernel_ncu.txt).
 template <int kU>
 __global__ void __launch_bounds__(kThreads)
 swap_pairs_kernel(double2* __restrict__ sv, const __grid_constant__ SwapPairsDesc d, u64 n_amps) {
+  __shared__ uint8_t dest[40];      // dest[s] = where index bit s goes
+  __shared__ u64 tab[5][256];       // tab[c][v] = image of byte c of the index holding the value v
+  if (threadIdx.x < 40) {
+    int to = threadIdx.x;
+    for (int q = 0; q < d.n_pairs; q++) {
+      if (d.a[q] == (int)threadIdx.x) to = d.b[q];
+      if (d.b[q] == (int)threadIdx.x) to = d.a[q];
+    }
+    dest[threadIdx.x] = (uint8_t)to;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 5 * 256; e += blockDim.x) {
+    const int c = e >> 8, v = e & 255;
+    u64 img = 0;
+    for (int j = 0; j < 8; j++)
+      if ((v >> j) & 1) img |= 1ull << dest[8 * c + j];
+    tab[c][v] = img;
+  }
+  __syncthreads();
   const u64 stride = (u64)gridDim.x * blockDim.x;
   for (u64 i0 = (u64)blockIdx.x * blockDim.x + threadIdx.x; i0 < n_amps; i0 += stride * kU) {
     u64 ii[kU], pp[kU];
@@ -217,11 +239,9 @@ swap_pairs_kernel(double2* __restrict__ sv, const __grid_constant__ SwapPairsDes
 #pragma unroll
     for (int u = 0; u < kU; u++) {
       const u64 i = i0 + (u64)u * stride;
-      u64 p = i;
-      for (int q = 0; q < d.n_pairs; q++) {
-        const u64 t = ((i >> d.a[q]) ^ (i >> d.b[q])) & 1ull;
-        p ^= (t << d.a[q]) | (t << d.b[q]);
-      }
+      const uint32_t lo = (uint32_t)i, hi = (uint32_t)(i >> 32);
+      const u64 p = tab[0][lo & 255u] | tab[1][(lo >> 8) & 255u] | tab[2][(lo >> 16) & 255u] | tab[3][lo >> 24] |
+                    tab[4][hi & 255u];
       ii[u] = i;
       pp[u] = p;
       act[u] = i < n_amps && p > i;
