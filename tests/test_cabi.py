@@ -47,6 +47,13 @@ def test_argument_validation_without_gpu():
     assert rc == _lib.QSV_EINVAL
     assert b"qsv_apply_pass" in lib.qsv_last_error()
     assert lib.qsv_prob_qubit(None, 4, 0, None, None, None) == _lib.QSV_EINVAL
+    import ctypes
+
+    pairs = (ctypes.c_int32 * 4)(4, 5, 5, 6)  # overlapping pairs; a dummy non-null pointer is never dereferenced on the host
+    assert lib.qsv_swap_qubit_pairs(None, 8, pairs, 2, None) == _lib.QSV_EINVAL
+    assert lib.qsv_swap_qubit_pairs(ctypes.c_void_p(16), 8, pairs, 2, None) == _lib.QSV_EINVAL
+    assert b"disjoint" in lib.qsv_last_error()
+    assert lib.qsv_swap_qubit_pairs(ctypes.c_void_p(16), 8, pairs, 0, None) == 0  # nothing to do: no launch
 
 
 def test_no_cpu_fallback_without_cuda():
