@@ -435,6 +435,58 @@ def test_partial_plan_runs_what_must_run_and_leaves_a_successor_closed_rest():
     assert np.max(np.abs(st.vec - ref)) < 1e-12
 
 
+@pytest.mark.parametrize("seed", range(12))
+def test_full_host_pipeline_on_random_diagonal_heavy_circuits(seed):
+    """merge_ops -> eliminate_swaps -> plan_passes(tails) with every planner rule on (diagonal tails, in-tile diagonals
+    behind a tail, diagonal packing, paired 1-qubit gates, in-pass scheduling) -> the numpy test double pass by pass, then
+    the swap rounds: the oracle's state for random circuits that are mostly diagonal gates, cx, swaps and rotations."""
+    from fake_state import FakeState
+    from oracle import basicaer_oracle as orc
+    from qiskit_sdk_py_b200 import _lib, lower, planner
+
+    rng = np.random.RandomState(500 + seed)
+    n = int(rng.randint(7, 11))
+    tile = int(rng.randint(5, min(n, 8) + 1))
+    ins = []
+    for _ in range(int(rng.randint(40, 120))):
+        r = rng.randint(10)
+        a, b = (int(x) for x in rng.choice(n, 2, replace=False))
+        if r < 3:    # controlled phase in the simulator basis: u1, cx, u1, cx, u1
+            lam = float(rng.uniform(-3, 3))
+            ins += [{"name": "u1", "qubits": [a], "params": [lam / 2]}, {"name": "cx", "qubits": [a, b]},
+                    {"name": "u1", "qubits": [b], "params": [-lam / 2]}, {"name": "cx", "qubits": [a, b]},
+                    {"name": "u1", "qubits": [b], "params": [lam / 2]}]
+        elif r < 5:
+            ins.append({"name": str(rng.choice(["u1", "rz"])), "qubits": [a], "params": [float(rng.uniform(-3, 3))]})
+        elif r < 6:
+            ins += [{"name": "cx", "qubits": [a, b]}, {"name": "cx", "qubits": [b, a]}, {"name": "cx", "qubits": [a, b]}]
+        elif r < 8:
+            ins.append({"name": "u3", "qubits": [a], "params": [float(x) for x in rng.uniform(-3, 3, 3)]})
+        elif r < 9:
+            ins.append({"name": "cx", "qubits": [a, b]})
+        else:
+            ins.append({"name": "u2", "qubits": [a], "params": [float(x) for x in rng.uniform(-3, 3, 2)]})
+    ops = [o for o in (lower.lower_gate(i["name"], i["qubits"], i.get("params")) for i in ins) if o is not None]
+    merged = planner.merge_ops(ops)
+    out, rounds = planner.eliminate_swaps(merged, n, low_qubits=min(planner.LOW_QUBITS, tile - 2), min_swaps=2)
+    passes = planner.plan_passes(out, n, tile_qubits=tile, tails=True)
+    st = FakeState(n, tile_qubits=tile)
+    vec = rng.standard_normal(2 ** n) + 1j * rng.standard_normal(2 ** n)
+    st.vec = vec.copy()
+    for p in passes:
+        st.apply_pass(p.tile_qubits, p.ops, tail=p.tail)
+    got = st.vec
+    for rnd in rounds:
+        for pair in rnd:
+            got = orc.apply_unitary(got.reshape([2] * n), planner._SWAP, list(pair)).reshape(-1)
+    ref = vec.copy()
+    for o in ops:
+        mat = np.diag(o.matrix) if o.kind in (_lib.GATE_DIAG1, _lib.GATE_DIAG2) else \
+            orc.cx_gate_matrix() if o.kind == _lib.GATE_CX else o.matrix
+        ref = orc.apply_unitary(ref.reshape([2] * n), mat, list(o.qubits)).reshape(-1)
+    assert np.max(np.abs(got - ref)) < 1e-10 * max(1.0, np.max(np.abs(ref)))
+
+
 def test_device_statevector_handle_against_oracle():
     """statevector.DeviceStatevector (here over the numpy test double): expectation values incl. qargs, linear
     combinations and signed labels, probabilities in the caller's qubit order, seeded sampling -- against the oracle's
